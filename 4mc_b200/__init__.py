@@ -1,0 +1,244 @@
+"""4mc_b200 -- host-side mirror of the reference's codec interface over lib4mcgpu.so.
+
+The product is the C-ABI library (include/fourmc.h, 4mc_b200/csrc/*): hand-written sm_100a CUDA
+for the per-4 MiB-block LZ4 compress / decompress, XXH32 and block-index path of fingltd/4mc.
+This module is the thin Python binding used by the tests and bench.py; it adds no arithmetic of
+its own and never falls back to a CPU codec -- if the library or a CUDA device is missing, calls
+raise FourMcError.
+
+Names follow the reference (java/hadoop-4mc/src/main/java/com/fing/compression/fourmc):
+  Lz4Compressor.compress_bytes_direct / Lz4Decompressor.decompress_bytes_direct / xxhash32
+      <- Lz4Compressor.java:314-321, Lz4Decompressor.java:287-290 (JNI natives)
+  FourMcCodec.compress / decompress (whole .4mc streams)
+      <- FourMcCodec.java:82-168, native/4mc.c:220 fourMCcompressFilename, :896 fourMcDecompressFileName
+The package name starts with a digit, so import it with importlib.import_module("4mc_b200").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib4mcgpu.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+BLOCKSIZE = 4 * 1024 * 1024
+OK, E_GENERIC, E_INPUT, E_OUTPUT, E_CONTENT = 0, -1, -2, -3, -4
+E_CUDA, E_ARG, E_UNSUPPORTED = -10, -11, -12
+BLOCK_OK, BLOCK_CHECKSUM, BLOCK_CORRUPT, BLOCK_TOOLARGE = 0, 1, 2, 3
+
+
+class FourMcError(RuntimeError):
+    def __init__(self, code: int, msg: str = ""):
+        super().__init__(f"fourmc error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compiles csrc/ into lib4mcgpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "fourmc.h")]
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs if os.path.isfile(s))
+    if stale:
+        subprocess.run(["make", "-C", CSRC, "-s"], check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads lib4mcgpu.so (building it first if the sources are newer and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    L = C.CDLL(LIB_PATH)
+    vp, sz, u64, u32, i32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int
+    sig = {
+        "fourmc_ctx_create": (i32, [C.POINTER(vp), i32]),
+        "fourmc_ctx_destroy": (None, [vp]),
+        "fourmc_last_error": (C.c_char_p, [vp]),
+        "fourmc_kernel_launches": (u64, [vp]),
+        "fourmc_sync": (i32, [vp, vp]),
+        "fourmc_lz4_compress_bound": (i32, [i32]),
+        "fourmc_lz4_compress": (i32, [vp, i32, vp, i32, vp, i32]),
+        "fourmc_lz4_decompress_safe": (i32, [vp, vp, i32, vp, i32]),
+        "fourmc_xxh32": (u32, [vp, vp, sz, u32, C.POINTER(i32)]),
+        "fourmc_4mc_bound": (sz, [sz]),
+        "fourmc_4mc_compress_host": (C.c_longlong, [vp, i32, vp, sz, vp, sz]),
+        "fourmc_4mc_decompress_host": (C.c_longlong, [vp, vp, sz, vp, sz]),
+        "fourmc_4mc_decoded_size_host": (C.c_longlong, [vp, sz]),
+        "fourmc_4mc_compress_device": (i32, [vp, vp, i32, vp, sz, vp, sz, vp, vp]),
+        "fourmc_4mc_compress_span_device": (i32, [vp, vp, i32, vp, sz, vp, sz, vp, vp]),
+        "fourmc_4mc_build_index_device": (i32, [vp, vp, vp, u32, vp, vp]),
+        "fourmc_4mc_decompress_device": (i32, [vp, vp, vp, sz, vp, sz, vp]),
+        "fourmc_lz4_decompress_batch_device": (i32, [vp, vp, u32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
+        "fourmc_xxh32_batch_device": (i32, [vp, vp, u32, vp, vp, vp, u32, vp]),
+        "fourmc_gen_device": (i32, [vp, vp, i32, u64, u64, u64, vp]),
+        "fourmc_gen_host": (i32, [i32, u64, u64, u64, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _buf(b):
+    """ctypes view of a bytes-like object without copying (read-only objects are copied)."""
+    if isinstance(b, (bytes, bytearray)):
+        return (C.c_char * len(b)).from_buffer_copy(b) if isinstance(b, bytes) else (C.c_char * len(b)).from_buffer(b)
+    mv = memoryview(b).cast("B")
+    return (C.c_char * len(mv)).from_buffer(mv) if not mv.readonly else (C.c_char * len(mv)).from_buffer_copy(mv)
+
+
+class Context:
+    """One fourmc_ctx: a CUDA device, a stream and grow-only workspaces (include/fourmc.h)."""
+
+    def __init__(self, device: int = -1):
+        self._h = C.c_void_p()
+        rc = lib().fourmc_ctx_create(C.byref(self._h), device)
+        if rc != OK:
+            self._h = C.c_void_p()
+            raise FourMcError(rc, "fourmc_ctx_create failed (no CUDA device?)")
+
+    def close(self):
+        if self._h:
+            lib().fourmc_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _check(self, rc: int):
+        if rc < 0:
+            raise FourMcError(rc, lib().fourmc_last_error(self._h).decode())
+        return rc
+
+    def last_error(self) -> str:
+        return lib().fourmc_last_error(self._h).decode()
+
+    def kernel_launches(self) -> int:
+        return int(lib().fourmc_kernel_launches(self._h))
+
+    def sync(self, stream=None):
+        self._check(lib().fourmc_sync(self._h, stream))
+
+    # ---- per block, host buffers (what the JNI natives and the CLI loop call) ----
+    def xxh32(self, data, seed: int = 0) -> int:
+        st = C.c_int(0)
+        b = _buf(data)
+        h = lib().fourmc_xxh32(self._h, b, len(b), seed & 0xFFFFFFFF, C.byref(st))
+        self._check(st.value)
+        return int(h)
+
+    def lz4_compress(self, data, level: int = 1, capacity: int | None = None) -> bytes | None:
+        """LZ4_compress_default semantics: None when the block does not fit in `capacity`."""
+        n = len(data)
+        cap = lib().fourmc_lz4_compress_bound(n) if capacity is None else capacity
+        out = C.create_string_buffer(max(cap, 1))
+        rc = lib().fourmc_lz4_compress(self._h, level, _buf(data), n, out, cap)
+        if rc < 0:
+            self._check(rc)
+        return None if rc == 0 else out.raw[:rc]
+
+    def lz4_decompress_safe(self, data, capacity: int):
+        """Returns (return value of LZ4_decompress_safe, decoded bytes)."""
+        out = C.create_string_buffer(max(capacity, 1))
+        rc = lib().fourmc_lz4_decompress_safe(self._h, _buf(data), len(data), out, capacity)
+        if rc in (E_CUDA, E_ARG) and self.last_error():
+            raise FourMcError(rc, self.last_error())
+        return rc, out.raw[:max(rc, 0)]
+
+    # ---- whole streams, host buffers ----
+    def compress_4mc(self, data, level: int = 1) -> bytes:
+        n = len(data)
+        cap = lib().fourmc_4mc_bound(n)
+        out = C.create_string_buffer(cap)
+        rc = lib().fourmc_4mc_compress_host(self._h, level, _buf(data), n, out, cap)
+        self._check(rc)
+        return out.raw[:rc]
+
+    def decompress_4mc(self, stream) -> bytes:
+        b = _buf(stream)
+        size = lib().fourmc_4mc_decoded_size_host(b, len(b))
+        cap = max(int(size), 0)
+        out = C.create_string_buffer(max(cap, 1))
+        rc = lib().fourmc_4mc_decompress_host(self._h, b, len(b), out, cap)
+        self._check(rc)
+        return out.raw[:rc]
+
+    def decompress_4mc_rc(self, stream) -> int:
+        """Only the status / decoded size (negative FOURMC_E_* on failure), no exception."""
+        b = _buf(stream)
+        size = lib().fourmc_4mc_decoded_size_host(b, len(b))
+        cap = max(int(size), 0)
+        out = C.create_string_buffer(max(cap, 1))
+        return int(lib().fourmc_4mc_decompress_host(self._h, b, len(b), out, cap))
+
+
+# ---- reference-shaped facades ---------------------------------------------------------------
+
+class Lz4Compressor:
+    """Mirror of com.fing.compression.fourmc.Lz4Compressor's native methods
+    (Lz4Compressor.java:314-321; native/jniCompressor.c:72-194)."""
+
+    def __init__(self, ctx: Context, level: int = 1):
+        self.ctx, self.level = ctx, level
+
+    @staticmethod
+    def compress_bound(n: int) -> int:
+        return int(lib().fourmc_lz4_compress_bound(n))
+
+    def compress_bytes_direct(self, uncompressed) -> bytes:
+        out = self.ctx.lz4_compress(uncompressed, self.level)
+        if out is None:
+            raise FourMcError(0, "LZ4_compress returned: 0")      # jniCompressor.c:95-100 InternalError
+        return out
+
+    def xxhash32(self, buf, off: int, length: int, seed: int) -> int:
+        return self.ctx.xxh32(bytes(buf[off:off + length]), seed)
+
+
+class Lz4Decompressor:
+    """Mirror of Lz4Decompressor's natives (Lz4Decompressor.java:287-290; native/jniDecompressor.c:67-118)."""
+
+    def __init__(self, ctx: Context, direct_buffer_size: int = BLOCKSIZE):
+        self.ctx, self.direct_buffer_size = ctx, direct_buffer_size
+
+    def decompress_bytes_direct(self, compressed) -> bytes:
+        rc, out = self.ctx.lz4_decompress_safe(compressed, self.direct_buffer_size)
+        if rc < 0:
+            raise FourMcError(rc, f"LZ4_decompress_safe returned: {rc}")     # jniDecompressor.c:93-97
+        return out
+
+    def xxhash32(self, buf, off: int, length: int, seed: int) -> int:
+        return self.ctx.xxh32(bytes(buf[off:off + length]), seed)
+
+
+class FourMcCodec:
+    """Whole-stream codec: FourMcCodec.java:82-168 / native/4mc.c:220,896."""
+
+    def __init__(self, ctx: Context, level: int = 1):
+        self.ctx, self.level = ctx, level
+
+    def compress(self, data) -> bytes:
+        return self.ctx.compress_4mc(data, self.level)
+
+    def decompress(self, stream) -> bytes:
+        return self.ctx.decompress_4mc(stream)
+
+
+# ---- block sharding across ranks ---------------------------------------------
+
+def shard_blocks(n_blocks: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous block range [lo, hi) of `rank`: r gets [r*ceil(n/G), (r+1)*ceil(n/G))."""
+    per = -(-n_blocks // world_size) if n_blocks else 0
+    lo = min(n_blocks, rank * per)
+    return lo, min(n_blocks, lo + per)

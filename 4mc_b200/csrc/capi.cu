@@ -1,0 +1,807 @@
+// capi.cu -- the C-ABI of lib4mcgpu.so (include/fourmc.h): contexts, workspaces, kernel launches.
+// Host code here is plumbing only; every byte of codec / checksum / index arithmetic runs in the
+// kernels of xxh32.cuh, lz4_decode.cuh, lz4_encode.cuh and container.cuh.  There is no CPU codec
+// in this library: without a CUDA device every entry point fails with FOURMC_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fourmc.h"
+#include "container.cuh"
+#include "fourmc_gen.h"
+#include "lz4_decode.cuh"
+#include "lz4_encode.cuh"
+#include "xxh32.cuh"
+
+using namespace fm;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct EncWs {
+    DevBuf scratch, meta, plan, lens, off, misc;   // misc: [0] work counter (u32), [8] span (u64), [16] total (u64)
+};
+
+struct DecWs {
+    DevBuf desc, xxh, status, tokmap, chunkop, result, info, tables, outsize, final_;
+};
+
+}  // namespace
+
+struct fourmc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;       // default stream of the context
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::string err;
+    uint64_t launches = 0;
+    EncWs enc[2];
+    DecWs dec[2];
+    DevBuf stage_in[2], stage_out[2];    // device staging for the host-pointer entry points
+    void *pinned = nullptr;              // small pinned scratch for scalars
+    size_t pinned_cap = 0;
+    bool region_attr_set = false;
+};
+
+namespace {
+
+int fail(fourmc_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) return fail(ctx, FOURMC_E_CUDA, #call, e__);          \
+    } while (0)
+
+#define CKL(what)                                                                     \
+    do {                                                                              \
+        ctx->launches++;                                                              \
+        cudaError_t e__ = cudaGetLastError();                                         \
+        if (e__ != cudaSuccess) return fail(ctx, FOURMC_E_CUDA, what, e__);           \
+    } while (0)
+
+int ensure(fourmc_ctx *ctx, DevBuf &b, size_t need)
+{
+    if (b.cap >= need && b.p) return FOURMC_OK;
+    if (b.p) { CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t cap = (need + 255) & ~(size_t)255;
+    if (cap < 256) cap = 256;
+    CK(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return FOURMC_OK;
+}
+
+void release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+}
+
+inline cudaStream_t pick(fourmc_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+inline uint32_t blocks_of(size_t n) { return (uint32_t)((n + FOURMC_BLOCKSIZE - 1) / FOURMC_BLOCKSIZE); }
+
+int slice_blocks()
+{
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("FOURMC_SLICE_BLOCKS");
+        v = e ? atoi(e) : 256;
+        if (v < 1) v = 1;
+        if (v > 4096) v = 4096;
+    }
+    return v;
+}
+
+int level_min_match(int level)
+{
+    // level 1 (Fast): minimum match 5 gives fewer, longer sequences at the same ratio on text
+    // (DESIGN.md); the other levels currently share the kernel.
+    const char *e = getenv("FOURMC_MIN_MATCH");
+    if (e) { int v = atoi(e); if (v >= 4 && v <= 16) return v; }
+    (void)level;
+    return 5;
+}
+
+// ---- encode --------------------------------------------------------------------------------
+
+// d_in[0..n) -> block records back to back at d_span (block b at d_span + off[b], off[0] = base).
+// raw_limit >= 0 selects the bare-block mode of the per-block API (single block, no header use).
+int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8_t *d_in, size_t n,
+             uint8_t *d_out_base, uint64_t base, uint32_t *d_block_lens_out, int64_t raw_limit)
+{
+    const uint32_t nb = blocks_of(n);
+    if (nb == 0) {
+        int r;
+        if ((r = ensure(ctx, ws.misc, 64))) return r;
+        CK(cudaMemsetAsync(ws.misc.p, 0, 64, st));
+        return FOURMC_OK;
+    }
+    const uint32_t nreg = nb * ENC_REGIONS_PER_BLOCK;
+    int r;
+    if ((r = ensure(ctx, ws.scratch, (size_t)nreg * ENC_SLOT))) return r;
+    if ((r = ensure(ctx, ws.meta, (size_t)nreg * sizeof(RegionMeta)))) return r;
+    if ((r = ensure(ctx, ws.plan, (size_t)nb * sizeof(BlockPlan)))) return r;
+    if ((r = ensure(ctx, ws.lens, (size_t)nb * 4))) return r;
+    if ((r = ensure(ctx, ws.off, (size_t)nb * 8))) return r;
+    if ((r = ensure(ctx, ws.misc, 64))) return r;
+    if (!ctx->region_attr_set) {
+        CK(cudaFuncSetAttribute(lz4_region_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        ctx->region_attr_set = true;
+    }
+    CK(cudaMemsetAsync(ws.misc.p, 0, 64, st));
+    EncParams P;
+    P.in = d_in; P.n = n; P.n_regions = nreg;
+    P.scratch = (uint8_t *)ws.scratch.p; P.meta = (RegionMeta *)ws.meta.p;
+    P.work_counter = (uint32_t *)ws.misc.p;
+    P.min_match = level_min_match(level);
+    const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
+    lz4_region_kernel<<<grid, ENC_THREADS, ENC_SMEM, st>>>(P);
+    CKL("lz4_region_kernel");
+    uint32_t *lens = d_block_lens_out ? d_block_lens_out : (uint32_t *)ws.lens.p;
+    lz4_block_size_kernel<<<(nb + 127) / 128, 128, 0, st>>>((const RegionMeta *)ws.meta.p, nb, n,
+                                                           (BlockPlan *)ws.plan.p, lens, raw_limit);
+    CKL("lz4_block_size_kernel");
+    scan_lens_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, base, (uint64_t *)ws.off.p,
+                                                 (uint64_t *)((uint8_t *)ws.misc.p + 8));
+    CKL("scan_lens_kernel");
+    lz4_block_write_kernel<<<nb, ENC_WRITE_THREADS, 0, st>>>(d_in, (const uint8_t *)ws.scratch.p,
+                                                             (const RegionMeta *)ws.meta.p, (const BlockPlan *)ws.plan.p,
+                                                             (const uint64_t *)ws.off.p, d_out_base, raw_limit >= 0 ? 1 : 0);
+    CKL("lz4_block_write_kernel");
+    return FOURMC_OK;
+}
+
+// ---- decode --------------------------------------------------------------------------------
+
+// Runs verify + D1 + D0 + D2 + finalize over n_blocks descriptors already in ws.desc / ws.xxh /
+// ws.status.  max_chunks bounds the chunk indices used by the descriptors.
+int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t max_chunks, int check_xxh,
+               int32_t *d_out_size, const IndexInfo *d_info, long long *d_result)
+{
+    int r;
+    if ((r = ensure(ctx, ws.tokmap, (max_chunks + 1) * LZ4_CHUNK_WORDS * 4))) return r;
+    if ((r = ensure(ctx, ws.chunkop, (max_chunks + 1) * 4))) return r;
+    if ((r = ensure(ctx, ws.result, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
+    if (nb) {
+        CK(cudaMemsetAsync(ws.tokmap.p, 0, (max_chunks + 1) * LZ4_CHUNK_WORDS * 4, st));
+        const BlockDesc *desc = (const BlockDesc *)ws.desc.p;
+        uint8_t *status = (uint8_t *)ws.status.p;
+        if (check_xxh) {
+            xxh_verify_kernel<<<(nb + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, st>>>(
+                desc, (const uint32_t *)ws.xxh.p, nb, status);
+            CKL("xxh_verify_kernel");
+        }
+        lz4_parse_kernel<<<(nb + 31) / 32, 32, 0, st>>>(desc, nb, (uint32_t *)ws.tokmap.p, (uint32_t *)ws.chunkop.p,
+                                                       (int32_t *)ws.result.p);
+        CKL("lz4_parse_kernel");
+        for (uint32_t b0 = 0; b0 < nb; b0 += 32768) {
+            const uint32_t cnt = std::min<uint32_t>(32768, nb - b0);
+            lz4_stored_kernel<<<dim3(32, cnt), 256, 0, st>>>(desc + b0, cnt);
+            CKL("lz4_stored_kernel");
+        }
+        lz4_copy_kernel<<<nb, LZ4_COPY_WARPS * 32, 0, st>>>(desc, (const uint32_t *)ws.tokmap.p,
+                                                            (const uint32_t *)ws.chunkop.p, (const int32_t *)ws.result.p);
+        CKL("lz4_copy_kernel");
+    }
+    finalize_kernel<<<1, SCAN_THREADS, 0, st>>>((const BlockDesc *)ws.desc.p, (const int32_t *)ws.result.p, nb,
+                                                (uint8_t *)ws.status.p, d_out_size, d_info, d_result);
+    CKL("finalize_kernel");
+    return FOURMC_OK;
+}
+
+// Builds BlockDesc[] from user tables (all device arrays).  One CTA.
+__global__ void __launch_bounds__(SCAN_THREADS)
+build_desc_kernel(uint32_t nb, const uint8_t *src, const uint64_t *src_off, const uint32_t *csize,
+                  const uint32_t *usize, uint8_t *dst, const uint64_t *dst_off, BlockDesc *desc, uint8_t *status)
+{
+    __shared__ unsigned long long tmp[32];
+    unsigned long long carry = 0;
+    for (uint32_t i0 = 0; i0 < nb; i0 += SCAN_THREADS) {
+        const uint32_t i = i0 + threadIdx.x;
+        const bool live = i < nb;
+        const uint32_t c = live ? csize[i] : 0, u = live ? usize[i] : 0;
+        const bool toolarge = c > FOURMC_BLOCKSIZE || (c != u && u > FOURMC_BLOCKSIZE);
+        const uint32_t nch = (live && !toolarge && c != u) ? (c + LZ4_CHUNK - 1) / LZ4_CHUNK : 0;
+        unsigned long long total;
+        const unsigned long long incl = cta_incl_scan_u64(nch, tmp, &total);
+        if (live) {
+            BlockDesc d;
+            d.src = src + src_off[i]; d.dst = dst + dst_off[i];
+            d.csize = c; d.usize = u; d.chunk_base = (uint32_t)(carry + incl - nch); d.stored = (c == u) ? 1u : 0u;
+            uint8_t s = FOURMC_BLOCK_OK;
+            if (toolarge) { s = FOURMC_BLOCK_TOOLARGE; d.csize = 0; d.usize = 0; d.stored = 1; }
+            desc[i] = d; status[i] = s;
+        }
+        carry += total;
+    }
+}
+
+__global__ void gen_kernel(int kind, uint64_t seed, uint64_t first_page, uint64_t n_pages, uint8_t *out)
+{
+    // one warp per CTA: each lane builds a page in shared memory (padded rows -> distinct banks),
+    // then the warp streams the 32 pages out with 16-byte stores.
+    extern __shared__ __align__(16) uint8_t pages[];
+    constexpr int ROW = FMG_PAGE + 16;
+    const uint64_t p0 = (uint64_t)blockIdx.x * 32;
+    const uint64_t mine = p0 + threadIdx.x;
+    (void)kind;
+    if (mine < n_pages) fmg_logtext_page(seed, first_page + mine, pages + (size_t)threadIdx.x * ROW);
+    __syncwarp();
+    for (int r = 0; r < 32 && p0 + r < n_pages; r++) {
+        const uint4 *s = (const uint4 *)(pages + (size_t)r * ROW);
+        uint4 *d = (uint4 *)(out + (p0 + r) * FMG_PAGE);
+        for (int i = threadIdx.x; i < (int)(FMG_PAGE / 16); i += 32) d[i] = s[i];
+    }
+}
+
+int pinned_scratch(fourmc_ctx *ctx, size_t need)
+{
+    if (ctx->pinned_cap >= need) return FOURMC_OK;
+    if (ctx->pinned) { cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_cap = 0; }
+    CK(cudaMallocHost(&ctx->pinned, need));
+    ctx->pinned_cap = need;
+    return FOURMC_OK;
+}
+
+inline uint32_t be32(const uint8_t *p)
+{
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+
+extern "C" {
+
+int fourmc_ctx_create(fourmc_ctx **out, int device)
+{
+    if (!out) return FOURMC_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FOURMC_E_CUDA;
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) return FOURMC_E_CUDA; }
+    if (device >= ndev) return FOURMC_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return FOURMC_E_CUDA;
+    fourmc_ctx *ctx = new fourmc_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return FOURMC_E_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FOURMC_E_CUDA; }
+    for (int i = 0; i < 2; i++) {
+        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            fourmc_ctx_destroy(ctx);
+            return FOURMC_E_CUDA;
+        }
+    }
+    *out = ctx;
+    return FOURMC_OK;
+}
+
+void fourmc_ctx_destroy(fourmc_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) {
+        EncWs &e = ctx->enc[i];
+        release(e.scratch); release(e.meta); release(e.plan); release(e.lens); release(e.off); release(e.misc);
+        DecWs &d = ctx->dec[i];
+        release(d.desc); release(d.xxh); release(d.status); release(d.tokmap); release(d.chunkop);
+        release(d.result); release(d.info); release(d.tables); release(d.outsize); release(d.final_);
+        release(ctx->stage_in[i]); release(ctx->stage_out[i]);
+        if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    }
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *fourmc_last_error(const fourmc_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+uint64_t fourmc_kernel_launches(const fourmc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fourmc_sync(fourmc_ctx *ctx, void *stream)
+{
+    if (!ctx) return FOURMC_E_ARG;
+    CK(cudaStreamSynchronize(pick(ctx, stream)));
+    return FOURMC_OK;
+}
+
+int fourmc_lz4_compress_bound(int n)
+{
+    return ((unsigned)n > 0x7E000000u) ? 0 : n + n / 255 + 16;      // native/lz4/lz4.h:211-212
+}
+
+size_t fourmc_4mc_bound(size_t n)
+{
+    const size_t nb = (n + FOURMC_BLOCKSIZE - 1) / FOURMC_BLOCKSIZE;
+    return 12 + n + 12 * nb + 12 + 20 + 4 * nb;
+}
+
+// ---- device-resident ---------------------------------------------------------------------------
+
+int fourmc_4mc_compress_span_device(fourmc_ctx *ctx, void *stream, int level, const void *d_in, size_t n,
+                                    void *d_span, size_t span_capacity, uint64_t *d_span_size,
+                                    uint32_t *d_block_lens)
+{
+    if (!ctx || (!d_in && n) || !d_span) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t nb = blocks_of(n);
+    if (span_capacity < n + 12ull * nb) return fail(ctx, FOURMC_E_OUTPUT, "span capacity below the all-stored bound");
+    cudaStream_t st = pick(ctx, stream);
+    EncWs &ws = ctx->enc[0];
+    int r = enc_span(ctx, st, ws, level, (const uint8_t *)d_in, n, (uint8_t *)d_span, 0, d_block_lens, -1);
+    if (r) return r;
+    if (d_span_size)
+        CK(cudaMemcpyAsync(d_span_size, (uint8_t *)ws.misc.p + 8, 8, cudaMemcpyDeviceToDevice, st));
+    return FOURMC_OK;
+}
+
+int fourmc_4mc_build_index_device(fourmc_ctx *ctx, void *stream, const uint32_t *d_block_lens, uint32_t n_blocks,
+                                  void *d_header, void *d_tail)
+{
+    if (!ctx || !d_tail || (n_blocks && !d_block_lens)) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(d_block_lens, n_blocks, 12, FOURMC_MAGIC_4MC, (uint8_t *)d_header,
+                                                   (uint8_t *)d_tail, nullptr, nullptr);
+    CKL("write_index_kernel");
+    return FOURMC_OK;
+}
+
+int fourmc_4mc_compress_device(fourmc_ctx *ctx, void *stream, int level, const void *d_in, size_t n, void *d_out,
+                               size_t out_capacity, uint64_t *d_out_size, uint32_t *d_block_lens)
+{
+    if (!ctx || (!d_in && n) || !d_out) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (out_capacity < fourmc_4mc_bound(n)) return fail(ctx, FOURMC_E_OUTPUT, "output capacity below fourmc_4mc_bound(n)");
+    cudaStream_t st = pick(ctx, stream);
+    EncWs &ws = ctx->enc[0];
+    const uint32_t nb = blocks_of(n);
+    int r;
+    if ((r = ensure(ctx, ws.lens, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
+    uint32_t *lens = d_block_lens ? d_block_lens : (uint32_t *)ws.lens.p;
+    // block b's header lands at d_out + 12 + sum of earlier record lengths
+    if ((r = enc_span(ctx, st, ws, level, (const uint8_t *)d_in, n, (uint8_t *)d_out, 12, lens, -1))) return r;
+    write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, 12, FOURMC_MAGIC_4MC, (uint8_t *)d_out, (uint8_t *)d_out + 12,
+                                                   (const uint64_t *)((uint8_t *)ws.misc.p + 8),
+                                                   (uint64_t *)((uint8_t *)ws.misc.p + 16));
+    CKL("write_index_kernel");
+    if (d_out_size)
+        CK(cudaMemcpyAsync(d_out_size, (uint8_t *)ws.misc.p + 16, 8, cudaMemcpyDeviceToDevice, st));
+    return FOURMC_OK;
+}
+
+int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n, void *d_out,
+                                 size_t out_capacity, long long *d_result)
+{
+    if (!ctx || !d_in || !d_result) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    DecWs &ws = ctx->dec[0];
+    int r;
+    if ((r = pinned_scratch(ctx, 4096))) return r;
+    long long *h = (long long *)ctx->pinned;
+    if (n < 44) {
+        h[0] = FOURMC_E_INPUT; h[1] = -1;
+        CK(cudaMemcpyAsync(d_result, h, 16, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        return FOURMC_OK;
+    }
+    // the only host round trip: the footer size field tells how many blocks to launch for
+    uint8_t *ft = (uint8_t *)ctx->pinned + 64;
+    CK(cudaMemcpyAsync(ft, (const uint8_t *)d_in + n - 12, 12, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t fsize = be32(ft);
+    if (fsize < 20 || (uint64_t)fsize > n - 24 || ((fsize - 20) & 3)) {
+        h[0] = FOURMC_E_CONTENT; h[1] = -1;
+        CK(cudaMemcpyAsync(d_result, h, 16, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        return FOURMC_OK;
+    }
+    const uint32_t nb = (fsize - 20) / 4;
+    if ((r = ensure(ctx, ws.desc, (size_t)std::max<uint32_t>(nb, 1) * sizeof(BlockDesc)))) return r;
+    if ((r = ensure(ctx, ws.xxh, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
+    if ((r = ensure(ctx, ws.status, (size_t)std::max<uint32_t>(nb, 1)))) return r;
+    if ((r = ensure(ctx, ws.info, sizeof(IndexInfo)))) return r;
+    // a rejected index leaves the descriptors untouched: zero them first so that the kernels
+    // queued behind (no host round trip to skip them) see empty blocks
+    CK(cudaMemsetAsync(ws.desc.p, 0, (size_t)std::max<uint32_t>(nb, 1) * sizeof(BlockDesc), st));
+    CK(cudaMemsetAsync(ws.status.p, 0, (size_t)std::max<uint32_t>(nb, 1), st));
+    CK(cudaMemsetAsync(ws.xxh.p, 0, (size_t)std::max<uint32_t>(nb, 1) * 4, st));
+    read_index_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint8_t *)d_in, n, nb, (uint8_t *)d_out, out_capacity,
+                                                  (BlockDesc *)ws.desc.p, (uint32_t *)ws.xxh.p, (uint8_t *)ws.status.p,
+                                                  (IndexInfo *)ws.info.p);
+    CKL("read_index_kernel");
+    const size_t max_chunks = n / LZ4_CHUNK + nb + 1;
+    return dec_blocks(ctx, st, ws, nb, max_chunks, 1, nullptr, (const IndexInfo *)ws.info.p, d_result);
+}
+
+int fourmc_lz4_decompress_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_blocks, const void *d_src,
+                                       const uint64_t *d_src_off, const uint32_t *d_csize, const uint32_t *d_usize,
+                                       const uint32_t *d_xxh, int check_xxh, void *d_dst, const uint64_t *d_dst_off,
+                                       int32_t *d_out_size, uint8_t *d_status)
+{
+    if (!ctx || !d_src || !d_src_off || !d_csize || !d_usize || !d_dst_off) return FOURMC_E_ARG;
+    if (check_xxh && !d_xxh) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    DecWs &ws = ctx->dec[0];
+    int r;
+    const uint32_t nb = n_blocks;
+    if ((r = ensure(ctx, ws.desc, (size_t)std::max<uint32_t>(nb, 1) * sizeof(BlockDesc)))) return r;
+    if ((r = ensure(ctx, ws.xxh, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
+    if ((r = ensure(ctx, ws.status, (size_t)std::max<uint32_t>(nb, 1)))) return r;
+    if (nb == 0) return FOURMC_OK;
+    build_desc_kernel<<<1, SCAN_THREADS, 0, st>>>(nb, (const uint8_t *)d_src, d_src_off, d_csize, d_usize,
+                                                  (uint8_t *)d_dst, d_dst_off, (BlockDesc *)ws.desc.p, (uint8_t *)ws.status.p);
+    CKL("build_desc_kernel");
+    if (check_xxh) CK(cudaMemcpyAsync(ws.xxh.p, d_xxh, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
+    // every compressed block has csize <= 4 MiB: bound the chunk count by that
+    const size_t max_chunks = (size_t)nb * (FOURMC_BLOCKSIZE / LZ4_CHUNK + 1);
+    if ((r = dec_blocks(ctx, st, ws, nb, max_chunks, check_xxh, d_out_size, nullptr, nullptr))) return r;
+    if (d_status) CK(cudaMemcpyAsync(d_status, ws.status.p, nb, cudaMemcpyDeviceToDevice, st));
+    return FOURMC_OK;
+}
+
+int fourmc_xxh32_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_items, const void *d_base,
+                              const uint64_t *d_off, const uint32_t *d_len, uint32_t seed, uint32_t *d_out)
+{
+    if (!ctx || !d_off || !d_len || !d_out) return FOURMC_E_ARG;
+    if (n_items == 0) return FOURMC_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    xxh_batch_kernel<<<(n_items + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, st>>>(
+        (const uint8_t *)d_base, d_off, d_len, n_items, seed, d_out);
+    CKL("xxh_batch_kernel");
+    return FOURMC_OK;
+}
+
+int fourmc_gen_device(fourmc_ctx *ctx, void *stream, int kind, uint64_t seed, uint64_t first_page,
+                      uint64_t n_pages, void *d_out)
+{
+    if (!ctx || !d_out) return FOURMC_E_ARG;
+    if (kind != 0) return fail(ctx, FOURMC_E_UNSUPPORTED, "only kind 0 (log-text) is implemented");
+    if (n_pages == 0) return FOURMC_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    const size_t smem = 32 * (FMG_PAGE + 16);
+    static bool attr = false;
+    if (!attr) { CK(cudaFuncSetAttribute(gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    const uint64_t max_grid = 1u << 30;
+    for (uint64_t p0 = 0; p0 < n_pages; p0 += max_grid * 32) {
+        const uint64_t cnt = std::min<uint64_t>(n_pages - p0, max_grid * 32);
+        gen_kernel<<<(unsigned)((cnt + 31) / 32), 32, smem, st>>>(kind, seed, first_page + p0, cnt,
+                                                                  (uint8_t *)d_out + p0 * FMG_PAGE);
+        CKL("gen_kernel");
+    }
+    return FOURMC_OK;
+}
+
+int fourmc_gen_host(int kind, uint64_t seed, uint64_t first_page, uint64_t n_pages, void *out)
+{
+    if (kind != 0 || !out) return FOURMC_E_ARG;
+    for (uint64_t p = 0; p < n_pages; p++) fmg_logtext_page(seed, first_page + p, (uint8_t *)out + p * FMG_PAGE);
+    return FOURMC_OK;
+}
+
+// ---- per-block, host pointers ------------------------------------------------------------------
+
+uint32_t fourmc_xxh32(fourmc_ctx *ctx, const void *data, size_t len, uint32_t seed, int *status)
+{
+    auto done = [&](int s, uint32_t v) { if (status) *status = s; return v; };
+    if (!ctx || (!data && len) || len > 0xffffffffull) return done(FOURMC_E_ARG, 0);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return done(fail(ctx, FOURMC_E_CUDA, "cudaSetDevice"), 0);
+    cudaStream_t st = ctx->stream;
+    if (ensure(ctx, ctx->stage_in[0], len + 64) || pinned_scratch(ctx, 4096)) return done(FOURMC_E_CUDA, 0);
+    // table: off (u64) | len (u32) | out (u32) in one small device buffer
+    if (ensure(ctx, ctx->dec[0].tables, 64)) return done(FOURMC_E_CUDA, 0);
+    uint8_t *tb = (uint8_t *)ctx->dec[0].tables.p;
+    uint64_t *h = (uint64_t *)ctx->pinned;
+    h[0] = 0; ((uint32_t *)h)[2] = (uint32_t)len; ((uint32_t *)h)[3] = 0;
+    cudaError_t e;
+    if (len && (e = cudaMemcpyAsync(ctx->stage_in[0].p, data, len, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return done(fail(ctx, FOURMC_E_CUDA, "H2D", e), 0);
+    if ((e = cudaMemcpyAsync(tb, h, 16, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+        return done(fail(ctx, FOURMC_E_CUDA, "H2D", e), 0);
+    int r = fourmc_xxh32_batch_device(ctx, st, 1, ctx->stage_in[0].p, (const uint64_t *)tb, (const uint32_t *)(tb + 8),
+                                      seed, (uint32_t *)(tb + 12));
+    if (r) return done(r, 0);
+    if ((e = cudaMemcpyAsync((uint8_t *)ctx->pinned + 32, tb + 12, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(st)) != cudaSuccess)
+        return done(fail(ctx, FOURMC_E_CUDA, "D2H", e), 0);
+    return done(FOURMC_OK, *(uint32_t *)((uint8_t *)ctx->pinned + 32));
+}
+
+int fourmc_lz4_compress(fourmc_ctx *ctx, int level, const void *src, int src_size, void *dst, int dst_capacity)
+{
+    if (!ctx || !src || !dst || src_size < 0 || dst_capacity < 0) return FOURMC_E_ARG;
+    if (src_size > FOURMC_BLOCKSIZE) return fail(ctx, FOURMC_E_ARG, "per-block calls take at most 4 MiB (native/4mc.c:116)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int r;
+    const size_t bound = (size_t)fourmc_lz4_compress_bound(src_size) + 64;
+    if ((r = ensure(ctx, ctx->stage_in[0], (size_t)src_size + 64))) return r;
+    if ((r = ensure(ctx, ctx->stage_out[0], bound + 64))) return r;
+    if ((r = pinned_scratch(ctx, 4096))) return r;
+    if (src_size == 0) {
+        // LZ4_compress_default(src, dst, 0, cap): one token, no literals (native/lz4/lz4.c:1266-1293)
+        if (dst_capacity < 1) return 0;
+        ((uint8_t *)dst)[0] = 0;
+        return 1;
+    }
+    CK(cudaMemcpyAsync(ctx->stage_in[0].p, src, (size_t)src_size, cudaMemcpyHostToDevice, st));
+    EncWs &ws = ctx->enc[0];
+    // the block record goes to stage_out + 4 so that the payload (record + 12) is 16-byte aligned
+    uint8_t *rec = (uint8_t *)ctx->stage_out[0].p + 4;
+    if ((r = enc_span(ctx, st, ws, level, (const uint8_t *)ctx->stage_in[0].p, (size_t)src_size, rec, 0,
+                      nullptr, (int64_t)std::min<size_t>((size_t)dst_capacity, bound))))
+        return r;
+    uint32_t *h = (uint32_t *)ctx->pinned;
+    CK(cudaMemcpyAsync(h, ws.plan.p, sizeof(BlockPlan), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const BlockPlan *p = (const BlockPlan *)h;
+    if (p->stored) return 0;                                      // does not fit in dst_capacity
+    const uint32_t c = p->payload;
+    CK(cudaMemcpyAsync(dst, rec + 12, c, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return (int)c;
+}
+
+int fourmc_lz4_decompress_safe(fourmc_ctx *ctx, const void *src, int compressed_size, void *dst, int dst_capacity)
+{
+    if (!ctx) return FOURMC_E_ARG;
+    if (!src || dst_capacity < 0) return -1;                                        // lz4.c:1951
+    if (dst_capacity == 0) return (compressed_size == 1 && ((const uint8_t *)src)[0] == 0) ? 0 : -1;   // :1977-1981
+    if (compressed_size <= 0) return -1;                                            // :1982
+    if (!dst) return FOURMC_E_ARG;
+    if (compressed_size > fourmc_lz4_compress_bound(FOURMC_BLOCKSIZE) || dst_capacity > (1 << 30))
+        return fail(ctx, FOURMC_E_ARG, "per-block calls take at most one 4 MiB block");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DecWs &ws = ctx->dec[0];
+    int r;
+    if ((r = ensure(ctx, ctx->stage_in[0], (size_t)compressed_size + 64))) return r;
+    if ((r = ensure(ctx, ctx->stage_out[0], (size_t)dst_capacity + 64))) return r;
+    if ((r = ensure(ctx, ws.desc, sizeof(BlockDesc)))) return r;
+    if ((r = ensure(ctx, ws.status, 16))) return r;
+    if ((r = pinned_scratch(ctx, 4096))) return r;
+    CK(cudaMemcpyAsync(ctx->stage_in[0].p, src, (size_t)compressed_size, cudaMemcpyHostToDevice, st));
+    BlockDesc *hd = (BlockDesc *)ctx->pinned;
+    hd->src = (const uint8_t *)ctx->stage_in[0].p; hd->dst = (uint8_t *)ctx->stage_out[0].p;
+    hd->csize = (uint32_t)compressed_size; hd->usize = (uint32_t)dst_capacity; hd->chunk_base = 0; hd->stored = 0;
+    CK(cudaMemcpyAsync(ws.desc.p, hd, sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ws.status.p, 0, 16, st));
+    const size_t max_chunks = (size_t)compressed_size / LZ4_CHUNK + 2;
+    if ((r = ensure(ctx, ws.outsize, 16))) return r;
+    if ((r = dec_blocks(ctx, st, ws, 1, max_chunks, 0, (int32_t *)ws.outsize.p, nullptr, nullptr))) return r;
+    int32_t *hr = (int32_t *)((uint8_t *)ctx->pinned + 256);
+    CK(cudaMemcpyAsync(hr, ws.outsize.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int32_t res = *hr;
+    if (res > 0) {
+        CK(cudaMemcpyAsync(dst, ctx->stage_out[0].p, (size_t)res, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return res;
+}
+
+// ---- whole stream, host buffers ----------------------------------------------------------------
+
+long long fourmc_4mc_compress_host(fourmc_ctx *ctx, int level, const void *in, size_t n, void *out, size_t out_capacity)
+{
+    if (!ctx || (!in && n) || !out) return FOURMC_E_ARG;
+    if (out_capacity < fourmc_4mc_bound(n)) return fail(ctx, FOURMC_E_OUTPUT, "output capacity below fourmc_4mc_bound(n)");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t nb = blocks_of(n);
+    const size_t sl_blocks = (size_t)slice_blocks();
+    const size_t sl_bytes = sl_blocks * FOURMC_BLOCKSIZE;
+    const size_t nslices = (n + sl_bytes - 1) / sl_bytes;
+    int r;
+    if ((r = pinned_scratch(ctx, 4096))) return r;
+    // all block lengths of the file, on the device, for the footer
+    DevBuf &all_lens = ctx->dec[1].tables;
+    if ((r = ensure(ctx, all_lens, (size_t)std::max<uint32_t>(nb, 1) * 4 + 64 + 32 + 4 * (size_t)nb))) return r;
+    uint64_t *h_span = (uint64_t *)ctx->pinned;          // [0], [1]: span size of the slice in flight per buffer
+    size_t pos = 12;                                     // output position of the next span
+    const size_t cap_in = std::min(n, sl_bytes) + 64, cap_out = std::min(n, sl_bytes) + 12 * sl_blocks + 64;
+    for (int i = 0; i < 2 && (size_t)i < std::max<size_t>(nslices, 1); i++) {
+        if ((r = ensure(ctx, ctx->stage_in[i], cap_in))) return r;
+        if ((r = ensure(ctx, ctx->stage_out[i], cap_out))) return r;
+    }
+    // software pipeline: slice s is uploaded and compressed on aux[s&1] while slice s-1 downloads
+    for (size_t s = 0; s <= nslices; s++) {
+        if (s < nslices) {
+            const int b = (int)(s & 1);
+            cudaStream_t st = ctx->aux[b];
+            const size_t off = s * sl_bytes, len = std::min(sl_bytes, n - off);
+            CK(cudaMemcpyAsync(ctx->stage_in[b].p, (const uint8_t *)in + off, len, cudaMemcpyHostToDevice, st));
+            if ((r = enc_span(ctx, st, ctx->enc[b], level, (const uint8_t *)ctx->stage_in[b].p, len,
+                              (uint8_t *)ctx->stage_out[b].p, 0, (uint32_t *)all_lens.p + s * sl_blocks, -1)))
+                return r;
+            CK(cudaMemcpyAsync(&h_span[b], (uint8_t *)ctx->enc[b].misc.p + 8, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(ctx->ev[b], st));
+        }
+        if (s > 0) {
+            const int b = (int)((s - 1) & 1);
+            cudaStream_t st = ctx->aux[b];
+            CK(cudaEventSynchronize(ctx->ev[b]));
+            const size_t span = (size_t)h_span[b];
+            CK(cudaMemcpyAsync((uint8_t *)out + pos, ctx->stage_out[b].p, span, cudaMemcpyDeviceToHost, st));
+            pos += span;
+            // the buffer pair is reused by slice s+1: its upload is queued on the same stream, in order
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->aux[0]));
+    CK(cudaStreamSynchronize(ctx->aux[1]));
+    // header + EOS + footer, assembled on the device from the gathered lengths
+    cudaStream_t st = ctx->stream;
+    uint8_t *d_hdr = (uint8_t *)all_lens.p + (((size_t)std::max<uint32_t>(nb, 1) * 4 + 15) & ~(size_t)15);
+    uint8_t *d_tail = d_hdr + 16;
+    if ((r = fourmc_4mc_build_index_device(ctx, st, (const uint32_t *)all_lens.p, nb, d_hdr, d_tail))) return r;
+    const size_t tail_bytes = 12 + 20 + 4 * (size_t)nb;
+    CK(cudaMemcpyAsync(out, d_hdr, 12, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((uint8_t *)out + pos, d_tail, tail_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return (long long)(pos + tail_bytes);
+}
+
+namespace {
+struct HostBlock { uint64_t src_off, dst_off; uint32_t csize, usize, xxh; };
+}
+
+// Walks one or more concatenated streams exactly like decodeFourMC (native/4mc.c:560-707) minus the
+// payload work.  Returns FOURMC_OK or the container error the serial reader would hit first,
+// together with the blocks seen before it (they are decoded first, so that an earlier block error
+// takes precedence).  *walk_err_at = number of blocks preceding the container error.
+static int walk_streams(const uint8_t *in, size_t n, std::vector<HostBlock> &blocks, uint64_t *total_out)
+{
+    size_t pos = 0;
+    uint64_t opos = 0;
+    while (pos < n) {
+        if (n - pos < 4) return FOURMC_E_CONTENT;                                  // :868
+        if (be32(in + pos) != FOURMC_MAGIC_4MC) return FOURMC_E_CONTENT;           // :873
+        if (n - pos < 12) return FOURMC_E_CONTENT;                                 // :577
+        if (be32(in + pos + 4) != FOURMC_VERSION) return FOURMC_E_CONTENT;         // :583
+        // header checksum (:584): XXH32 of "4MC\0" + version 1 is the constant 0xA4B73443
+        if (be32(in + pos + 8) != 0xA4B73443u) return FOURMC_E_CONTENT;
+        pos += 12;
+        for (;;) {
+            if (n - pos < 12) { *total_out = opos; return FOURMC_E_INPUT; }       // :610
+            const uint32_t u = be32(in + pos), c = be32(in + pos + 4), ck = be32(in + pos + 8);
+            pos += 12;
+            if (u == 0 && c == 0 && ck == 0) break;                                // :616
+            if (c > FOURMC_BLOCKSIZE) { *total_out = opos; return FOURMC_E_CONTENT; }   // :618
+            if (n - pos < c) { *total_out = opos; return FOURMC_E_INPUT; }         // :632
+            if (u != c && u > FOURMC_BLOCKSIZE) { *total_out = opos; return FOURMC_E_CONTENT; }   // :651
+            blocks.push_back(HostBlock{(uint64_t)pos, opos, c, u, ck});
+            opos += u;
+            pos += c;
+        }
+        *total_out = opos;
+        // footer :670-688 -- its checksum is verified on the device with the payloads
+        if (n - pos < 4) return FOURMC_E_GENERIC;                                  // :672
+        const uint32_t fsize = be32(in + pos);
+        if (fsize < 4 || n - pos < fsize) return FOURMC_E_INPUT;                   // :680
+        if (fsize < 8) return FOURMC_E_CONTENT;
+        // represented as a pseudo block: csize = fsize - 4, usize = 0xffffffff marks "hash only"
+        blocks.push_back(HostBlock{(uint64_t)pos, opos, fsize - 4, 0xffffffffu, be32(in + pos + fsize - 4)});
+        if (be32(in + pos + 4) != 1) return FOURMC_E_CONTENT;                      // :687 (after the checksum, checked below)
+        pos += fsize;
+    }
+    return FOURMC_OK;
+}
+
+long long fourmc_4mc_decoded_size_host(const void *in, size_t n)
+{
+    if (!in && n) return FOURMC_E_ARG;
+    std::vector<HostBlock> blocks;
+    uint64_t total = 0;
+    const int e = walk_streams((const uint8_t *)in, n, blocks, &total);
+    return e ? e : (long long)total;
+}
+
+long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, void *out, size_t out_capacity)
+{
+    if (!ctx || (!in && n) || (!out && out_capacity)) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint8_t *src = (const uint8_t *)in;
+    std::vector<HostBlock> blocks;
+    uint64_t total = 0;
+    const int walk_err = walk_streams(src, n, blocks, &total);
+    if (total > out_capacity) return fail(ctx, FOURMC_E_OUTPUT, "destination too small");
+    // slices of consecutive blocks; footers travel as hash-only items
+    const size_t sl_blocks = (size_t)slice_blocks();
+    int r;
+    if ((r = pinned_scratch(ctx, 4096))) return r;
+    std::vector<uint8_t> status(blocks.size(), 0);
+    std::vector<uint32_t> hashes(blocks.size(), 0);
+    struct Slice { size_t b0, b1; uint64_t s0, s1, d0, d1; };
+    std::vector<Slice> slices;
+    for (size_t b0 = 0; b0 < blocks.size(); b0 += sl_blocks) {
+        const size_t b1 = std::min(blocks.size(), b0 + sl_blocks);
+        Slice s{b0, b1, blocks[b0].src_off, blocks[b1 - 1].src_off + blocks[b1 - 1].csize, blocks[b0].dst_off, 0};
+        s.d1 = blocks[b1 - 1].dst_off + (blocks[b1 - 1].usize == 0xffffffffu ? 0 : blocks[b1 - 1].usize);
+        slices.push_back(s);
+    }
+    size_t max_in = 0, max_out = 0;
+    for (auto &s : slices) { max_in = std::max<size_t>(max_in, s.s1 - s.s0); max_out = std::max<size_t>(max_out, s.d1 - s.d0); }
+    std::vector<uint8_t> h_tables[2];
+    for (size_t k = 0; k < slices.size(); k++) {
+        const int b = (int)(k & 1);
+        const Slice &s = slices[k];
+        cudaStream_t st = ctx->aux[b];
+        const uint32_t cnt = (uint32_t)(s.b1 - s.b0);
+        if ((r = ensure(ctx, ctx->stage_in[b], max_in + 64))) return r;
+        if ((r = ensure(ctx, ctx->stage_out[b], max_out + 64))) return r;
+        DecWs &ws = ctx->dec[b];
+        // tables: src_off u64[cnt] | dst_off u64[cnt] | csize u32[cnt] | usize u32[cnt] | xxh u32[cnt] | hash_out u32[cnt] | status u8[cnt]
+        const size_t tb_bytes = (size_t)cnt * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 1) + 64;
+        if ((r = ensure(ctx, ws.tables, tb_bytes))) return r;
+        CK(cudaStreamSynchronize(st));                       // previous use of this buffer pair is complete
+        h_tables[b].assign(tb_bytes, 0);
+        uint64_t *t_src = (uint64_t *)h_tables[b].data();
+        uint64_t *t_dst = t_src + cnt;
+        uint32_t *t_c = (uint32_t *)(t_dst + cnt), *t_u = t_c + cnt, *t_x = t_u + cnt;
+        for (uint32_t i = 0; i < cnt; i++) {
+            const HostBlock &hb = blocks[s.b0 + i];
+            t_src[i] = hb.src_off - s.s0; t_dst[i] = hb.dst_off - s.d0;
+            t_c[i] = hb.csize; t_x[i] = hb.xxh;
+            // hash-only items (footers) decode nothing: present them as empty stored blocks
+            t_u[i] = hb.usize;
+        }
+        uint8_t *d_tb = (uint8_t *)ws.tables.p;
+        CK(cudaMemcpyAsync(ctx->stage_in[b].p, src + s.s0, s.s1 - s.s0, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tb, h_tables[b].data(), (size_t)cnt * 28, cudaMemcpyHostToDevice, st));
+        const uint64_t *d_src_off = (const uint64_t *)d_tb, *d_dst_off = d_src_off + cnt;
+        const uint32_t *d_c = (const uint32_t *)(d_dst_off + cnt), *d_u = d_c + cnt, *d_x = d_u + cnt;
+        uint32_t *d_hash = (uint32_t *)(d_x + cnt);
+        int32_t *d_osz = (int32_t *)(d_hash + cnt);
+        uint8_t *d_st = (uint8_t *)(d_osz + cnt);
+        // footers: hash every item's payload first (cheap: same kernel as the block verify)
+        if ((r = fourmc_xxh32_batch_device(ctx, st, cnt, ctx->stage_in[b].p, d_src_off, d_c, 0, d_hash))) return r;
+        // blocks: footers carry usize 0xffffffff -> marked too large by build_desc, decode nothing
+        if ((r = fourmc_lz4_decompress_batch_device(ctx, st, cnt, ctx->stage_in[b].p, d_src_off, d_c, d_u, d_hash, 0,
+                                                    ctx->stage_out[b].p, d_dst_off, d_osz, d_st)))
+            return r;
+        CK(cudaMemcpyAsync((uint8_t *)out + s.d0, ctx->stage_out[b].p, s.d1 - s.d0, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status.data() + s.b0, d_st, cnt, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hashes.data() + s.b0, d_hash, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(ctx->aux[0]));
+    CK(cudaStreamSynchronize(ctx->aux[1]));
+    // verdict in stream order: checksum first (:637/:645), then the decoder (:662)
+    for (size_t i = 0; i < blocks.size(); i++) {
+        if (hashes[i] != blocks[i].xxh) return FOURMC_E_CONTENT;
+        if (blocks[i].usize == 0xffffffffu) continue;        // footer: checksum only
+        if (status[i] != FOURMC_BLOCK_OK) return FOURMC_E_CONTENT;
+    }
+    if (walk_err) return walk_err;
+    return (long long)total;
+}
+
+}  // extern "C"

@@ -1,0 +1,449 @@
+// lz4_encode.cuh -- LZ4 block compression kernels ("4mc Fast").
+//
+// Reference behaviour being replaced: LZ4_compress_default / LZ4_compress_generic_validated
+// (native/lz4/lz4.c:1435, :910-1302) as called per 4 MiB block at native/4mc.c:301 and
+// native/jniCompressor.c:91.  The reference is a serial greedy parse with a 4096-entry hash of
+// "last seen" positions.  Compressed bytes need not match it, only be a valid LZ4 block, so the
+// algorithm here is shaped for the GPU instead (DESIGN.md "LZ4 encode"):
+//
+//  E1 lz4_region_kernel   persistent CTAs; each takes 64 KiB REGIONS of a block:
+//       stage   region -> shared memory with one bulk async copy (cp.async.bulk + mbarrier)
+//       index   16384-entry table of the FIRST position of each 4-byte hash in the region,
+//               order-independent (descending sweep, later stores win), so all threads build it
+//               at once; any earlier occurrence is a usable LZ4 match candidate
+//       parse   every thread greedily parses its own 132-byte SLICE (132 = 33 words: slices
+//               start in distinct shared-memory banks); matches may run past the slice end
+//       stitch  two CTA-wide max-scans: matches of later slices are trimmed to what earlier
+//               slices left uncovered, and every slice learns where its first literal run starts
+//       emit    prefix-sum of encoded sizes, then every thread writes its own sequences
+//     Output per region: the encoded sequences ("body", as if the region stood alone) in a
+//     scratch slot, plus a RegionMeta.  Literals after the region's last match are not stored:
+//     they are input bytes.
+//  E2 lz4_block_size_kernel   per block: walks its <= 64 RegionMeta, merges each region's
+//     leading literals with the literals carried over from the previous region (re-encoding one
+//     token per region join), and decides compressed vs stored (native/4mc.c:301-329).
+//  E3 lz4_block_write_kernel  per block: copies the pieces to their final place in the .4mc
+//     stream, hashes the payload (XXH32, native/4mc.c:311/323) and writes the 12-byte header.
+#pragma once
+
+#include "fm_common.cuh"
+#include "xxh32.cuh"
+
+namespace fm {
+
+constexpr int ENC_REGION = 65536;
+constexpr int ENC_REGIONS_PER_BLOCK = FOURMC_BLOCKSIZE / ENC_REGION;   // 64
+constexpr int ENC_SLOT = ENC_REGION + 512;       // scratch bytes per region body (worst case R + R/255 + 16)
+constexpr int ENC_THREADS = 512;
+constexpr int ENC_WARPS = ENC_THREADS / 32;
+constexpr int ENC_SLICE = 132;
+constexpr int ENC_HASH_BITS = 14;
+constexpr int ENC_MAXREC = ENC_SLICE / 4 + 1;    // inner records of one slice
+constexpr int ENC_PAD = 64;
+constexpr size_t ENC_SMEM = ENC_REGION + ENC_PAD + (sizeof(uint16_t) << ENC_HASH_BITS);
+
+static_assert(ENC_THREADS * ENC_SLICE >= ENC_REGION, "slices must cover the region");
+
+struct RegionMeta {
+    uint32_t body_bytes;     // bytes in the scratch slot
+    uint32_t tail_lits;      // input bytes after the region's last match (whole region if nseq == 0)
+    uint32_t lead;           // literal count of the region's first sequence
+    uint32_t nseq;
+};
+
+struct EncParams {
+    const uint8_t *in;       // contiguous input
+    uint64_t n;              // input bytes
+    uint32_t n_regions;      // total over all blocks (64 per block, trailing ones may be empty)
+    uint8_t *scratch;        // n_regions * ENC_SLOT
+    RegionMeta *meta;        // n_regions
+    uint32_t *work_counter;  // zeroed before launch
+    int min_match;           // >= 4
+};
+
+__device__ __forceinline__ uint32_t enc_hash(uint32_t v) { return (v * 2654435761u) >> (32 - ENC_HASH_BITS); }
+
+// bytes of LZ4 length continuation for a field value v (0 when v < 15)
+__device__ __forceinline__ int enc_ext_bytes(int v) { return v < 15 ? 0 : 1 + (v - 15) / 255; }
+
+__device__ __forceinline__ uint32_t smem_read4(const uint32_t *data32, int p)
+{
+    const int w = p >> 2;
+    return __funnelshift_r(data32[w], data32[w + 1], (p & 3) * 8);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// CTA-wide exclusive scan over ENC_THREADS values (max or add); `tmp` holds ENC_WARPS ints.
+// Identity is 0 for both (all values are >= 0).  *total (optional) = reduction over the CTA.
+template <bool IS_MAX>
+__device__ __forceinline__ int cta_excl_scan(int v, int *tmp, int *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int incl = IS_MAX ? warp_incl_scan_max(v) : warp_incl_scan_add(v);
+    if (lane == 31) tmp[warp] = incl;
+    __syncthreads();
+    const int wv = lane < ENC_WARPS ? tmp[lane] : 0;
+    const int wincl = IS_MAX ? warp_incl_scan_max(wv) : warp_incl_scan_add(wv);
+    int wexcl = __shfl_up_sync(FM_FULL, wincl, 1);
+    if (lane == 0) wexcl = 0;
+    const int base = __shfl_sync(FM_FULL, wexcl, warp);
+    if (total) *total = __shfl_sync(FM_FULL, wincl, 31);
+    int excl = __shfl_up_sync(FM_FULL, incl, 1);
+    if (lane == 0) excl = 0;
+    __syncthreads();                                           // tmp reusable
+    return IS_MAX ? max(base, excl) : base + excl;
+}
+
+__device__ __forceinline__ uint8_t *emit_len(uint8_t *o, int v)
+{
+    while (v >= 255) { *o++ = 255; v -= 255; }
+    *o++ = (uint8_t)v;
+    return o;
+}
+
+// inner record: start (relative to the slice, 8 bits) | length (8 bits) | offset (16 bits)
+__device__ __forceinline__ uint32_t enc_pack(int st_rel, int len, int off)
+{
+    return ((uint32_t)st_rel << 24) | ((uint32_t)len << 16) | (uint32_t)off;
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *data = smem;                                          // ENC_REGION + ENC_PAD
+    uint32_t *data32 = (uint32_t *)smem;
+    uint16_t *table = (uint16_t *)(smem + ENC_REGION + ENC_PAD);
+    __shared__ int s_scan[ENC_WARPS];
+    __shared__ uint32_t s_work;
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint32_t phase = 0;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) s_work = atomicAdd(P.work_counter, 1u);
+        __syncthreads();
+        const uint32_t rg = s_work;
+        if (rg >= P.n_regions) break;
+
+        // ---- locate the region
+        const uint32_t blk = rg / ENC_REGIONS_PER_BLOCK, rib = rg % ENC_REGIONS_PER_BLOCK;
+        const uint64_t blk_off = (uint64_t)blk * FOURMC_BLOCKSIZE;
+        const uint32_t blk_len = (uint32_t)min((uint64_t)FOURMC_BLOCKSIZE, P.n - blk_off);
+        const uint32_t r_off = rib * ENC_REGION;                   // within the block
+        if (r_off >= blk_len) {                                    // region beyond a short last block
+            if (tid == 0) P.meta[rg] = RegionMeta{0, 0, 0, 0};
+            __syncthreads();
+            continue;
+        }
+        const int rlen = (int)min((uint32_t)ENC_REGION, blk_len - r_off);
+        const uint8_t *gsrc = P.in + blk_off + r_off;
+        // LZ4 end-of-block rules, relative to the region (native/lz4/lz4.c:243-247): the last
+        // match starts at least 12 bytes before the block end and ends at least 5 before it.
+        const int mf_limit = min(rlen - 1, (int)blk_len - 12 - (int)r_off);
+        const int match_limit = min(rlen, (int)blk_len - 5 - (int)r_off);
+
+        // ---- stage: bulk async copy of the 16-byte multiple, plain loads for the rest
+        const int bulk = (((uintptr_t)gsrc & 15) == 0) ? (rlen & ~15) : 0;
+        if (tid == 0 && bulk) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bulk) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(data)), "l"(gsrc), "r"(bulk), "r"(smem_u32(&s_bar)) : "memory");
+        }
+        for (int i = bulk + tid; i < rlen; i += ENC_THREADS) data[i] = gsrc[i];
+        if (tid < ENC_PAD) data[rlen + tid] = 0;                   // reads past the end see zeros
+        for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += ENC_THREADS) ((uint32_t *)table)[i] = 0xffffffffu;
+        if (bulk) {
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\t"
+                             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(smem_u32(&s_bar)), "r"(phase) : "memory");
+            }
+            phase ^= 1;
+        }
+        __syncthreads();
+
+        // ---- index: first occurrence of every 4-byte hash (descending sweep, later stores win)
+        {
+            const int last = rlen - 4;                             // last position with 4 bytes
+            for (int base = ((rlen - 1) / ENC_THREADS) * ENC_THREADS; base >= 0; base -= ENC_THREADS) {
+                const int p = base + tid;
+                if (p <= last) table[enc_hash(smem_read4(data32, p))] = (uint16_t)p;
+                __syncthreads();
+            }
+        }
+
+        // ---- parse: one slice per thread.  Inner sequences (all but the last) end inside the
+        // slice and fit a packed word; the last one may be long and lives in registers.
+        uint32_t rec[ENC_MAXREC];
+        int nrec = 0;
+        int l_st = 0, l_len = 0, l_off = 0;                        // last sequence (l_len == 0: none)
+        const int ss = tid * ENC_SLICE;
+        if (ss < rlen) {
+            const int se = min(ss + ENC_SLICE, rlen);
+            int p = ss, anchor = ss;
+            while (p < se && p <= mf_limit) {
+                const uint32_t v = smem_read4(data32, p);
+                const int c = (int)table[enc_hash(v)];
+                if (c < p && smem_read4(data32, c) == v) {
+                    int len = 4;
+                    const int maxlen = match_limit - p;
+                    while (len < maxlen) {
+                        const uint32_t x = smem_read4(data32, p + len) ^ smem_read4(data32, c + len);
+                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                        len += 4;
+                    }
+                    len = min(len, maxlen);
+                    int st = p, m = c;
+                    while (st > anchor && m > 0 && data[st - 1] == data[m - 1]) { st--; m--; len++; }
+                    if (len >= P.min_match) {
+                        if (l_len) rec[nrec++] = enc_pack(l_st - ss, l_len, l_off);
+                        l_st = st; l_len = len; l_off = st - m;
+                        p = st + len; anchor = p;
+                        continue;
+                    }
+                }
+                p++;
+            }
+        }
+
+        // ---- stitch 1: trim against everything earlier slices cover
+        const int cov = cta_excl_scan<true>(l_len ? l_st + l_len : 0, s_scan, nullptr);
+        int surv_end = 0;                                           // end of my last surviving sequence
+        {
+            int w = 0;
+            for (int k = 0; k < nrec; k++) {
+                const uint32_t r = rec[k];
+                int st = ss + (int)(r >> 24), len = (int)((r >> 16) & 255);
+                const int end = st + len;
+                if (st < cov) { len = end - cov; st = cov; }
+                if (len < 4 || st > mf_limit) continue;             // dropped: its bytes become literals
+                rec[w++] = enc_pack(st - ss, len, (int)(r & 0xffffu));
+                surv_end = end;
+            }
+            nrec = w;
+            if (l_len) {
+                const int end = l_st + l_len;
+                if (l_st < cov) { l_len = end - cov; l_st = cov; }
+                if (l_len < 4 || l_st > mf_limit) l_len = 0; else surv_end = end;
+            }
+        }
+        // ---- stitch 2: where does my first literal run start; encoded size of my sequences
+        int total_anchor;
+        const int anchor0 = cta_excl_scan<true>(surv_end, s_scan, &total_anchor);
+        int bytes = 0;
+        {
+            int a = anchor0;
+            for (int k = 0; k < nrec; k++) {
+                const uint32_t r = rec[k];
+                const int st = ss + (int)(r >> 24), len = (int)((r >> 16) & 255);
+                const int lit = st - a;
+                bytes += 1 + enc_ext_bytes(lit) + lit + 2 + enc_ext_bytes(len - 4);
+                a = st + len;
+            }
+            if (l_len) {
+                const int lit = l_st - a;
+                bytes += 1 + enc_ext_bytes(lit) + lit + 2 + enc_ext_bytes(l_len - 4);
+            }
+        }
+        const int myseq = nrec + (l_len ? 1 : 0);
+        int total_bytes, total_seq;
+        const int out_off = cta_excl_scan<false>(bytes, s_scan, &total_bytes);
+        const int seq_before = cta_excl_scan<false>(myseq, s_scan, &total_seq);
+
+        // ---- emit.  Only a slice's first literal run can be long (it may reach back over
+        // match-free slices); those are copied by the whole warp afterwards.
+        uint8_t *slot = P.scratch + (size_t)rg * ENC_SLOT;
+        int long_n = 0, long_src = 0;
+        uint8_t *long_dst = nullptr;
+        {
+            uint8_t *o = slot + out_off;
+            int a = anchor0;
+            for (int k = 0; k <= nrec; k++) {
+                int st, len, off;
+                if (k < nrec) {
+                    const uint32_t r = rec[k];
+                    st = ss + (int)(r >> 24); len = (int)((r >> 16) & 255); off = (int)(r & 0xffffu);
+                } else {
+                    if (!l_len) break;
+                    st = l_st; len = l_len; off = l_off;
+                }
+                const int lit = st - a, ml = len - 4;
+                if (k == 0 && seq_before == 0) P.meta[rg].lead = (uint32_t)lit;
+                *o++ = (uint8_t)((min(lit, 15) << 4) | min(ml, 15));
+                if (lit >= 15) o = emit_len(o, lit - 15);
+                if (lit > ENC_SLICE) { long_n = lit; long_src = a; long_dst = o; }
+                else { for (int i = 0; i < lit; i++) o[i] = data[a + i]; }
+                o += lit;
+                *o++ = (uint8_t)(off & 0xff); *o++ = (uint8_t)(off >> 8);
+                if (ml >= 15) o = emit_len(o, ml - 15);
+                a = st + len;
+            }
+        }
+        for (unsigned mm = __ballot_sync(FM_FULL, long_n > 0); mm; mm &= mm - 1) {
+            const int l = __ffs(mm) - 1;
+            const int n = __shfl_sync(FM_FULL, long_n, l);
+            const int sp = __shfl_sync(FM_FULL, long_src, l);
+            uint8_t *dp = (uint8_t *)__shfl_sync(FM_FULL, (unsigned long long)long_dst, l);
+            for (int i = lane; i < n; i += 32) dp[i] = data[sp + i];
+        }
+        if (tid == 0) {
+            RegionMeta *mt = &P.meta[rg];
+            mt->body_bytes = (uint32_t)total_bytes;
+            mt->tail_lits = (uint32_t)(rlen - total_anchor);
+            mt->nseq = (uint32_t)total_seq;
+            if (total_seq == 0) mt->lead = 0;
+        }
+        __syncthreads();        // smem is reused by the next region
+    }
+}
+
+// ---- E2 / E3 ---------------------------------------------------------------------------------
+
+struct BlockPlan {              // produced by E2, consumed by the index scan and E3
+    uint32_t usize;
+    uint32_t payload;           // csize, or usize when stored
+    uint32_t stored;
+    uint32_t final_lits;        // literals of the closing sequence
+};
+
+// raw_limit < 0: container mode, a block is stored when its compressed size reaches its raw size.
+// raw_limit >= 0: bare LZ4 block for the per-block API; "stored" then means "does not fit in
+// raw_limit bytes" (LZ4_compress_default returns 0, native/lz4/lz4.c:1290-1300).
+__global__ void lz4_block_size_kernel(const RegionMeta *meta, uint32_t n_blocks, uint64_t n,
+                                      BlockPlan *plan, uint32_t *block_lens, int64_t raw_limit)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint64_t blk_off = (uint64_t)b * FOURMC_BLOCKSIZE;
+    const uint32_t u = (uint32_t)min((uint64_t)FOURMC_BLOCKSIZE, n - blk_off);
+    const RegionMeta *m = meta + (size_t)b * ENC_REGIONS_PER_BLOCK;
+    uint32_t carry = 0, c = 0;
+    for (int r = 0; r < ENC_REGIONS_PER_BLOCK; r++) {
+        const RegionMeta x = m[r];
+        if (x.nseq == 0) { carry += x.tail_lits; continue; }
+        const int old_hdr = 1 + enc_ext_bytes((int)x.lead);
+        const int new_hdr = 1 + enc_ext_bytes((int)(x.lead + carry));
+        c += (uint32_t)new_hdr + carry + (x.body_bytes - (uint32_t)old_hdr);
+        carry = x.tail_lits;
+    }
+    c += 1u + (uint32_t)enc_ext_bytes((int)carry) + carry;
+    BlockPlan p;
+    p.usize = u;
+    if (raw_limit >= 0) {
+        p.stored = ((int64_t)c > raw_limit) ? 1u : 0u;
+        p.payload = p.stored ? 0u : c;
+    } else {
+        p.stored = (c >= u) ? 1u : 0u;      // the reference offers u-1 bytes (native/4mc.c:301)
+        p.payload = p.stored ? u : c;
+    }
+    p.final_lits = carry;
+    plan[b] = p;
+    if (block_lens) block_lens[b] = 12u + p.payload;
+}
+
+// CTA-cooperative copy, arbitrary alignment: byte head, 16-byte stores with funnel-shifted loads.
+__device__ __forceinline__ void cta_copy(uint8_t *d, const uint8_t *s, uint32_t n)
+{
+    const uint32_t tid = threadIdx.x, nth = blockDim.x;
+    if (n < 64) { for (uint32_t i = tid; i < n; i += nth) d[i] = s[i]; return; }
+    const uint32_t head = (uint32_t)((16 - ((uintptr_t)d & 15)) & 15);
+    for (uint32_t i = tid; i < head; i += nth) d[i] = s[i];
+    const uint8_t *s2 = s + head;
+    const uint32_t sh = (uint32_t)((uintptr_t)s2 & 3) * 8;
+    const uint32_t *sw = (const uint32_t *)((uintptr_t)s2 & ~(uintptr_t)3);
+    const uint32_t body = (n - head - 4) >> 4;              // keep the funnel's extra word in range
+    uint4 *dv = (uint4 *)(d + head);
+    for (uint32_t i = tid; i < body; i += nth) {
+        const uint32_t a = sw[4 * i], b = sw[4 * i + 1], c = sw[4 * i + 2], e = sw[4 * i + 3], f = sw[4 * i + 4];
+        dv[i] = make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh),
+                           __funnelshift_r(c, e, sh), __funnelshift_r(e, f, sh));
+    }
+    for (uint32_t i = head + (body << 4) + tid; i < n; i += nth) d[i] = s[i];
+}
+
+constexpr int ENC_WRITE_THREADS = 256;
+
+// out_base + block_off[b] is where block b's 12-byte header goes.
+__global__ void __launch_bounds__(ENC_WRITE_THREADS)
+lz4_block_write_kernel(const uint8_t *in, const uint8_t *scratch, const RegionMeta *meta,
+                       const BlockPlan *plan, const uint64_t *block_off, uint8_t *out_base, int raw_mode)
+{
+    __shared__ __align__(16) uint32_t s_stage[XXH_WARP_SMEM_WORDS];
+    __shared__ uint32_t s_dst[ENC_REGIONS_PER_BLOCK + 1];   // payload offset of each region's piece
+    __shared__ uint32_t s_carry[ENC_REGIONS_PER_BLOCK + 1]; // literals carried INTO the region
+
+    const uint32_t b = blockIdx.x;
+    const BlockPlan p = plan[b];
+    const uint64_t blk_off = (uint64_t)b * FOURMC_BLOCKSIZE;
+    const uint8_t *src = in + blk_off;
+    uint8_t *rec = out_base + block_off[b];
+    uint8_t *pay = rec + 12;
+    const RegionMeta *m = meta + (size_t)b * ENC_REGIONS_PER_BLOCK;
+
+    if (p.stored) {
+        if (raw_mode) return;               // nothing to write: the caller reports 0
+        cta_copy(pay, src, p.usize);
+    } else {
+        if (threadIdx.x == 0) {
+            uint32_t carry = 0, c = 0;
+            for (int r = 0; r < ENC_REGIONS_PER_BLOCK; r++) {
+                const RegionMeta x = m[r];
+                s_dst[r] = c; s_carry[r] = carry;
+                if (x.nseq == 0) { carry += x.tail_lits; continue; }
+                const int old_hdr = 1 + enc_ext_bytes((int)x.lead);
+                const int new_hdr = 1 + enc_ext_bytes((int)(x.lead + carry));
+                c += (uint32_t)new_hdr + carry + (x.body_bytes - (uint32_t)old_hdr);
+                carry = x.tail_lits;
+            }
+            s_dst[ENC_REGIONS_PER_BLOCK] = c; s_carry[ENC_REGIONS_PER_BLOCK] = carry;
+        }
+        __syncthreads();
+        for (int r = 0; r < ENC_REGIONS_PER_BLOCK; r++) {
+            const RegionMeta x = m[r];
+            if (x.nseq == 0) continue;
+            const uint32_t carry = s_carry[r];
+            const uint8_t *slot = scratch + ((size_t)b * ENC_REGIONS_PER_BLOCK + r) * ENC_SLOT;
+            uint8_t *o = pay + s_dst[r];
+            const int old_hdr = 1 + enc_ext_bytes((int)x.lead);
+            const int lit = (int)(x.lead + carry);
+            const int new_hdr = 1 + enc_ext_bytes(lit);
+            if (threadIdx.x == 0) {
+                uint8_t *q = o;
+                *q++ = (uint8_t)((min(lit, 15) << 4) | (slot[0] & 15));
+                if (lit >= 15) emit_len(q, lit - 15);
+            }
+            // carried literals are input bytes just before the region
+            cta_copy(o + new_hdr, src + (size_t)r * ENC_REGION - carry, carry);
+            cta_copy(o + new_hdr + carry, slot + old_hdr, x.body_bytes - (uint32_t)old_hdr);
+        }
+        {   // closing sequence: literals only
+            const uint32_t carry = s_carry[ENC_REGIONS_PER_BLOCK];
+            uint8_t *o = pay + s_dst[ENC_REGIONS_PER_BLOCK];
+            const int hdr = 1 + enc_ext_bytes((int)carry);
+            if (threadIdx.x == 0) {
+                uint8_t *q = o;
+                *q++ = (uint8_t)(min((int)carry, 15) << 4);
+                if (carry >= 15) emit_len(q, (int)carry - 15);
+            }
+            cta_copy(o + hdr, src + p.usize - carry, carry);
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t h = xxh32_warp<false>(pay, p.payload, 0, s_stage);
+        if (threadIdx.x == 0) { st_be32(rec, p.usize); st_be32(rec + 4, p.payload); st_be32(rec + 8, h); }
+    }
+}
+
+}  // namespace fm

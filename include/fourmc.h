@@ -1,0 +1,166 @@
+/*
+ * fourmc.h -- C-ABI of lib4mcgpu.so, the B200 (sm_100a) implementation of the 4mc block hot path.
+ *
+ * Plain C: pointers, sizes, integer status codes.  No CUDA or torch types in any signature
+ * (a CUDA stream is passed as void*, NULL = the context's own stream).  Every entry point names
+ * the reference call site(s) it replaces; paths are relative to the reference repository root.
+ *
+ * Threading: a fourmc_ctx owns its stream and workspaces and must not be used from two threads at
+ * once; distinct contexts are independent (the reference is re-entrant the same way: one
+ * stack/heap context per call, native/lz4/lz4.c:1416-1432).  Nothing here ever falls back to a
+ * CPU codec: without a usable CUDA device every call fails with FOURMC_E_CUDA.
+ */
+#ifndef FOURMC_H
+#define FOURMC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOURMC_BLOCKSIZE      (4 * 1024 * 1024)   /* native/4mc.c:116 FOURMC_BLOCKSIZE */
+#define FOURMC_MAGIC_4MC      0x344D4300u          /* native/4mc.c:111 */
+#define FOURMC_MAGIC_4MZ      0x344D5A00u          /* native/4mc.c:112 */
+#define FOURMC_VERSION        1u                   /* native/4mc.c:113 */
+#define FOURMC_HEADERSIZE     12                   /* native/4mc.c:115 */
+
+/* status / error codes (all negative).  The container functions map the CLI's exit codes
+ * (native/4mc.c:135-161): 1 generic, 2 input, 3 output, 4 content. */
+#define FOURMC_OK             0
+#define FOURMC_E_GENERIC     (-1)   /* exit(1): allocation, unreadable footer                       */
+#define FOURMC_E_INPUT       (-2)   /* exit(2): truncated stream ("cannot read next block size")    */
+#define FOURMC_E_OUTPUT      (-3)   /* exit(3): destination too small                               */
+#define FOURMC_E_CONTENT     (-4)   /* exit(4): bad magic/version/checksum, corrupt LZ4 block       */
+#define FOURMC_E_CUDA        (-10)  /* no device, or a CUDA call failed (see fourmc_last_error)     */
+#define FOURMC_E_ARG         (-11)  /* invalid argument                                             */
+#define FOURMC_E_UNSUPPORTED (-12)  /* valid request this build does not implement (e.g. 4mz)       */
+
+/* per-block status written by the batch decoders */
+#define FOURMC_BLOCK_OK        0
+#define FOURMC_BLOCK_CHECKSUM  1    /* XXH32(payload) != header checksum   (native/4mc.c:637,645)  */
+#define FOURMC_BLOCK_CORRUPT   2    /* LZ4_decompress_safe(...) < 0        (native/4mc.c:662)      */
+#define FOURMC_BLOCK_TOOLARGE  3    /* csize or usize beyond 4 MiB         (native/4mc.c:618,651)  */
+
+typedef struct fourmc_ctx fourmc_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* Creates a context on CUDA device `device` (-1 = current device).  Returns FOURMC_OK or
+ * FOURMC_E_CUDA.  Workspaces grow on demand and are kept until fourmc_ctx_destroy. */
+int  fourmc_ctx_create(fourmc_ctx **out, int device);
+void fourmc_ctx_destroy(fourmc_ctx *ctx);
+/* Text of the last failure on this context (never NULL). */
+const char *fourmc_last_error(const fourmc_ctx *ctx);
+/* Number of kernels this library has launched on the context since creation. */
+uint64_t fourmc_kernel_launches(const fourmc_ctx *ctx);
+/* Blocks until everything queued on the context's stream (or `stream`) has finished. */
+int  fourmc_sync(fourmc_ctx *ctx, void *stream);
+
+/* ---- per-block calls, HOST pointers: what native/jni*.c and the native/4mc.c loops call ----- */
+
+/* LZ4_compressBound: native/jniCompressor.c:171, native/lz4/lz4.h:212.  No device needed. */
+int fourmc_lz4_compress_bound(int n);
+
+/* One LZ4 block.  Replaces LZ4_compress_default (native/4mc.c:301 via :214, level <= 1),
+ * LZ4_compress / LZ4_compressMC / LZ4_compressHC2 (native/jniCompressor.c:91,123,156).
+ * Returns the compressed size (> 0), 0 when it does not fit in dst_capacity (the caller then
+ * stores the block raw, native/4mc.c:318-329), or a negative FOURMC_E_*.
+ * The bytes are a valid LZ4 block but not the reference's bytes.  level: 1 fast .. 4 ultra. */
+int fourmc_lz4_compress(fourmc_ctx *ctx, int level, const void *src, int src_size,
+                        void *dst, int dst_capacity);
+
+/* LZ4_decompress_safe: native/4mc.c:661, native/jniDecompressor.c:88.  Same return convention
+ * as the reference: decoded size >= 0, or -(input position)-1 on malformed input
+ * (native/lz4/lz4.c:2337); FOURMC_E_CUDA (-10) cannot be confused with it only by asking
+ * fourmc_last_error(), so device failures are also latched in the context. */
+int fourmc_lz4_decompress_safe(fourmc_ctx *ctx, const void *src, int compressed_size,
+                               void *dst, int dst_capacity);
+
+/* XXH32: native/4mc.c:269,311,323,585,637,645,685; native/jniCompressor.c:188,
+ * native/jniDecompressor.c:112.  *status (may be NULL) receives FOURMC_OK or FOURMC_E_CUDA. */
+uint32_t fourmc_xxh32(fourmc_ctx *ctx, const void *data, size_t len, uint32_t seed, int *status);
+
+/* ---- whole-stream calls, HOST buffers: the bodies of fourMCcompressFilename /
+ *      fourMcDecompressFileName (native/4mc.c:220-386, :896-934) minus stdio ------------------- */
+
+/* Upper bound of a .4mc stream for n input bytes (every block stored). */
+size_t fourmc_4mc_bound(size_t n);
+
+/* in[0..n) -> header, one block per 4 MiB, EOS, footer.  Copies the input
+ * to the device in pipelined slices, runs the block kernels, copies the stream back.
+ * Returns the stream size or a negative FOURMC_E_*. */
+long long fourmc_4mc_compress_host(fourmc_ctx *ctx, int level, const void *in, size_t n,
+                                   void *out, size_t out_capacity);
+
+/* Decodes one or more concatenated .4mc streams (native/4mc.c:908-912).  Headers are walked on
+ * the host exactly like decodeFourMC (:603-668); payload verification (XXH32) and LZ4 decoding
+ * run on the device.  Returns the decoded size or a negative FOURMC_E_* with the reference's
+ * precedence (the first failing block in stream order decides). */
+long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n,
+                                     void *out, size_t out_capacity);
+
+/* Size a stream decodes to (sum of the block headers' usize), without decoding.  Negative on a
+ * malformed container. */
+long long fourmc_4mc_decoded_size_host(const void *in, size_t n);
+
+/* ---- device-resident calls: inputs and outputs already in HBM ------------------------------- */
+/* All d_* are device pointers on the context's device.  Calls are asynchronous on `stream`
+ * unless stated; results land in device memory and are read after fourmc_sync(). */
+
+/* Whole stream on device.  d_out receives the complete .4mc stream; *d_out_size (device u64)
+ * its length.  d_block_lens (device u32[n_blocks], may be NULL) receives 12+csize per block --
+ * the footer deltas a multi-GPU writer all-gathers. */
+int fourmc_4mc_compress_device(fourmc_ctx *ctx, void *stream, int level,
+                               const void *d_in, size_t n,
+                               void *d_out, size_t out_capacity,
+                               uint64_t *d_out_size, uint32_t *d_block_lens);
+
+/* Block range only (no file header / EOS / footer): the per-rank span of a sharded writer.
+ * d_span receives block records back to back; *d_span_size its length. */
+int fourmc_4mc_compress_span_device(fourmc_ctx *ctx, void *stream, int level,
+                                    const void *d_in, size_t n,
+                                    void *d_span, size_t span_capacity,
+                                    uint64_t *d_span_size, uint32_t *d_block_lens);
+
+/* Footer (and file header / EOS) assembly from block lengths: native/4mc.c:263-274,335-362.
+ * d_block_lens[i] = 12 + csize_i for ALL blocks of the file; writes the 12-byte header to
+ * d_header (may be NULL), and EOS+footer (12 + 20 + 4*n_blocks bytes) to d_tail. */
+int fourmc_4mc_build_index_device(fourmc_ctx *ctx, void *stream, const uint32_t *d_block_lens,
+                                  uint32_t n_blocks, void *d_header, void *d_tail);
+
+/* Whole single stream on device (located through its footer index, cross-checked against the
+ * block headers and the EOS mark).  d_result (device i64[2]): [0] decoded size or FOURMC_E_*,
+ * [1] index of the first failing block or -1. */
+int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n,
+                                 void *d_out, size_t out_capacity, long long *d_result);
+
+/* Batch of independent blocks.  Block i: payload at d_src + src_off[i] (csize[i] bytes, raw when
+ * csize[i] == usize[i]), expected checksum xxh[i] (ignored when check_xxh == 0), output at
+ * d_dst + dst_off[i] with capacity usize[i].  The five tables are DEVICE arrays.
+ * d_status[i] receives FOURMC_BLOCK_*; d_out_size[i] the decoded size (or the negative
+ * LZ4_decompress_safe value). */
+int fourmc_lz4_decompress_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_blocks,
+                                       const void *d_src, const uint64_t *d_src_off,
+                                       const uint32_t *d_csize, const uint32_t *d_usize,
+                                       const uint32_t *d_xxh, int check_xxh,
+                                       void *d_dst, const uint64_t *d_dst_off,
+                                       int32_t *d_out_size, uint8_t *d_status);
+
+/* XXH32 of n_items device ranges: d_out[i] = XXH32(d_base + d_off[i], d_len[i], seed). */
+int fourmc_xxh32_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_items,
+                              const void *d_base, const uint64_t *d_off, const uint32_t *d_len,
+                              uint32_t seed, uint32_t *d_out);
+
+/* ---- synthetic inputs, bit-identical on host and device ---------------------- */
+
+/* kind 0 = log-text.  Fills pages [first_page, first_page + n_pages) of 4096 bytes each. */
+int fourmc_gen_device(fourmc_ctx *ctx, void *stream, int kind, uint64_t seed,
+                      uint64_t first_page, uint64_t n_pages, void *d_out);
+int fourmc_gen_host(int kind, uint64_t seed, uint64_t first_page, uint64_t n_pages, void *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

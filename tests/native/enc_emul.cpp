@@ -1,0 +1,126 @@
+// enc_emul.cpp -- TEST-ONLY sequential emulation of the encode kernels' algorithm
+// (4mc_b200/csrc/lz4_encode.cuh: region parse / stitch / emit, block size, block write).
+// It mirrors the kernels step by step with "for each thread" loops so that the algorithm (slice
+// stitching, region joins, end-of-block rules) can be checked against the oracle decoder on a
+// machine without a GPU.  It is not part of the product and is never shipped.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace {
+constexpr int BLOCK = 4 << 20, REGION = 65536, RPB = BLOCK / REGION, THREADS = 512, SLICE = 132, HB = 14, PAD = 64;
+struct Meta { uint32_t body_bytes, tail_lits, lead, nseq; };
+struct Seq { int st, len, off; };
+inline uint32_t rd4(const uint8_t *d, int p) { uint32_t v; memcpy(&v, d + p, 4); return v; }
+inline uint32_t hsh(uint32_t v) { return (v * 2654435761u) >> (32 - HB); }
+inline int ext(int v) { return v < 15 ? 0 : 1 + (v - 15) / 255; }
+inline uint8_t *emit_len(uint8_t *o, int v) { while (v >= 255) { *o++ = 255; v -= 255; } *o++ = (uint8_t)v; return o; }
+
+void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_off, int min_match, std::vector<uint8_t> &body, Meta &mt)
+{
+    const int rlen = (int)std::min<uint32_t>(REGION, blk_len - r_off);
+    std::vector<uint8_t> data(REGION + PAD, 0);
+    memcpy(data.data(), blk + r_off, rlen);
+    const int mf_limit = std::min(rlen - 1, (int)blk_len - 12 - (int)r_off);
+    const int match_limit = std::min(rlen, (int)blk_len - 5 - (int)r_off);
+    std::vector<uint16_t> table(1 << HB, 0xffff);
+    // index: descending sweep in steps of THREADS; within a step the order is unspecified on
+    // the GPU -- emulate "highest thread wins" (any order is legal)
+    for (int base = ((rlen - 1) / THREADS) * THREADS; base >= 0; base -= THREADS)
+        for (int t = 0; t < THREADS; t++) { int p = base + t; if (p <= rlen - 4) table[hsh(rd4(data.data(), p))] = (uint16_t)p; }
+    std::vector<std::vector<Seq>> inner(THREADS);
+    std::vector<Seq> last(THREADS, Seq{0, 0, 0});
+    const uint8_t *d = data.data();
+    for (int t = 0; t < THREADS; t++) {
+        const int ss = t * SLICE;
+        if (ss >= rlen) continue;
+        const int se = std::min(ss + SLICE, rlen);
+        int p = ss, anchor = ss;
+        while (p < se && p <= mf_limit) {
+            const uint32_t v = rd4(d, p);
+            const int c = table[hsh(v)];
+            if (c < p && rd4(d, c) == v) {
+                int len = 4; const int maxlen = match_limit - p;
+                while (len < maxlen && d[p + len] == d[c + len]) len++;
+                len = std::min(len, maxlen);
+                int st = p, m = c;
+                while (st > anchor && m > 0 && d[st - 1] == d[m - 1]) { st--; m--; len++; }
+                if (len >= min_match) {
+                    if (last[t].len) inner[t].push_back(last[t]);
+                    last[t] = Seq{st, len, st - m};
+                    p = st + len; anchor = p; continue;
+                }
+            }
+            p++;
+        }
+    }
+    // stitch 1
+    std::vector<int> surv_end(THREADS, 0);
+    int cov = 0;
+    for (int t = 0; t < THREADS; t++) {
+        const int my_end = last[t].len ? last[t].st + last[t].len : 0;
+        std::vector<Seq> keep;
+        for (auto s : inner[t]) {
+            const int end = s.st + s.len;
+            if (s.st < cov) { s.len = end - cov; s.st = cov; }
+            if (s.len < 4 || s.st > mf_limit) continue;
+            keep.push_back(s); surv_end[t] = end;
+        }
+        inner[t] = keep;
+        if (last[t].len) {
+            const int end = last[t].st + last[t].len;
+            if (last[t].st < cov) { last[t].len = end - cov; last[t].st = cov; }
+            if (last[t].len < 4 || last[t].st > mf_limit) last[t].len = 0; else surv_end[t] = end;
+        }
+        cov = std::max(cov, my_end);
+    }
+    // stitch 2 + emit
+    body.clear();
+    int anchor = 0; uint32_t nseq = 0; mt.lead = 0;
+    for (int t = 0; t < THREADS; t++) {
+        std::vector<Seq> all = inner[t];
+        if (last[t].len) all.push_back(last[t]);
+        int a = anchor;
+        for (auto &s : all) {
+            const int lit = s.st - a, ml = s.len - 4;
+            if (nseq == 0) mt.lead = lit;
+            size_t o0 = body.size();
+            body.resize(o0 + 1 + ext(lit) + lit + 2 + ext(ml));
+            uint8_t *o = body.data() + o0;
+            *o++ = (uint8_t)((std::min(lit, 15) << 4) | std::min(ml, 15));
+            if (lit >= 15) o = emit_len(o, lit - 15);
+            memcpy(o, d + a, lit); o += lit;
+            *o++ = (uint8_t)(s.off & 0xff); *o++ = (uint8_t)(s.off >> 8);
+            if (ml >= 15) o = emit_len(o, ml - 15);
+            a = s.st + s.len; nseq++;
+        }
+        anchor = std::max(anchor, surv_end[t]);
+    }
+    mt.body_bytes = (uint32_t)body.size(); mt.tail_lits = (uint32_t)(rlen - anchor); mt.nseq = nseq;
+}
+}  // namespace
+
+// Compresses one block (n <= 4 MiB) the way the kernels do.  Returns the LZ4 payload size written
+// to dst (capacity must be >= n + n/255 + 64), never "stored".
+extern "C" int enc_emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match)
+{
+    std::vector<Meta> meta(RPB, Meta{0, 0, 0, 0});
+    std::vector<std::vector<uint8_t>> bodies(RPB);
+    for (int r = 0; r < RPB; r++) if ((uint32_t)r * REGION < (uint32_t)n) region(src, (uint32_t)n, (uint32_t)r * REGION, min_match, bodies[r], meta[r]);
+    uint8_t *o = dst; uint32_t carry = 0;
+    for (int r = 0; r < RPB; r++) {
+        const Meta &x = meta[r];
+        if (x.nseq == 0) { carry += x.tail_lits; continue; }
+        const int old_hdr = 1 + ext((int)x.lead), lit = (int)(x.lead + carry);
+        *o++ = (uint8_t)((std::min(lit, 15) << 4) | (bodies[r][0] & 15));
+        if (lit >= 15) o = emit_len(o, lit - 15);
+        memcpy(o, src + (size_t)r * REGION - carry, carry); o += carry;
+        memcpy(o, bodies[r].data() + old_hdr, x.body_bytes - old_hdr); o += x.body_bytes - old_hdr;
+        carry = x.tail_lits;
+    }
+    *o++ = (uint8_t)(std::min((int)carry, 15) << 4);
+    if (carry >= 15) o = emit_len(o, (int)carry - 15);
+    memcpy(o, src + n - carry, carry); o += carry;
+    return (int)(o - dst);
+}

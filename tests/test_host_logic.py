@@ -1,0 +1,110 @@
+"""CPU checks of product logic that is host-compilable: the D1 parser (lz4_parse.h, HD code shared
+with the kernel), the generator, the encode algorithm's sequential emulation, and the ABI surface."""
+import ctypes as C
+import os
+import random
+import re
+
+import pytest
+
+from conftest import ROOT, build_native, golden_bytes, golden_json, gen_logtext
+
+
+@pytest.fixture(scope="module")
+def shim():
+    L = build_native("parse_shim", ["tests/native/parse_shim.cpp"])
+    L.parse_shim.restype = C.c_int
+    L.parse_shim.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    return L
+
+
+def test_parser_matches_reference_golden(shim):
+    """The product's D1 state machine returns exactly what LZ4_decompress_safe returned."""
+    for v in golden_json("lz4_decode.json"):
+        src = bytes.fromhex(v["hex"])
+        r = shim.parse_shim(src if src else None, len(src), v["cap"], None, None, None) if src else \
+            shim.parse_shim(b"", 0, v["cap"], None, None, None)
+        assert r == v["ret"], (v["hex"][:40], v["cap"], r, v["ret"])
+
+
+def test_parser_matches_oracle_fuzz(shim, ora, pkg):
+    rng = random.Random(3)
+    text = gen_logtext(pkg, 200000)
+    for it in range(30):
+        n = rng.choice([13, 64, 200, 5000, 70000, 200000])
+        comp = ora.lz4_compress(text[:n])
+        nt = C.c_int()
+        assert shim.parse_shim(comp, len(comp), n, C.byref(nt), None, None) == n and nt.value >= 1
+        for k in range(60):
+            m = bytearray(comp)
+            i = rng.randrange(len(m))
+            if k % 3 == 0:
+                m[i] = rng.getrandbits(8)
+            elif k % 3 == 1:
+                m = m[:i]
+            else:
+                m[i:i] = bytes([rng.choice([0, 255, 0xF0, 0x0F])])
+            m = bytes(m)
+            for cap in (n, n + 50, 4 << 20):
+                assert shim.parse_shim(m, len(m), cap, None, None, None) == ora.lz4_decompress(m, cap)[0]
+
+
+def test_generator_deterministic(pkg):
+    a = gen_logtext(pkg, 3 * 4096 + 100)
+    b = gen_logtext(pkg, 4096, first_page=2)
+    assert a[2 * 4096:3 * 4096] == b
+    assert a[:11] == b"1700000002 " or a[:4] == b"1700"
+    assert a == golden_bytes("logtext_128k.bin")[:len(a)]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    L = build_native("enc_emul", ["tests/native/enc_emul.cpp"])
+    L.enc_emul_block.restype = C.c_int
+    L.enc_emul_block.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    return L
+
+
+@pytest.mark.parametrize("n", [0, 1, 12, 13, 14, 131, 132, 133, 65535, 65536, 65537, 65549, 200000, 4194304 - 1, 4194304])
+def test_encode_algorithm_roundtrip(emul, ora, pkg, n):
+    """Sequential emulation of lz4_region_kernel + block write: output decodes to the input."""
+    text = gen_logtext(pkg, 4 * 1024 * 1024)
+    for name, src in (("text", text[:n]), ("zeros", bytes(n)), ("period", (b"abcdefg" * (n // 7 + 1))[:n])):
+        dst = C.create_string_buffer(n + n // 255 + 128)
+        c = emul.enc_emul_block(src, n, dst, 5)
+        assert ora.lz4_decompress(dst.raw[:c], n) == (n, src), (name, n)
+
+
+def test_encode_algorithm_ratio(emul, pkg):
+    text = gen_logtext(pkg, 4 * 1024 * 1024)
+    dst = C.create_string_buffer(len(text) + len(text) // 255 + 128)
+    c = emul.enc_emul_block(text, len(text), dst, 5)
+    assert len(text) / c > 2.0          # the reference's LZ4_compress_default gives 2.02 on this input
+
+
+def test_abi_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "fourmc.h")).read()
+    declared = sorted(set(re.findall(r"\b(fourmc_[a-z0-9_]+)\s*\(", hdr)) - {"fourmc_ctx"})
+    assert len(declared) >= 20
+    L = pkg.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_no_cpu_fallback_without_device(pkg):
+    """Without a CUDA device the product fails loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.FourMcError) as e:
+        pkg.Context(0)
+    assert e.value.code == pkg.E_CUDA
+    assert pkg.lib().fourmc_lz4_compress_bound(4 * 1024 * 1024) == 4210768   # lz4.h:212
+
+
+def test_shard_blocks(pkg):
+    for nb in (0, 1, 7, 8, 9, 16384, 4096 + 3):
+        for g in (1, 2, 4, 8):
+            ranges = [pkg.shard_blocks(nb, g, r) for r in range(g)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == nb
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
