@@ -183,6 +183,37 @@ class Context:
         return int(lib().fourmc_4mc_decompress_host(self._h, b, len(b), out, cap))
 
 
+    # ---- device-resident calls: raw device pointers (ints) and an optional CUDA stream handle ----
+    def gen_device(self, d_out: int, n_pages: int, seed: int = 0x4D43, first_page: int = 0, kind: int = 0, stream=None):
+        self._check(lib().fourmc_gen_device(self._h, stream, kind, seed, first_page, n_pages, d_out))
+
+    def compress_device(self, d_in: int, n: int, d_out: int, out_capacity: int, d_out_size: int,
+                        d_block_lens: int | None = None, level: int = 1, stream=None):
+        self._check(lib().fourmc_4mc_compress_device(self._h, stream, level, d_in, n, d_out, out_capacity,
+                                                     d_out_size, d_block_lens))
+
+    def compress_span_device(self, d_in: int, n: int, d_span: int, span_capacity: int, d_span_size: int,
+                             d_block_lens: int | None = None, level: int = 1, stream=None):
+        self._check(lib().fourmc_4mc_compress_span_device(self._h, stream, level, d_in, n, d_span, span_capacity,
+                                                          d_span_size, d_block_lens))
+
+    def build_index_device(self, d_block_lens: int, n_blocks: int, d_header: int | None, d_tail: int, stream=None):
+        self._check(lib().fourmc_4mc_build_index_device(self._h, stream, d_block_lens, n_blocks, d_header, d_tail))
+
+    def decompress_device(self, d_in: int, n: int, d_out: int, out_capacity: int, d_result: int, stream=None):
+        self._check(lib().fourmc_4mc_decompress_device(self._h, stream, d_in, n, d_out, out_capacity, d_result))
+
+    def xxh32_batch_device(self, n_items: int, d_base: int, d_off: int, d_len: int, d_out: int, seed: int = 0, stream=None):
+        self._check(lib().fourmc_xxh32_batch_device(self._h, stream, n_items, d_base, d_off, d_len, seed, d_out))
+
+    def compress_host_ptr(self, in_ptr: int, n: int, out_ptr: int, cap: int, level: int = 1) -> int:
+        """fourmc_4mc_compress_host on raw host addresses (e.g. pinned torch tensors)."""
+        return self._check(lib().fourmc_4mc_compress_host(self._h, level, in_ptr, n, out_ptr, cap))
+
+    def decompress_host_ptr(self, in_ptr: int, n: int, out_ptr: int, cap: int) -> int:
+        return self._check(lib().fourmc_4mc_decompress_host(self._h, in_ptr, n, out_ptr, cap))
+
+
 # ---- reference-shaped facades ---------------------------------------------------------------
 
 class Lz4Compressor:

@@ -575,6 +575,7 @@ int fourmc_lz4_compress(fourmc_ctx *ctx, int level, const void *src, int src_siz
 int fourmc_lz4_decompress_safe(fourmc_ctx *ctx, const void *src, int compressed_size, void *dst, int dst_capacity)
 {
     if (!ctx) return FOURMC_E_ARG;
+    ctx->err.clear();                                  // -10 / -11 are also legal LZ4 error values
     if (!src || dst_capacity < 0) return -1;                                        // lz4.c:1951
     if (dst_capacity == 0) return (compressed_size == 1 && ((const uint8_t *)src)[0] == 0) ? 0 : -1;   // :1977-1981
     if (compressed_size <= 0) return -1;                                            // :1982

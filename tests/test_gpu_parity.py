@@ -1,0 +1,239 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI of lib4mcgpu.so, against the oracle,
+the committed golden vectors (outputs of the reference) and -- where oracle/_ref travelled -- the
+reference CLI itself.  Bit-exact throughout (integer / byte work)."""
+import ctypes as C
+import random
+import subprocess
+
+import pytest
+
+from conftest import golden_bytes, golden_json, gen_logtext
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------- XXH32
+
+def test_xxh32_golden(ctx, lcg):
+    for v in golden_json("xxh32.json"):
+        data = bytes.fromhex(v["hex"]) if "hex" in v else lcg[v["lcg_off"]:v["lcg_off"] + v["lcg_len"]]
+        assert ctx.xxh32(data, v["seed"]) == v["xxh32"], v
+
+
+def test_xxh32_vs_oracle_large(ctx, ora, pkg):
+    text = gen_logtext(pkg, 4 * 1024 * 1024)
+    for n in (4 * 1024 * 1024, 4 * 1024 * 1024 - 1, 2035746, 2048, 2049, 2063, 2064, 2065, 4095):
+        for off in (0, 1, 7, 12):
+            assert ctx.xxh32(text[off:off + n - off]) == ora.xxh32(text[off:off + n - off])
+
+
+def test_xxh32_batch_device(ctx, ora, pkg):
+    import torch
+    data = gen_logtext(pkg, 1 << 20)
+    t = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    rng = random.Random(9)
+    items = [(rng.randrange(0, 1 << 19), rng.choice([0, 1, 15, 16, 17, 100, 4096, 70001, 1 << 19])) for _ in range(300)]
+    off = torch.tensor([o for o, _ in items], dtype=torch.int64).cuda()
+    ln = torch.tensor([l for _, l in items], dtype=torch.int32).cuda()
+    out = torch.zeros(len(items), dtype=torch.int32).cuda()
+    ctx.xxh32_batch_device(len(items), t.data_ptr(), off.data_ptr(), ln.data_ptr(), out.data_ptr(), seed=0,
+                           stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = [x & 0xFFFFFFFF for x in out.cpu().tolist()]
+    assert got == [ora.xxh32(data[o:o + l]) for o, l in items]
+
+
+# ---------------------------------------------------------------- LZ4 decode
+
+def test_lz4_decode_golden(ctx, ora):
+    """Return value (incl. the exact negative code) and bytes equal LZ4_decompress_safe's."""
+    for v in golden_json("lz4_decode.json"):
+        src = bytes.fromhex(v["hex"])
+        r, out = ctx.lz4_decompress_safe(src, v["cap"])
+        assert r == v["ret"], (v["hex"][:40], v["cap"], r, v["ret"])
+        assert ora.xxh32(out) == v["out_xxh32"]
+
+
+def test_lz4_decode_vs_oracle_blocks(ctx, ora, pkg):
+    text = gen_logtext(pkg, 4 * 1024 * 1024)
+    rng = random.Random(4)
+    cases = [text, text[:4194303], text[:65537], bytes(4 * 1024 * 1024), (b"abcdefg" * 600000)[:4 * 1024 * 1024],
+             bytes(rng.getrandbits(8) for _ in range(100000)) + text[:200000],
+             b"".join(bytes([rng.getrandbits(8)]) * rng.choice([1, 2, 3, 40, 300, 5000]) for _ in range(3000))]
+    for src in cases:
+        comp = ora.lz4_compress(src)
+        for cap in (len(src), 4 * 1024 * 1024):
+            if cap < len(src):
+                continue
+            r, out = ctx.lz4_decompress_safe(comp, cap)
+            assert r == len(src) and out == src
+        # capacity one short: the reference fails, with a specific code
+        if len(src) > 64:
+            assert ctx.lz4_decompress_safe(comp, len(src) - 1)[0] == ora.lz4_decompress(comp, len(src) - 1)[0]
+
+
+def test_lz4_decode_mutations_vs_oracle(ctx, ora, pkg):
+    rng = random.Random(8)
+    text = gen_logtext(pkg, 100000)
+    comp = ora.lz4_compress(text)
+    for k in range(150):
+        m = bytearray(comp)
+        i = rng.randrange(len(m))
+        if k % 3 == 0:
+            m[i] = rng.getrandbits(8)
+        elif k % 3 == 1:
+            m = m[:i + 1]
+        else:
+            m[i:i] = bytes([rng.choice([0, 255, 0xF0, 0x0F])])
+        m = bytes(m)
+        cap = rng.choice([len(text), len(text) + 50, 4 << 20])
+        r, out = ctx.lz4_decompress_safe(m, cap)
+        er, eout = ora.lz4_decompress(m, cap)
+        assert r == er and out == eout
+
+
+# ---------------------------------------------------------------- container decode
+
+def test_container_decode_golden(ctx):
+    text = golden_bytes("logtext_128k.bin")
+    for lvl in (1, 2, 3, 4):                      # reference-compressed at all four LZ4 levels
+        assert ctx.decompress_4mc(golden_bytes(f"logtext_128k.l{lvl}.4mc")) == text
+    assert ctx.decompress_4mc(golden_bytes("empty.4mc")) == b""
+    assert ctx.decompress_4mc(golden_bytes("A.4mc")) == b"A"
+    assert ctx.decompress_4mc(golden_bytes("zeros_4m1.4mc")) == bytes(4 * 1024 * 1024 + 1)
+    assert ctx.decompress_4mc(golden_bytes("random_70000.4mc")) == golden_bytes("random_70000.bin")
+    assert ctx.decompress_4mc(golden_bytes("two_streams.4mc")) == b"A" + text
+
+
+def test_container_decode_errors_match_reference_exit_codes(ctx, ora):
+    good = golden_bytes("logtext_128k.l1.4mc")
+    n = 128 * 1024
+    muts = []
+    for pos in (100, 9, 7, len(good) - 1, len(good) - 30, 14, 20, 5000):
+        b = bytearray(good); b[pos] ^= 0x10; muts.append(bytes(b))
+    muts += [good[:20], good[:30000], good[:-5], good.replace(b"4MC\0", b"4MZ\0", 1), good + good[:7]]
+    for m in muts:
+        assert ctx.decompress_4mc_rc(m) == ora.decompress_4mc(m, n + 16)[0]
+
+
+# ---------------------------------------------------------------- compress
+
+SIZES = [0, 1, 5, 12, 13, 14, 131, 132, 133, 4096, 65535, 65536, 65537, 65549, 131072 + 5, 200000,
+         4194304 - 1, 4194304, 4194304 + 1, 4194304 + 65536 + 7, 3 * 4194304 + 12345]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_compress_4mc_roundtrip_text(ctx, ora, pkg, n):
+    data = gen_logtext(pkg, n)
+    stream = ctx.compress_4mc(data)
+    r, out = ora.decompress_4mc(stream, n)            # oracle = reference reader semantics
+    assert r == n and out == data
+    assert ctx.decompress_4mc(stream) == data         # and our own reader
+
+
+def test_compress_4mc_special_inputs(ctx, ora):
+    rng = random.Random(2)
+    n = 4 * 1024 * 1024 + 70001
+    rnd = rng.randbytes(n)
+    cases = {"random": rnd, "zeros": bytes(n), "period7": (b"abcdefg" * (n // 7 + 1))[:n],
+             "mixed": rnd[:100000] + bytes(300000) + rnd[:50000] * 3 + b"xyz" * 100000}
+    for name, data in cases.items():
+        stream = ctx.compress_4mc(data)
+        r, out = ora.decompress_4mc(stream, len(data))
+        assert r == len(data) and out == data, name
+        assert ctx.decompress_4mc(stream) == data, name
+    # incompressible blocks are stored: file = input + 12 header + 12/block + 12 EOS + footer
+    s = ctx.compress_4mc(rnd)
+    assert len(s) == n + 12 + 2 * 12 + 12 + 20 + 2 * 4
+    # empty and 1-byte files are byte-identical to the reference's
+    assert ctx.compress_4mc(b"") == golden_bytes("empty.4mc")
+    assert ctx.compress_4mc(b"A") == golden_bytes("A.4mc")
+    assert ctx.compress_4mc(golden_bytes("random_70000.bin")) == golden_bytes("random_70000.4mc")
+
+
+def test_compress_ratio_not_worse_than_reference(ctx, pkg):
+    data = gen_logtext(pkg, 8 * 1024 * 1024)
+    assert len(data) / len(ctx.compress_4mc(data)) > 2.0      # reference: 2.02 on this input
+
+
+def test_lz4_compress_block_api(ctx, ora, pkg):
+    text = gen_logtext(pkg, 4 * 1024 * 1024)
+    for n in (0, 1, 13, 100, 65536, 1000000, 4 * 1024 * 1024):
+        c = ctx.lz4_compress(text[:n])
+        assert c is not None and len(c) <= pkg.Lz4Compressor.compress_bound(n)
+        assert ora.lz4_decompress(c, n) == (n, text[:n])
+    rnd = random.Random(1).randbytes(100000)
+    c = ctx.lz4_compress(rnd)                               # bound-sized destination: always fits
+    assert ora.lz4_decompress(c, len(rnd)) == (len(rnd), rnd)
+    assert ctx.lz4_compress(rnd, capacity=len(rnd) - 1) is None      # native/4mc.c:301 -> stored
+
+
+def test_reference_cli_decodes_gpu_output(ctx, ref_cli, pkg, tmp_path):
+    data = gen_logtext(pkg, 9 * 1024 * 1024 + 4321) + bytes(100000) + random.Random(3).randbytes(4 * 1024 * 1024 + 5)
+    p, q = tmp_path / "g.4mc", tmp_path / "g.out"
+    p.write_bytes(ctx.compress_4mc(data))
+    subprocess.run([ref_cli, "-f", "-q", "-q", "-d", str(p), str(q)], check=True)
+    assert q.read_bytes() == data
+
+
+def test_gpu_decodes_reference_cli_output(ctx, ref_cli, pkg, tmp_path):
+    data = gen_logtext(pkg, 9 * 1024 * 1024 + 4321) + bytes(100000)
+    p = tmp_path / "r.bin"
+    p.write_bytes(data)
+    for lvl in (1, 2, 3, 4):
+        q = tmp_path / f"r{lvl}.4mc"
+        subprocess.run([ref_cli, "-f", "-q", "-q", f"-{lvl}", str(p), str(q)], check=True)
+        assert ctx.decompress_4mc(q.read_bytes()) == data
+
+
+# ---------------------------------------------------------------- device-resident pipeline
+
+def _device_roundtrip(ctx, pkg, n_bytes, seed=0x4D43):
+    import torch
+    st = torch.cuda.current_stream().cuda_stream
+    pages = (n_bytes + 4095) // 4096
+    src = torch.empty(pages * 4096, dtype=torch.uint8, device="cuda")
+    ctx.gen_device(src.data_ptr(), pages, seed=seed, stream=st)
+    cap = pkg.lib().fourmc_4mc_bound(n_bytes)
+    comp = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    size = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ctx.compress_device(src.data_ptr(), n_bytes, comp.data_ptr(), cap, size.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    csz = int(size.item())
+    out = torch.zeros(n_bytes + 16, dtype=torch.uint8, device="cuda")
+    res = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ctx.decompress_device(comp.data_ptr(), csz, out.data_ptr(), n_bytes, res.data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    return src, comp[:csz], out, res.cpu().tolist()
+
+
+@pytest.mark.parametrize("n", [4096, 4 * 1024 * 1024 + 4096, 64 * 1024 * 1024, 1024 * 1024 * 1024 + 8192])
+def test_device_roundtrip(ctx, ora, pkg, n):
+    import torch
+    src, comp, out, res = _device_roundtrip(ctx, pkg, n)
+    assert res == [n, -1]
+    assert torch.equal(out[:n], src[:n])
+    assert n / comp.numel() > 1.9
+    if n <= 64 * 1024 * 1024:
+        # the generator on the device equals the host generator; the stream decodes with the oracle
+        host = gen_logtext(pkg, n)
+        assert bytes(src[:n].cpu().numpy().tobytes()) == host
+        r, o = ora.decompress_4mc(comp.cpu().numpy().tobytes(), n)
+        assert r == n and o == host
+
+
+def test_device_decode_detects_corruption(ctx, pkg):
+    import torch
+    n = 16 * 1024 * 1024
+    src, comp, out, res = _device_roundtrip(ctx, pkg, n)
+    st = torch.cuda.current_stream().cuda_stream
+    for pos, expect_block in ((5 * 1024 * 1024, None), (30, 0)):
+        bad = comp.clone()
+        bad[pos] ^= 0x40
+        r = torch.zeros(2, dtype=torch.int64, device="cuda")
+        ctx.decompress_device(bad.data_ptr(), bad.numel(), out.data_ptr(), n, r.data_ptr(), stream=st)
+        torch.cuda.synchronize()
+        code, blk = r.cpu().tolist()
+        assert code == pkg.E_CONTENT and blk >= 0
+        if expect_block is not None:
+            assert blk == expect_block
