@@ -174,11 +174,10 @@ class Context:
         self._check(rc)
         return out.raw[:rc]
 
-    def decompress_4mc_rc(self, stream) -> int:
+    def decompress_4mc_rc(self, stream, capacity: int) -> int:
         """Only the status / decoded size (negative FOURMC_E_* on failure), no exception."""
         b = _buf(stream)
-        size = lib().fourmc_4mc_decoded_size_host(b, len(b))
-        cap = max(int(size), 0)
+        cap = capacity
         out = C.create_string_buffer(max(cap, 1))
         return int(lib().fourmc_4mc_decompress_host(self._h, b, len(b), out, cap))
 

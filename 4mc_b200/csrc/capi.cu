@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -70,11 +71,29 @@ int fail(fourmc_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
         if (e__ != cudaSuccess) return fail(ctx, FOURMC_E_CUDA, #call, e__);          \
     } while (0)
 
+// development aid (FOURMC_PROFILE=1): serialises every launch and prints its wall time
+bool profile_mode()
+{
+    static int v = -1;
+    if (v < 0) v = getenv("FOURMC_PROFILE") ? 1 : 0;
+    return v == 1;
+}
+void profile_mark(const char *what)
+{
+    static double last = 0;
+    cudaDeviceSynchronize();
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double now = ts.tv_sec * 1e3 + ts.tv_nsec / 1e6;
+    fprintf(stderr, "[fourmc profile] %-28s %9.3f ms\n", what, last ? now - last : 0.0);
+    last = now;
+}
+
 #define CKL(what)                                                                     \
     do {                                                                              \
         ctx->launches++;                                                              \
         cudaError_t e__ = cudaGetLastError();                                         \
         if (e__ != cudaSuccess) return fail(ctx, FOURMC_E_CUDA, what, e__);           \
+        if (profile_mode()) profile_mark(what);                                       \
     } while (0)
 
 int ensure(fourmc_ctx *ctx, DevBuf &b, size_t need)
@@ -189,7 +208,7 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
                 desc, (const uint32_t *)ws.xxh.p, nb, status);
             CKL("xxh_verify_kernel");
         }
-        lz4_parse_kernel<<<(nb + 31) / 32, 32, 0, st>>>(desc, nb, (uint32_t *)ws.tokmap.p, (uint32_t *)ws.chunkop.p,
+        lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, 0, st>>>(desc, nb, (uint32_t *)ws.tokmap.p, (uint32_t *)ws.chunkop.p,
                                                        (int32_t *)ws.result.p);
         CKL("lz4_parse_kernel");
         for (uint32_t b0 = 0; b0 < nb; b0 += 32768) {

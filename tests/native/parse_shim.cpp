@@ -8,10 +8,10 @@ namespace {
 struct Rec { std::vector<int> pos, op; void token(int p, int o) { pos.push_back(p); op.push_back(o); } };
 }
 
-extern "C" int parse_shim(const uint8_t *src, int n, int cap, int *n_tokens, long long *pos_sum, long long *op_sum)
+extern "C" int parse_shim(const uint8_t *src, int n, int cap, int *n_tokens, long long *pos_sum, long long *op_sum, int step)
 {
     Rec r;
-    const int ret = fm::lz4_parse_block(src, n, cap, r);
+    const int ret = fm::lz4_parse_block(src, n, cap, r, step > 0 ? step : 0x7fffffff);
     long long ps = 0, os = 0;
     for (size_t i = 0; i < r.pos.size(); i++) { ps += r.pos[i]; os += r.op[i]; }
     if (n_tokens) *n_tokens = (int)r.pos.size();

@@ -36,6 +36,7 @@ def test_xxh32_batch_device(ctx, ora, pkg):
     off = torch.tensor([o for o, _ in items], dtype=torch.int64).cuda()
     ln = torch.tensor([l for _, l in items], dtype=torch.int32).cuda()
     out = torch.zeros(len(items), dtype=torch.int32).cuda()
+    torch.cuda.synchronize()
     ctx.xxh32_batch_device(len(items), t.data_ptr(), off.data_ptr(), ln.data_ptr(), out.data_ptr(), seed=0,
                            stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
@@ -113,7 +114,7 @@ def test_container_decode_errors_match_reference_exit_codes(ctx, ora):
         b = bytearray(good); b[pos] ^= 0x10; muts.append(bytes(b))
     muts += [good[:20], good[:30000], good[:-5], good.replace(b"4MC\0", b"4MZ\0", 1), good + good[:7]]
     for m in muts:
-        assert ctx.decompress_4mc_rc(m) == ora.decompress_4mc(m, n + 16)[0]
+        assert ctx.decompress_4mc_rc(m, n + 16) == ora.decompress_4mc(m, n + 16)[0]
 
 
 # ---------------------------------------------------------------- compress
@@ -190,18 +191,19 @@ def test_gpu_decodes_reference_cli_output(ctx, ref_cli, pkg, tmp_path):
 
 def _device_roundtrip(ctx, pkg, n_bytes, seed=0x4D43):
     import torch
-    st = torch.cuda.current_stream().cuda_stream
+    st = None                              # the context's own stream
     pages = (n_bytes + 4095) // 4096
     src = torch.empty(pages * 4096, dtype=torch.uint8, device="cuda")
-    ctx.gen_device(src.data_ptr(), pages, seed=seed, stream=st)
     cap = pkg.lib().fourmc_4mc_bound(n_bytes)
     comp = torch.empty(cap, dtype=torch.uint8, device="cuda")
     size = torch.zeros(1, dtype=torch.int64, device="cuda")
+    out = torch.zeros(n_bytes + 16, dtype=torch.uint8, device="cuda")
+    res = torch.zeros(2, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()               # torch's fills run on another stream than the context's
+    ctx.gen_device(src.data_ptr(), pages, seed=seed, stream=st)
     ctx.compress_device(src.data_ptr(), n_bytes, comp.data_ptr(), cap, size.data_ptr(), stream=st)
     torch.cuda.synchronize()
     csz = int(size.item())
-    out = torch.zeros(n_bytes + 16, dtype=torch.uint8, device="cuda")
-    res = torch.zeros(2, dtype=torch.int64, device="cuda")
     ctx.decompress_device(comp.data_ptr(), csz, out.data_ptr(), n_bytes, res.data_ptr(), stream=st)
     torch.cuda.synchronize()
     return src, comp[:csz], out, res.cpu().tolist()
@@ -226,11 +228,12 @@ def test_device_decode_detects_corruption(ctx, pkg):
     import torch
     n = 16 * 1024 * 1024
     src, comp, out, res = _device_roundtrip(ctx, pkg, n)
-    st = torch.cuda.current_stream().cuda_stream
+    st = None
     for pos, expect_block in ((5 * 1024 * 1024, None), (30, 0)):
         bad = comp.clone()
         bad[pos] ^= 0x40
         r = torch.zeros(2, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
         ctx.decompress_device(bad.data_ptr(), bad.numel(), out.data_ptr(), n, r.data_ptr(), stream=st)
         torch.cuda.synchronize()
         code, blk = r.cpu().tolist()

@@ -14,7 +14,7 @@ from conftest import ROOT, build_native, golden_bytes, golden_json, gen_logtext
 def shim():
     L = build_native("parse_shim", ["tests/native/parse_shim.cpp"])
     L.parse_shim.restype = C.c_int
-    L.parse_shim.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+    L.parse_shim.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]
     return L
 
 
@@ -22,9 +22,9 @@ def test_parser_matches_reference_golden(shim):
     """The product's D1 state machine returns exactly what LZ4_decompress_safe returned."""
     for v in golden_json("lz4_decode.json"):
         src = bytes.fromhex(v["hex"])
-        r = shim.parse_shim(src if src else None, len(src), v["cap"], None, None, None) if src else \
-            shim.parse_shim(b"", 0, v["cap"], None, None, None)
-        assert r == v["ret"], (v["hex"][:40], v["cap"], r, v["ret"])
+        for step in (0, 1, 7, 2048):            # the parser is resumable at any sequence boundary
+            r = shim.parse_shim(src, len(src), v["cap"], None, None, None, step)
+            assert r == v["ret"], (v["hex"][:40], v["cap"], step, r, v["ret"])
 
 
 def test_parser_matches_oracle_fuzz(shim, ora, pkg):
@@ -34,7 +34,7 @@ def test_parser_matches_oracle_fuzz(shim, ora, pkg):
         n = rng.choice([13, 64, 200, 5000, 70000, 200000])
         comp = ora.lz4_compress(text[:n])
         nt = C.c_int()
-        assert shim.parse_shim(comp, len(comp), n, C.byref(nt), None, None) == n and nt.value >= 1
+        assert shim.parse_shim(comp, len(comp), n, C.byref(nt), None, None, 0) == n and nt.value >= 1
         for k in range(60):
             m = bytearray(comp)
             i = rng.randrange(len(m))
@@ -46,7 +46,7 @@ def test_parser_matches_oracle_fuzz(shim, ora, pkg):
                 m[i:i] = bytes([rng.choice([0, 255, 0xF0, 0x0F])])
             m = bytes(m)
             for cap in (n, n + 50, 4 << 20):
-                assert shim.parse_shim(m, len(m), cap, None, None, None) == ora.lz4_decompress(m, cap)[0]
+                assert shim.parse_shim(m, len(m), cap, None, None, None, [0, 3, 100][k % 3]) == ora.lz4_decompress(m, cap)[0]
 
 
 def test_generator_deterministic(pkg):

@@ -15,7 +15,9 @@ def main():
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     n = int(gib * (1 << 30)) // 4096 * 4096
     ctx = pkg.Context(0)
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream()          # a real (non-default) stream: handle 0 would mean "context stream"
+    torch.cuda.set_stream(stream)
+    st = stream.cuda_stream
     src = torch.empty(n, dtype=torch.uint8, device="cuda")
     t0 = time.time()
     ctx.gen_device(src.data_ptr(), n // 4096, stream=st)
