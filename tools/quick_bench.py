@@ -42,8 +42,13 @@ def main():
         tc = e[0].elapsed_time(e[1]) if False else None
         print(f"iter {it}: csize {csz} ratio {n / csz:.3f} result {res.cpu().tolist()}")
     # separate clean timings
-    for name, fn in (("compress", lambda: ctx.compress_device(src.data_ptr(), n, comp.data_ptr(), cap, size.data_ptr(), stream=st)),
-                     ("decompress", lambda: ctx.decompress_device(comp.data_ptr(), csz, out.data_ptr(), n, res.data_ptr(), stream=st))):
+    def comp_fn():
+        ctx.compress_device(src.data_ptr(), n, comp.data_ptr(), cap, size.data_ptr(), stream=st)
+
+    def dec_fn():
+        ctx.decompress_device(comp.data_ptr(), int(size.item()), out.data_ptr(), n, res.data_ptr(), stream=st)
+
+    for name, fn in (("compress", comp_fn), ("decompress", dec_fn)):
         ts = []
         for it in range(iters):
             torch.cuda.synchronize()
@@ -52,7 +57,7 @@ def main():
             ts.append(e[0].elapsed_time(e[1]))
         best = min(ts)
         print(f"{name}: best {best:.2f} ms  -> {n / best / 1e6:.1f} GB/s (uncompressed)   all: {[round(t, 2) for t in ts]}")
-    print("equal:", bool(torch.equal(out, src)))
+    print("equal:", bool(torch.equal(out, src)), "result", res.cpu().tolist())
 
 
 if __name__ == "__main__":
