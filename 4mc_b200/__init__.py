@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
         "fourmc_last_error": (C.c_char_p, [vp]),
         "fourmc_kernel_launches": (u64, [vp]),
         "fourmc_sync": (i32, [vp, vp]),
+        "fourmc_timing_enable": (i32, [vp, i32]),
+        "fourmc_timing_collect": (C.c_longlong, [vp, C.c_char_p, sz]),
         "fourmc_lz4_compress_bound": (i32, [i32]),
         "fourmc_lz4_compress": (i32, [vp, i32, vp, i32, vp, i32]),
         "fourmc_lz4_decompress_safe": (i32, [vp, vp, i32, vp, i32]),
@@ -129,6 +131,19 @@ class Context:
 
     def sync(self, stream=None):
         self._check(lib().fourmc_sync(self._h, stream))
+
+    def timing_enable(self, on: bool = True):
+        self._check(lib().fourmc_timing_enable(self._h, 1 if on else 0))
+
+    def timing_collect(self) -> dict:
+        """{kernel name: (launches, total ms)} since the last collect; synchronises the device."""
+        buf = C.create_string_buffer(1 << 16)
+        n = self._check(lib().fourmc_timing_collect(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.raw[:n].decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
 
     # ---- per block, host buffers (what the JNI natives and the CLI loop call) ----
     def xxh32(self, data, seed: int = 0) -> int:

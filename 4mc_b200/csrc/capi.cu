@@ -52,6 +52,11 @@ struct fourmc_ctx {
     void *pinned = nullptr;              // small pinned scratch for scalars
     size_t pinned_cap = 0;
     bool region_attr_set = false;
+    // optional per-kernel timing (fourmc_timing_enable): CUDA event pairs around every launch
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;        // pool: [2i] start, [2i+1] stop
+    std::vector<const char *> tname;     // kernel name of pair i
+    size_t tused = 0;
 };
 
 namespace {
@@ -94,6 +99,32 @@ void profile_mark(const char *what)
         cudaError_t e__ = cudaGetLastError();                                         \
         if (e__ != cudaSuccess) return fail(ctx, FOURMC_E_CUDA, what, e__);           \
         if (profile_mode()) profile_mark(what);                                       \
+    } while (0)
+
+void ktime_mark(fourmc_ctx *ctx, const char *name, cudaStream_t st, int which)
+{
+    if (!ctx->timing) return;
+    if (which == 0) {
+        if (ctx->tused * 2 + 2 > ctx->tev.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            ctx->tev.push_back(a); ctx->tev.push_back(b); ctx->tname.push_back(name);
+        }
+        ctx->tname[ctx->tused] = name;
+        cudaEventRecord(ctx->tev[ctx->tused * 2], st);
+    } else {
+        cudaEventRecord(ctx->tev[ctx->tused * 2 + 1], st);
+        ctx->tused++;
+    }
+}
+
+// KL(name, stream, kernel<<<...>>>(...)): launch with optional event timing and error check
+#define KL(name, st, ...)                                                             \
+    do {                                                                              \
+        ktime_mark(ctx, name, st, 0);                                                 \
+        __VA_ARGS__;                                                                  \
+        ktime_mark(ctx, name, st, 1);                                                 \
+        CKL(name);                                                                    \
     } while (0)
 
 int ensure(fourmc_ctx *ctx, DevBuf &b, size_t need)
@@ -172,19 +203,15 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     P.work_counter = (uint32_t *)ws.misc.p;
     P.min_match = level_min_match(level);
     const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
-    lz4_region_kernel<<<grid, ENC_THREADS, ENC_SMEM, st>>>(P);
-    CKL("lz4_region_kernel");
+    KL("lz4_region_kernel", st, lz4_region_kernel<<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
     uint32_t *lens = d_block_lens_out ? d_block_lens_out : (uint32_t *)ws.lens.p;
-    lz4_block_size_kernel<<<(nb + 127) / 128, 128, 0, st>>>((const RegionMeta *)ws.meta.p, nb, n,
-                                                           (BlockPlan *)ws.plan.p, lens, raw_limit);
-    CKL("lz4_block_size_kernel");
-    scan_lens_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, base, (uint64_t *)ws.off.p,
-                                                 (uint64_t *)((uint8_t *)ws.misc.p + 8));
-    CKL("scan_lens_kernel");
-    lz4_block_write_kernel<<<nb, ENC_WRITE_THREADS, 0, st>>>(d_in, (const uint8_t *)ws.scratch.p,
+    KL("lz4_block_size_kernel", st, lz4_block_size_kernel<<<(nb + 127) / 128, 128, 0, st>>>((const RegionMeta *)ws.meta.p, nb, n,
+                                                           (BlockPlan *)ws.plan.p, lens, raw_limit));
+    KL("scan_lens_kernel", st, scan_lens_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, base, (uint64_t *)ws.off.p,
+                                                 (uint64_t *)((uint8_t *)ws.misc.p + 8)));
+    KL("lz4_block_write_kernel", st, lz4_block_write_kernel<<<nb, ENC_WRITE_THREADS, 0, st>>>(d_in, (const uint8_t *)ws.scratch.p,
                                                              (const RegionMeta *)ws.meta.p, (const BlockPlan *)ws.plan.p,
-                                                             (const uint64_t *)ws.off.p, d_out_base, raw_limit >= 0 ? 1 : 0);
-    CKL("lz4_block_write_kernel");
+                                                             (const uint64_t *)ws.off.p, d_out_base, raw_limit >= 0 ? 1 : 0));
     return FOURMC_OK;
 }
 
@@ -204,25 +231,20 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
         const BlockDesc *desc = (const BlockDesc *)ws.desc.p;
         uint8_t *status = (uint8_t *)ws.status.p;
         if (check_xxh) {
-            xxh_verify_kernel<<<(nb + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, st>>>(
-                desc, (const uint32_t *)ws.xxh.p, nb, status);
-            CKL("xxh_verify_kernel");
+            KL("xxh_verify_kernel", st, xxh_verify_kernel<<<(nb + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, st>>>(
+                desc, (const uint32_t *)ws.xxh.p, nb, status));
         }
-        lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, 0, st>>>(desc, nb, (uint32_t *)ws.tokmap.p, (uint32_t *)ws.chunkop.p,
-                                                       (int32_t *)ws.result.p);
-        CKL("lz4_parse_kernel");
+        KL("lz4_parse_kernel", st, lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, 0, st>>>(desc, nb, (uint32_t *)ws.tokmap.p, (uint32_t *)ws.chunkop.p,
+                                                       (int32_t *)ws.result.p));
         for (uint32_t b0 = 0; b0 < nb; b0 += 32768) {
             const uint32_t cnt = std::min<uint32_t>(32768, nb - b0);
-            lz4_stored_kernel<<<dim3(32, cnt), 256, 0, st>>>(desc + b0, cnt);
-            CKL("lz4_stored_kernel");
+            KL("lz4_stored_kernel", st, lz4_stored_kernel<<<dim3(32, cnt), 256, 0, st>>>(desc + b0, cnt));
         }
-        lz4_copy_kernel<<<nb, LZ4_COPY_WARPS * 32, 0, st>>>(desc, (const uint32_t *)ws.tokmap.p,
-                                                            (const uint32_t *)ws.chunkop.p, (const int32_t *)ws.result.p);
-        CKL("lz4_copy_kernel");
+        KL("lz4_copy_kernel", st, lz4_copy_kernel<<<nb, LZ4_COPY_WARPS * 32, 0, st>>>(desc, (const uint32_t *)ws.tokmap.p,
+                                                            (const uint32_t *)ws.chunkop.p, (const int32_t *)ws.result.p));
     }
-    finalize_kernel<<<1, SCAN_THREADS, 0, st>>>((const BlockDesc *)ws.desc.p, (const int32_t *)ws.result.p, nb,
-                                                (uint8_t *)ws.status.p, d_out_size, d_info, d_result);
-    CKL("finalize_kernel");
+    KL("finalize_kernel", st, finalize_kernel<<<1, SCAN_THREADS, 0, st>>>((const BlockDesc *)ws.desc.p, (const int32_t *)ws.result.p, nb,
+                                                (uint8_t *)ws.status.p, d_out_size, d_info, d_result));
     return FOURMC_OK;
 }
 
@@ -334,6 +356,7 @@ void fourmc_ctx_destroy(fourmc_ctx *ctx)
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     }
+    for (auto e : ctx->tev) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -348,6 +371,39 @@ int fourmc_sync(fourmc_ctx *ctx, void *stream)
     if (!ctx) return FOURMC_E_ARG;
     CK(cudaStreamSynchronize(pick(ctx, stream)));
     return FOURMC_OK;
+}
+
+int fourmc_timing_enable(fourmc_ctx *ctx, int on)
+{
+    if (!ctx) return FOURMC_E_ARG;
+    ctx->timing = on != 0;
+    ctx->tused = 0;
+    return FOURMC_OK;
+}
+
+long long fourmc_timing_collect(fourmc_ctx *ctx, char *buf, size_t cap)
+{
+    if (!ctx || !buf || cap == 0) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    struct Acc { const char *name; int count; double ms; };
+    std::vector<Acc> acc;
+    for (size_t i = 0; i < ctx->tused; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->tev[2 * i], ctx->tev[2 * i + 1]) != cudaSuccess) continue;
+        bool found = false;
+        for (auto &a : acc) if (!strcmp(a.name, ctx->tname[i])) { a.count++; a.ms += ms; found = true; break; }
+        if (!found) acc.push_back(Acc{ctx->tname[i], 1, ms});
+    }
+    ctx->tused = 0;
+    size_t pos = 0;
+    buf[0] = 0;
+    for (auto &a : acc) {
+        const int w = snprintf(buf + pos, cap - pos, "%s %d %.6f\n", a.name, a.count, a.ms);
+        if (w < 0 || (size_t)w >= cap - pos) break;
+        pos += (size_t)w;
+    }
+    return (long long)pos;
 }
 
 int fourmc_lz4_compress_bound(int n)
@@ -386,9 +442,8 @@ int fourmc_4mc_build_index_device(fourmc_ctx *ctx, void *stream, const uint32_t 
     if (!ctx || !d_tail || (n_blocks && !d_block_lens)) return FOURMC_E_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
-    write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(d_block_lens, n_blocks, 12, FOURMC_MAGIC_4MC, (uint8_t *)d_header,
-                                                   (uint8_t *)d_tail, nullptr, nullptr);
-    CKL("write_index_kernel");
+    KL("write_index_kernel", st, write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(d_block_lens, n_blocks, 12, FOURMC_MAGIC_4MC, (uint8_t *)d_header,
+                                                   (uint8_t *)d_tail, nullptr, nullptr));
     return FOURMC_OK;
 }
 
@@ -406,10 +461,9 @@ int fourmc_4mc_compress_device(fourmc_ctx *ctx, void *stream, int level, const v
     uint32_t *lens = d_block_lens ? d_block_lens : (uint32_t *)ws.lens.p;
     // block b's header lands at d_out + 12 + sum of earlier record lengths
     if ((r = enc_span(ctx, st, ws, level, (const uint8_t *)d_in, n, (uint8_t *)d_out, 12, lens, -1))) return r;
-    write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, 12, FOURMC_MAGIC_4MC, (uint8_t *)d_out, (uint8_t *)d_out + 12,
+    KL("write_index_kernel", st, write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, 12, FOURMC_MAGIC_4MC, (uint8_t *)d_out, (uint8_t *)d_out + 12,
                                                    (const uint64_t *)((uint8_t *)ws.misc.p + 8),
-                                                   (uint64_t *)((uint8_t *)ws.misc.p + 16));
-    CKL("write_index_kernel");
+                                                   (uint64_t *)((uint8_t *)ws.misc.p + 16)));
     if (d_out_size)
         CK(cudaMemcpyAsync(d_out_size, (uint8_t *)ws.misc.p + 16, 8, cudaMemcpyDeviceToDevice, st));
     return FOURMC_OK;
@@ -452,10 +506,9 @@ int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in
     CK(cudaMemsetAsync(ws.desc.p, 0, (size_t)std::max<uint32_t>(nb, 1) * sizeof(BlockDesc), st));
     CK(cudaMemsetAsync(ws.status.p, 0, (size_t)std::max<uint32_t>(nb, 1), st));
     CK(cudaMemsetAsync(ws.xxh.p, 0, (size_t)std::max<uint32_t>(nb, 1) * 4, st));
-    read_index_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint8_t *)d_in, n, nb, (uint8_t *)d_out, out_capacity,
+    KL("read_index_kernel", st, read_index_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint8_t *)d_in, n, nb, (uint8_t *)d_out, out_capacity,
                                                   (BlockDesc *)ws.desc.p, (uint32_t *)ws.xxh.p, (uint8_t *)ws.status.p,
-                                                  (IndexInfo *)ws.info.p);
-    CKL("read_index_kernel");
+                                                  (IndexInfo *)ws.info.p));
     const size_t max_chunks = n / LZ4_CHUNK + nb + 1;
     return dec_blocks(ctx, st, ws, nb, max_chunks, 1, nullptr, (const IndexInfo *)ws.info.p, d_result);
 }
@@ -476,9 +529,8 @@ int fourmc_lz4_decompress_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n
     if ((r = ensure(ctx, ws.xxh, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
     if ((r = ensure(ctx, ws.status, (size_t)std::max<uint32_t>(nb, 1)))) return r;
     if (nb == 0) return FOURMC_OK;
-    build_desc_kernel<<<1, SCAN_THREADS, 0, st>>>(nb, (const uint8_t *)d_src, d_src_off, d_csize, d_usize,
-                                                  (uint8_t *)d_dst, d_dst_off, (BlockDesc *)ws.desc.p, (uint8_t *)ws.status.p);
-    CKL("build_desc_kernel");
+    KL("build_desc_kernel", st, build_desc_kernel<<<1, SCAN_THREADS, 0, st>>>(nb, (const uint8_t *)d_src, d_src_off, d_csize, d_usize,
+                                                  (uint8_t *)d_dst, d_dst_off, (BlockDesc *)ws.desc.p, (uint8_t *)ws.status.p));
     if (check_xxh) CK(cudaMemcpyAsync(ws.xxh.p, d_xxh, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
     // every compressed block has csize <= 4 MiB: bound the chunk count by that
     const size_t max_chunks = (size_t)nb * (FOURMC_BLOCKSIZE / LZ4_CHUNK + 1);
@@ -494,9 +546,8 @@ int fourmc_xxh32_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_items, c
     if (n_items == 0) return FOURMC_OK;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
-    xxh_batch_kernel<<<(n_items + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, st>>>(
-        (const uint8_t *)d_base, d_off, d_len, n_items, seed, d_out);
-    CKL("xxh_batch_kernel");
+    KL("xxh_batch_kernel", st, xxh_batch_kernel<<<(n_items + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, st>>>(
+        (const uint8_t *)d_base, d_off, d_len, n_items, seed, d_out));
     return FOURMC_OK;
 }
 
@@ -514,9 +565,8 @@ int fourmc_gen_device(fourmc_ctx *ctx, void *stream, int kind, uint64_t seed, ui
     const uint64_t max_grid = 1u << 30;
     for (uint64_t p0 = 0; p0 < n_pages; p0 += max_grid * 32) {
         const uint64_t cnt = std::min<uint64_t>(n_pages - p0, max_grid * 32);
-        gen_kernel<<<(unsigned)((cnt + 31) / 32), 32, smem, st>>>(kind, seed, first_page + p0, cnt,
-                                                                  (uint8_t *)d_out + p0 * FMG_PAGE);
-        CKL("gen_kernel");
+        KL("gen_kernel", st, gen_kernel<<<(unsigned)((cnt + 31) / 32), 32, smem, st>>>(kind, seed, first_page + p0, cnt,
+                                                                  (uint8_t *)d_out + p0 * FMG_PAGE));
     }
     return FOURMC_OK;
 }

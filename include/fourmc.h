@@ -55,6 +55,12 @@ void fourmc_ctx_destroy(fourmc_ctx *ctx);
 const char *fourmc_last_error(const fourmc_ctx *ctx);
 /* Number of kernels this library has launched on the context since creation. */
 uint64_t fourmc_kernel_launches(const fourmc_ctx *ctx);
+/* Per-kernel device timing for benchmarks: while enabled, every launch is bracketed by a CUDA
+ * event pair on its own stream (no synchronisation).  fourmc_timing_collect() synchronises the
+ * device, writes one line "kernel_name launches total_ms\n" per kernel into buf, resets the
+ * counters and returns the text length. */
+int  fourmc_timing_enable(fourmc_ctx *ctx, int on);
+long long fourmc_timing_collect(fourmc_ctx *ctx, char *buf, size_t cap);
 /* Blocks until everything queued on the context's stream (or `stream`) has finished. */
 int  fourmc_sync(fourmc_ctx *ctx, void *stream);
 
