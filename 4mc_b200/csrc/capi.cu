@@ -234,7 +234,12 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             KL("xxh_verify_kernel", st, xxh_verify_kernel<<<(nb + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, st>>>(
                 desc, (const uint32_t *)ws.xxh.p, nb, status));
         }
-        KL("lz4_parse_kernel", st, lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, 0, st>>>(desc, nb, (uint32_t *)ws.tokmap.p, (uint32_t *)ws.chunkop.p,
+        static bool d1_attr = false;
+        if (!d1_attr) {
+            CK(cudaFuncSetAttribute(lz4_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D1_SMEM));
+            d1_attr = true;
+        }
+        KL("lz4_parse_kernel", st, lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, D1_SMEM, st>>>(desc, nb, (uint32_t *)ws.tokmap.p, (uint32_t *)ws.chunkop.p,
                                                        (int32_t *)ws.result.p));
         for (uint32_t b0 = 0; b0 < nb; b0 += 32768) {
             const uint32_t cnt = std::min<uint32_t>(32768, nb - b0);
@@ -260,7 +265,7 @@ build_desc_kernel(uint32_t nb, const uint8_t *src, const uint64_t *src_off, cons
         const bool live = i < nb;
         const uint32_t c = live ? csize[i] : 0, u = live ? usize[i] : 0;
         const bool toolarge = c > FOURMC_BLOCKSIZE || (c != u && u > FOURMC_BLOCKSIZE);
-        const uint32_t nch = (live && !toolarge && c != u) ? (c + LZ4_CHUNK - 1) / LZ4_CHUNK : 0;
+        const uint32_t nch = (live && !toolarge && c != u) ? (c + 15 + LZ4_CHUNK - 1) / LZ4_CHUNK : 0;
         unsigned long long total;
         const unsigned long long incl = cta_incl_scan_u64(nch, tmp, &total);
         if (live) {
@@ -509,7 +514,7 @@ int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in
     KL("read_index_kernel", st, read_index_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint8_t *)d_in, n, nb, (uint8_t *)d_out, out_capacity,
                                                   (BlockDesc *)ws.desc.p, (uint32_t *)ws.xxh.p, (uint8_t *)ws.status.p,
                                                   (IndexInfo *)ws.info.p));
-    const size_t max_chunks = n / LZ4_CHUNK + nb + 1;
+    const size_t max_chunks = n / LZ4_CHUNK + 2 * (size_t)nb + 2;
     return dec_blocks(ctx, st, ws, nb, max_chunks, 1, nullptr, (const IndexInfo *)ws.info.p, d_result);
 }
 
@@ -533,7 +538,7 @@ int fourmc_lz4_decompress_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n
                                                   (uint8_t *)d_dst, d_dst_off, (BlockDesc *)ws.desc.p, (uint8_t *)ws.status.p));
     if (check_xxh) CK(cudaMemcpyAsync(ws.xxh.p, d_xxh, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
     // every compressed block has csize <= 4 MiB: bound the chunk count by that
-    const size_t max_chunks = (size_t)nb * (FOURMC_BLOCKSIZE / LZ4_CHUNK + 1);
+    const size_t max_chunks = (size_t)nb * (FOURMC_BLOCKSIZE / LZ4_CHUNK + 2);
     if ((r = dec_blocks(ctx, st, ws, nb, max_chunks, check_xxh, d_out_size, nullptr, nullptr))) return r;
     if (d_status) CK(cudaMemcpyAsync(d_status, ws.status.p, nb, cudaMemcpyDeviceToDevice, st));
     return FOURMC_OK;
@@ -666,7 +671,7 @@ int fourmc_lz4_decompress_safe(fourmc_ctx *ctx, const void *src, int compressed_
     hd->csize = (uint32_t)compressed_size; hd->usize = (uint32_t)dst_capacity; hd->chunk_base = 0; hd->stored = 0;
     CK(cudaMemcpyAsync(ws.desc.p, hd, sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ws.status.p, 0, 16, st));
-    const size_t max_chunks = (size_t)compressed_size / LZ4_CHUNK + 2;
+    const size_t max_chunks = (size_t)compressed_size / LZ4_CHUNK + 3;
     if ((r = ensure(ctx, ws.outsize, 16))) return r;
     if ((r = dec_blocks(ctx, st, ws, 1, max_chunks, 0, (int32_t *)ws.outsize.p, nullptr, nullptr))) return r;
     int32_t *hr = (int32_t *)((uint8_t *)ctx->pinned + 256);

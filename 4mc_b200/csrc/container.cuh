@@ -186,7 +186,7 @@ read_index_kernel(const uint8_t *in, uint64_t n, uint32_t n_blocks_host, uint8_t
         const unsigned long long oincl = cta_incl_scan_u64(usable ? u : 0, tmp, &total);
         const unsigned long long dst_off = c_out + oincl - (usable ? u : 0);
         c_out += total;
-        const uint32_t nch = usable && c != u ? (c + LZ4_CHUNK - 1) / LZ4_CHUNK : 0;
+        const uint32_t nch = usable && c != u ? (c + 15 + LZ4_CHUNK - 1) / LZ4_CHUNK : 0;   // +15: aligned coordinates
         const unsigned long long cincl = cta_incl_scan_u64(nch, tmp, &total);
         const unsigned long long chunk_base = c_chunks + cincl - nch;
         c_chunks += total;

@@ -1,9 +1,8 @@
 // lz4_decode.cuh -- LZ4 block decode kernels (reference: LZ4_decompress_safe,
 // native/lz4/lz4.c:2345, called per block at native/4mc.c:661 and native/jniDecompressor.c:88).
 //
-//  D1  lz4_parse_kernel   one WARP per block: 32 lanes stream the payload through a shared-memory
-//                         ring, lane 0 walks the token chain (lz4_parse.h), decides the return
-//                         value, and leaves two small side tables in HBM:
+//  D1  lz4_parse_kernel   one WARP per block finds where every sequence starts, decides the return
+//                         value, and leaves two small side tables in HBM (details at the kernel):
 //                           tokmap   1 bit per compressed byte, set where a sequence's token sits
 //                           chunk_op u32 per 128 compressed bytes: output position of the first
 //                                    sequence whose token lies in that 128-byte chunk
@@ -43,29 +42,40 @@ struct BlockDesc {                         // one per block, built on the device
 
 // ---- D1 ------------------------------------------------------------------------------------
 
+// Token positions are recorded in ALIGNED coordinates q = ip + d, d = (payload address & 15), so
+// that the ring, the 2 KiB halves and the 128-byte D2 chunks all line up with 16-byte loads.
 struct TokSink {
     uint32_t *tokmap;      // block's first word
     uint32_t *chunk_op;    // block's first entry
+    int d;
     uint32_t cur_word;     // index of the word being accumulated
     uint32_t bits;
     uint32_t cur_chunk;
-    __device__ __forceinline__ void token(int pos, int op)
+    __device__ __forceinline__ void token(int ip, int op)
     {
-        const uint32_t w = (uint32_t)pos >> 5;
+        const uint32_t q = (uint32_t)(ip + d);
+        const uint32_t w = q >> 5;
         if (w != cur_word) {
-            if (bits) tokmap[cur_word] = bits;
+            if (bits) atomicOr(&tokmap[cur_word], bits);
             cur_word = w; bits = 0;
         }
-        bits |= 1u << (pos & 31);
-        const uint32_t c = (uint32_t)pos >> 7;
+        bits |= 1u << (q & 31);
+        const uint32_t c = q >> 7;
         if (c != cur_chunk) { chunk_op[c] = (uint32_t)op; cur_chunk = c; }
     }
-    __device__ __forceinline__ void flush() { if (bits) tokmap[cur_word] = bits; }
+    __device__ __forceinline__ void flush() { if (bits) atomicOr(&tokmap[cur_word], bits); bits = 0; }
 };
 
 constexpr int D1_HALF = 2048;             // bytes per ring half
 constexpr int D1_RING = 2 * D1_HALF;
 constexpr int D1_WARPS = 4;               // blocks per CTA
+constexpr int D1_SUB = 64;                // positions per lane per half (32 lanes x 64 = one half)
+constexpr int D1_A_WORDS = (D1_HALF + 2 * 32 + 8) / 2;     // u16 table, 2 entries of padding per sub-chunk
+constexpr int D1_B_WORDS = D1_HALF + 32 + 8;               // u32 table, 1 entry of padding per sub-chunk
+constexpr int D1_WARP_SMEM = D1_RING + D1_A_WORDS * 4 + D1_B_WORDS * 4 + 64 * 4 + 64 * 2;
+constexpr int D1_SMEM = D1_WARPS * ((D1_WARP_SMEM + 15) & ~15);
+constexpr int D1_SPECIAL = 0x8000;
+constexpr int D1_NONE = 0xffff;
 
 // bytes of the compressed block through this warp's shared-memory ring; positions outside the
 // staged window (far look-ahead after a long literal run) fall back to global memory
@@ -82,25 +92,75 @@ struct RingReader {
     }
 };
 
-// One WARP per block: all lanes stream the payload into a double-buffered ring (coalesced 128-bit
-// loads, the next half in flight while the current one is parsed), lane 0 walks the chain.
+// One sequence, any length, for the bulk phase: everything read lies below `limit` (block
+// coordinates) or the sequence is reported as not clean.  next = position of the next token.
+struct SeqDec { int lit, ml, off, next; bool clean; };
+__device__ __forceinline__ SeqDec d1_decode_slow(const RingReader &rd, int ip, int limit)
+{
+    SeqDec r; r.clean = false; r.lit = r.ml = r.off = 0; r.next = ip;
+    if (ip >= limit) return r;
+    const unsigned tok = rd(ip++);
+    int lit = (int)(tok >> 4);
+    if (lit == 15) {
+        unsigned b;
+        do { if (ip >= limit) return r; b = rd(ip++); lit += (int)b; } while (b == 255);
+    }
+    if (lit > limit - ip) return r;
+    ip += lit;
+    if (ip + 2 > limit) return r;
+    r.off = (int)rd(ip) | ((int)rd(ip + 1) << 8); ip += 2;
+    int ml = (int)(tok & 15);
+    if (ml == 15) {
+        unsigned b;
+        do { if (ip >= limit) return r; b = rd(ip++); ml += (int)b; } while (b == 255);
+    }
+    r.lit = lit; r.ml = ml + 4; r.next = ip; r.clean = true;
+    return r;
+}
+
+// D1.  One WARP per block.  All lanes stream the payload through a double-buffered ring.
+//
+// BULK phase (all of the block except its last few sequences), one 2 KiB half at a time:
+//   A  every byte position is decoded AS IF a token started there (length of that sequence in the
+//      stream, bytes it produces) -- 64 positions per lane, no dependencies;
+//   B  each lane folds its own 64-position sub-chunk back to front into an "exit function":
+//      for every entry position, where the chain leaves the sub-chunk and how many bytes it
+//      produced on the way;
+//   C  lane 0 walks the real chain with ONE table lookup per sub-chunk instead of one dependent
+//      step per sequence (32 hops per half instead of ~400 sequences);
+//   D  every lane re-walks its sub-chunk from its real entry: sets the token bits, checks the
+//      one test that can fail this far from the ends of the buffers (offset beyond the start of
+//      the output, lz4.c:2065) and watches for the first sequence that comes within 32 bytes of
+//      the end of the input or 64 bytes of the end of the output.
+// From that first "not clean" sequence on, lane 0 runs the exact two-loop state machine of
+// lz4_parse.h (TAIL phase); every end-of-buffer rule of the reference lives there.  A sequence is
+// clean iff next_token <= iend - 32 and op_after < oend - 64; both grow along the chain, so the
+// clean sequences are a prefix of the stream and none of the reference's fast-loop exits
+// (:2010, :2014, :2045, :2050) nor any length-field limit (:1911-1920) can trigger inside it.
 __global__ void __launch_bounds__(D1_WARPS * 32)
 lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, uint32_t *chunk_op, int32_t *result)
 {
-    __shared__ __align__(16) uint8_t s_ring[D1_WARPS][D1_RING];
+    extern __shared__ __align__(16) uint8_t d1_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * D1_WARPS + warp;
     if (b >= n_blocks) return;
     const BlockDesc bd = blocks[b];
     if (bd.stored) { if (lane == 0) result[b] = (int32_t)bd.usize; return; }
 
-    uint8_t *ring = s_ring[warp];
+    uint8_t *ring = d1_smem + (size_t)warp * ((D1_WARP_SMEM + 15) & ~15);
+    uint16_t *A = (uint16_t *)(ring + D1_RING);                    // seq length -> exit position
+    uint32_t *B = (uint32_t *)(ring + D1_RING + D1_A_WORDS * 4);   // seq output -> output until exit
+    uint32_t *s_op = B + D1_B_WORDS;                               // per sub-chunk: op at its entry
+    uint16_t *s_entry = (uint16_t *)(s_op + 64);                   // per sub-chunk: entry position
+
     const uintptr_t a = (uintptr_t)bd.src;
     const uint4 *base = (const uint4 *)(a & ~(uintptr_t)15);
     const int d = (int)(a & 15);
-    const int csize = (int)bd.csize;
+    const int csize = (int)bd.csize, oend = (int)bd.usize;
     const int nchunks = (d + csize + 15) >> 4;            // 16-byte chunks holding payload bytes
     constexpr int HC = D1_HALF / 16;                      // chunks per half
+    uint32_t *my_map = tokmap + (size_t)bd.chunk_base * LZ4_CHUNK_WORDS;
+    uint32_t *my_cop = chunk_op + bd.chunk_base;
 
     uint4 r0, r1, r2, r3;
     auto load_half = [&](int h) {
@@ -115,20 +175,170 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
         uint4 *q = (uint4 *)(ring + (h & 1) * D1_HALF);
         q[lane] = r0; q[lane + 32] = r1; q[lane + 64] = r2; q[lane + 96] = r3;
     };
+    auto idxA = [](int j) { return j + 2 * (j >> 6); };   // padded: sub-chunks start in distinct banks
+    auto idxB = [](int j) { return j + (j >> 6); };
 
     ParseState st;
     TokSink sink;
-    sink.tokmap = tokmap + (size_t)bd.chunk_base * LZ4_CHUNK_WORDS;
-    sink.chunk_op = chunk_op + bd.chunk_base;
+    sink.tokmap = my_map; sink.chunk_op = my_cop; sink.d = d;
     sink.cur_word = 0; sink.bits = 0; sink.cur_chunk = 0xffffffffu;
-    lz4_parse_init(st, bd.src == nullptr, csize, (int)bd.usize,
+    lz4_parse_init(st, bd.src == nullptr, csize, oend,
                    (lane == 0 && bd.src != nullptr && csize > 0) ? (unsigned)bd.src[0] : 0u);
 
+    int k = 0;                                            // ring holds halves k and k+1
     if (!st.status) {
-        load_half(0); store_half(0);
-        load_half(1); store_half(1);
+        // ================= BULK =================
+        const int clean_ip = csize - 32;                  // next token must not pass this
+        const int clean_op = oend - 64;                   // op after the sequence must stay below
+        int e_q = d, e_op = 0;                            // chain entry (aligned coordinate) and its op
+        bool bulk = clean_ip > 0 && clean_op > 0;
+        bool staged = false;                              // ring already holds halves k, k+1
+        while (bulk) {
+            k = e_q >> 11;
+            if (!staged) { load_half(k); store_half(k); load_half(k + 1); store_half(k + 1); __syncwarp(); }
+            const bool more = (k + 2) * HC < nchunks;
+            if (more) load_half(k + 2);                   // in flight during the phases below
+            const int base_q = k * D1_HALF;
+            RingReader rd;
+            rd.ring = ring; rd.src = bd.src; rd.d = d;
+            rd.lo = base_q - d; rd.span = min(base_q + D1_RING - d, csize) - rd.lo;
+
+            // ---- A: every position as a token (at most one continuation byte per field)
+#pragma unroll 4
+            for (int i = 0; i < D1_SUB; i++) {
+                const int j = i * 32 + lane;
+                const int q = base_q + j;
+                const unsigned tok = ring[q & (D1_RING - 1)];
+                int lit = (int)(tok >> 4), ml = (int)(tok & 15), e = 1;
+                bool special = false;
+                if (lit == 15) { const unsigned x = ring[(q + 1) & (D1_RING - 1)]; special = x == 255; lit += (int)x; e = 2; }
+                if (ml == 15) { const unsigned x = ring[(q + e + lit + 2) & (D1_RING - 1)]; special |= x == 255; ml += (int)x; e++; }
+                A[idxA(j)] = special ? (uint16_t)0 : (uint16_t)(e + lit + 2);
+                B[idxB(j)] = (uint32_t)(lit + ml + 4);
+            }
+            __syncwarp();
+            // ---- B: exit function of my sub-chunk, back to front, in place
+            {
+                const int s0 = lane * D1_SUB, s1 = s0 + D1_SUB;
+#pragma unroll 4
+                for (int j = s1 - 1; j >= s0; j--) {
+                    const int sl = (int)A[idxA(j)];
+                    uint32_t os = B[idxB(j)];
+                    int ex;
+                    if (sl == 0) { ex = j | D1_SPECIAL; os = 0; }
+                    else {
+                        const int n = j + sl;
+                        if (n < s1) { ex = (int)A[idxA(n)]; os += B[idxB(n)]; }
+                        else ex = n;
+                    }
+                    A[idxA(j)] = (uint16_t)ex;
+                    B[idxB(j)] = os;
+                }
+            }
+            s_entry[lane] = (uint16_t)D1_NONE;
+            __syncwarp();
+            // ---- C: lane 0 hops sub-chunk to sub-chunk along the real chain
+            int e = e_q - base_q, op = e_op;
+            if (lane == 0) {
+                while (e < D1_HALF) {
+                    const int sc = e >> 6;
+                    if (s_entry[sc] == D1_NONE) { s_entry[sc] = (uint16_t)e; s_op[sc] = (uint32_t)op; }
+                    const int x = (int)A[idxA(e)];
+                    op += (int)B[idxB(e)];
+                    if (x & D1_SPECIAL) {
+                        const SeqDec sd = d1_decode_slow(rd, base_q + (x & 0x7fff) - d, clean_ip);
+                        if (!sd.clean) break;             // phase D finds it too and ends the bulk phase
+                        op += sd.lit + sd.ml;
+                        e = sd.next + d - base_q;
+                    } else e = x;
+                }
+            }
+            e = __shfl_sync(FM_FULL, e, 0); op = __shfl_sync(FM_FULL, op, 0);
+            __syncwarp();
+            // ---- D: my sub-chunk from its real entry: bits, offset test, first unclean sequence
+            uint32_t w0 = 0, w1 = 0;
+            int first_op = -1, viol = 0x7fffffff, viol_next = 0, uncl = 0x7fffffff, uncl_op = 0;
+            {
+                int p = (int)s_entry[lane];
+                if (p != D1_NONE) {
+                    int o = (int)s_op[lane];
+                    const int s1 = (lane + 1) * D1_SUB;
+                    while (p < s1) {
+                        const int ip = base_q + p - d;
+                        int lit, mlen, off, next;
+                        const unsigned tok = ring[(base_q + p) & (D1_RING - 1)];
+                        if ((tok >> 4) == 15 || (tok & 15) == 15) {
+                            const SeqDec sd = d1_decode_slow(rd, ip, clean_ip);
+                            if (!sd.clean) { uncl = p; uncl_op = o; break; }
+                            lit = sd.lit; mlen = sd.ml; off = sd.off; next = sd.next;
+                        } else {
+                            lit = (int)(tok >> 4); mlen = (int)(tok & 15) + 4;
+                            const int qo = base_q + p + 1 + lit;
+                            off = (int)ring[qo & (D1_RING - 1)] | ((int)ring[(qo + 1) & (D1_RING - 1)] << 8);
+                            next = ip + lit + 3;
+                        }
+                        if (next > clean_ip || o + lit + mlen >= clean_op) { uncl = p; uncl_op = o; break; }
+                        if (off > o + lit) { viol = p; viol_next = next; break; }         // lz4.c:2041/:2065
+                        if (first_op < 0) first_op = o;
+                        const int bit = p - lane * D1_SUB;
+                        if (bit < 32) w0 |= 1u << bit; else w1 |= 1u << (bit - 32);
+                        o += lit + mlen;
+                        p = next + d - base_q;
+                    }
+                }
+            }
+            const int pu = warp_min(uncl), pv = warp_min(viol);
+            if (pv < pu) {                                // corrupt: offset before the start of the output
+                const int src_lane = __ffs(__ballot_sync(FM_FULL, viol == pv)) - 1;
+                const int vn = __shfl_sync(FM_FULL, viol_next, src_lane);
+                st.status = 1; st.result = -vn - 1;       // lz4.c:2337 with ip at the next token
+                bulk = false;
+                break;
+            }
+            // token bits and per-chunk output positions of this half
+            {
+                uint32_t *mw = my_map + (base_q >> 5) + 2 * lane;
+                if (w0) mw[0] = w0;
+                if (w1) mw[1] = w1;
+                const int f_even = __shfl_sync(FM_FULL, first_op, lane & ~1), f_odd = __shfl_sync(FM_FULL, first_op, lane | 1);
+                const int f = f_even >= 0 ? f_even : f_odd;
+                if (!(lane & 1) && f >= 0) my_cop[(base_q >> 7) + (lane >> 1)] = (uint32_t)f;
+            }
+            if (pu != 0x7fffffff) {                       // hand over to the exact state machine
+                const int src_lane = __ffs(__ballot_sync(FM_FULL, uncl == pu)) - 1;
+                st.ip = base_q + pu - d;
+                st.op = __shfl_sync(FM_FULL, uncl_op, src_lane);
+                // the word and chunk holding the hand-over token may already carry earlier tokens
+                const int c_first = __shfl_sync(FM_FULL, first_op, (pu >> 6) & ~1);
+                const int c_mine = __shfl_sync(FM_FULL, first_op, pu >> 6);
+                const bool chunk_has = ((pu >> 6) & 1) ? (c_first >= 0 || c_mine >= 0) : (c_mine >= 0);
+                sink.cur_word = (uint32_t)(base_q + pu) >> 5; sink.bits = 0;
+                sink.cur_chunk = chunk_has ? (uint32_t)(base_q + pu) >> 7 : 0xffffffffu;
+                bulk = false;
+                __syncwarp();
+                break;
+            }
+            // next half
+            e_q = base_q + e; e_op = op;
+            __syncwarp();
+            if (e < D1_RING && more) { store_half(k + 2); staged = true; }
+            else staged = false;                          // jumped far ahead (or nothing left): restage
+            __syncwarp();
+            if (e_q - d >= csize) {                       // cannot happen after a clean sequence; be safe
+                st.status = 1; st.result = -(e_q - d) - 1;
+                bulk = false;
+            }
+        }
+    }
+
+    if (!st.status) {
+        // ================= TAIL =================
+        k = (st.ip + d) >> 11;
         __syncwarp();
-        for (int k = 0;; k++) {
+        load_half(k); store_half(k);
+        load_half(k + 1); store_half(k + 1);
+        __syncwarp();
+        for (;; k++) {
             const bool more = (k + 2) * HC < nchunks;
             if (more) load_half(k + 2);                   // in flight during the walk below
             if (lane == 0 && !st.status) {
@@ -138,7 +348,7 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
                 rd.span = min((k + 2) * D1_HALF - d, csize) - rd.lo;
                 // tokens below the middle of the window keep their next 32 bytes staged
                 const int stop = more ? (k + 1) * D1_HALF - d : 0x7fffffff;
-                lz4_parse_run(st, rd, sink, csize, (int)bd.usize, stop);
+                lz4_parse_run(st, rd, sink, csize, oend, stop);
             }
             if (__shfl_sync(FM_FULL, st.status, 0)) break;
             __syncwarp();
@@ -210,7 +420,8 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
     const uint8_t *__restrict__ src = bd.src;
     uint8_t *out = bd.dst;
     const int csize = (int)bd.csize;
-    const int nchunks = (csize + LZ4_CHUNK - 1) / LZ4_CHUNK;
+    const int dq = (int)((uintptr_t)bd.src & 15);     // D1 records tokens at aligned positions ip + dq
+    const int nchunks = (dq + csize + LZ4_CHUNK - 1) / LZ4_CHUNK;
     const uint4 *maps = (const uint4 *)(tokmap + (size_t)bd.chunk_base * LZ4_CHUNK_WORDS);
     const uint32_t *cops = chunk_op + bd.chunk_base;
     volatile int *owed = s_owed;
@@ -245,7 +456,7 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
             const bool active = batch + lane < ntok;
             int lit = 0, ml = 0, off = 0, lit_src = 0;
             if (active) {
-                int ip = k * LZ4_CHUNK + (int)s_tokpos[warp][batch + lane];
+                int ip = k * LZ4_CHUNK + (int)s_tokpos[warp][batch + lane] - dq;
                 const unsigned tok = src[ip++];
                 lit = (int)(tok >> 4);
                 if (lit == 15) { unsigned s; do { s = src[ip++]; lit += (int)s; } while (s == 255); }

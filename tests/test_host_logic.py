@@ -108,3 +108,53 @@ def test_shard_blocks(pkg):
             ranges = [pkg.shard_blocks(nb, g, r) for r in range(g)]
             assert ranges[0][0] == 0 and ranges[-1][1] == nb
             assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+
+
+@pytest.fixture(scope="module")
+def d1():
+    L = build_native("d1_emul", ["tests/native/d1_emul.cpp"])
+    for f in (L.d1_emul, L.d1_serial):
+        f.restype = C.c_int
+        f.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int64), C.c_int, C.c_int]
+    return L
+
+
+def _d1_both(d1, comp, cap, d):
+    nw, nc = (len(comp) + 16) // 32 + 2, (len(comp) + 16) // 128 + 2
+    out = []
+    for f in (d1.d1_emul, d1.d1_serial):
+        m = (C.c_uint32 * nw)(); c = (C.c_int64 * nc)()
+        r = f(comp, len(comp), cap, d, m, c, nw, nc)
+        out.append((r, list(m), list(c)) if r >= 0 else (r, None, None))     # tables only matter for valid blocks
+    return out
+
+
+def test_warp_parallel_parse_equals_serial_walk(d1, ora, pkg):
+    """Sequential emulation of lz4_parse_kernel's bulk phase (per-position decode, exit DP, hop chain,
+    per-lane re-walk, hand-over to the state machine): same verdict, token bits and chunk positions."""
+    rng = random.Random(12)
+    text = gen_logtext(pkg, 600000)
+    samples = [text, text[:70000], text[:5000], text[:100], bytes(300000), (b"abcdefg" * 90000)[:500000],
+               rng.randbytes(5000) + text[:100000] + bytes(5000) + rng.randbytes(300) * 50,
+               b"".join(bytes([rng.getrandbits(8)]) * rng.choice([1, 2, 3, 40, 300, 5000, 70000]) for _ in range(400))]
+    for src in samples:
+        comp = ora.lz4_compress(src)
+        for d in (0, 1, 7, 12, 15):
+            for cap in (len(src), len(src) + 100, 4 << 20, max(0, len(src) - 1), len(src) // 2):
+                a, b = _d1_both(d1, comp, cap, d)
+                assert a == b, (len(src), d, cap, a[0], b[0])
+        # corrupt streams: same error value
+        for k in range(120):
+            m = bytearray(comp)
+            i = rng.randrange(len(m))
+            if k % 4 == 0:
+                m[i] = rng.getrandbits(8)
+            elif k % 4 == 1:
+                m = m[:i + 1]
+            elif k % 4 == 2:
+                m[i:i] = bytes([rng.choice([0, 255, 0xF0, 0x0F])])
+            else:
+                j = rng.randrange(len(m) - 1); m[j] = 0xFF; m[j + 1] = 0xFF      # far offsets / long lengths
+            m = bytes(m)
+            a, b = _d1_both(d1, m, rng.choice([len(src), len(src) + 64, 4 << 20]), rng.choice([0, 3, 12]))
+            assert a == b, (len(src), k, a[0], b[0])
