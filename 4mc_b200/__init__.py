@@ -287,3 +287,13 @@ def shard_blocks(n_blocks: int, world_size: int, rank: int) -> tuple[int, int]:
     per = -(-n_blocks // world_size) if n_blocks else 0
     lo = min(n_blocks, rank * per)
     return lo, min(n_blocks, lo + per)
+
+
+def span_base_offsets(span_sizes: list[int]) -> list[int]:
+    """File offset of every rank's span in the single output stream: rank r starts at
+    12 (file header) + the spans of ranks < r (native/4mc.c:285-293 block offsets)."""
+    out, pos = [], 12
+    for s in span_sizes:
+        out.append(pos)
+        pos += s
+    return out

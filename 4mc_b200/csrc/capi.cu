@@ -245,8 +245,22 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             const uint32_t cnt = std::min<uint32_t>(32768, nb - b0);
             KL("lz4_stored_kernel", st, lz4_stored_kernel<<<dim3(32, cnt), 256, 0, st>>>(desc + b0, cnt));
         }
-        KL("lz4_copy_kernel", st, lz4_copy_kernel<<<nb, LZ4_COPY_WARPS * 32, 0, st>>>(desc, (const uint32_t *)ws.tokmap.p,
-                                                            (const uint32_t *)ws.chunkop.p, (const int32_t *)ws.result.p));
+        {
+            // warps per block: enough to fill the chip when blocks are few, few when blocks are many
+            static int forced = -1;
+            if (forced < 0) { const char *e = getenv("FOURMC_D2_WARPS"); forced = e ? atoi(e) : 0; }
+            int w = forced;
+            if (w != 1 && w != 2 && w != 4 && w != 8) {
+                const uint32_t want = (uint32_t)ctx->sm_count * 48;        // resident warps to aim for
+                w = nb * 1 >= want ? 1 : nb * 2 >= want ? 2 : nb * 4 >= want ? 4 : 8;
+            }
+            const uint32_t *tm = (const uint32_t *)ws.tokmap.p, *co = (const uint32_t *)ws.chunkop.p;
+            const int32_t *rs = (const int32_t *)ws.result.p;
+            if (w == 1) KL("lz4_copy_kernel", st, lz4_copy_kernel<1><<<nb, 32, 0, st>>>(desc, tm, co, rs));
+            else if (w == 2) KL("lz4_copy_kernel", st, lz4_copy_kernel<2><<<nb, 64, 0, st>>>(desc, tm, co, rs));
+            else if (w == 4) KL("lz4_copy_kernel", st, lz4_copy_kernel<4><<<nb, 128, 0, st>>>(desc, tm, co, rs));
+            else KL("lz4_copy_kernel", st, lz4_copy_kernel<8><<<nb, 256, 0, st>>>(desc, tm, co, rs));
+        }
     }
     KL("finalize_kernel", st, finalize_kernel<<<1, SCAN_THREADS, 0, st>>>((const BlockDesc *)ws.desc.p, (const int32_t *)ws.result.p, nb,
                                                 (uint8_t *)ws.status.p, d_out_size, d_info, d_result));
@@ -812,9 +826,6 @@ long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
     // slices of consecutive blocks; footers travel as hash-only items
     const size_t sl_blocks = (size_t)slice_blocks();
     int r;
-    if ((r = pinned_scratch(ctx, 4096))) return r;
-    std::vector<uint8_t> status(blocks.size(), 0);
-    std::vector<uint32_t> hashes(blocks.size(), 0);
     struct Slice { size_t b0, b1; uint64_t s0, s1, d0, d1; };
     std::vector<Slice> slices;
     for (size_t b0 = 0; b0 < blocks.size(); b0 += sl_blocks) {
@@ -823,9 +834,20 @@ long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
         s.d1 = blocks[b1 - 1].dst_off + (blocks[b1 - 1].usize == 0xffffffffu ? 0 : blocks[b1 - 1].usize);
         slices.push_back(s);
     }
-    size_t max_in = 0, max_out = 0;
-    for (auto &s : slices) { max_in = std::max<size_t>(max_in, s.s1 - s.s0); max_out = std::max<size_t>(max_out, s.d1 - s.d0); }
-    std::vector<uint8_t> h_tables[2];
+    size_t max_in = 0, max_out = 0, max_cnt = 0;
+    for (auto &s : slices) {
+        max_in = std::max<size_t>(max_in, s.s1 - s.s0); max_out = std::max<size_t>(max_out, s.d1 - s.d0);
+        max_cnt = std::max<size_t>(max_cnt, s.b1 - s.b0);
+    }
+    // everything the device reads from / writes to the host besides the payload lives in pinned
+    // memory, so that no copy blocks the host and the two slice pipelines really overlap
+    const size_t tb_host = (max_cnt * 28 + 63) & ~(size_t)63;
+    const size_t pin_need = 4096 + 2 * tb_host + blocks.size() * 5 + 64;
+    if ((r = pinned_scratch(ctx, pin_need))) return r;
+    uint8_t *pin = (uint8_t *)ctx->pinned + 4096;
+    uint8_t *h_tables[2] = {pin, pin + tb_host};
+    uint32_t *hashes = (uint32_t *)(pin + 2 * tb_host);
+    uint8_t *status = (uint8_t *)(hashes + blocks.size());
     for (size_t k = 0; k < slices.size(); k++) {
         const int b = (int)(k & 1);
         const Slice &s = slices[k];
@@ -834,38 +856,36 @@ long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
         if ((r = ensure(ctx, ctx->stage_in[b], max_in + 64))) return r;
         if ((r = ensure(ctx, ctx->stage_out[b], max_out + 64))) return r;
         DecWs &ws = ctx->dec[b];
-        // tables: src_off u64[cnt] | dst_off u64[cnt] | csize u32[cnt] | usize u32[cnt] | xxh u32[cnt] | hash_out u32[cnt] | status u8[cnt]
+        // tables: src_off u64[cnt] | dst_off u64[cnt] | csize u32[cnt] | usize u32[cnt] | xxh u32[cnt] | hash_out u32[cnt] | out_size i32[cnt] | status u8[cnt]
         const size_t tb_bytes = (size_t)cnt * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 1) + 64;
         if ((r = ensure(ctx, ws.tables, tb_bytes))) return r;
         CK(cudaStreamSynchronize(st));                       // previous use of this buffer pair is complete
-        h_tables[b].assign(tb_bytes, 0);
-        uint64_t *t_src = (uint64_t *)h_tables[b].data();
+        uint64_t *t_src = (uint64_t *)h_tables[b];
         uint64_t *t_dst = t_src + cnt;
         uint32_t *t_c = (uint32_t *)(t_dst + cnt), *t_u = t_c + cnt, *t_x = t_u + cnt;
         for (uint32_t i = 0; i < cnt; i++) {
             const HostBlock &hb = blocks[s.b0 + i];
             t_src[i] = hb.src_off - s.s0; t_dst[i] = hb.dst_off - s.d0;
             t_c[i] = hb.csize; t_x[i] = hb.xxh;
-            // hash-only items (footers) decode nothing: present them as empty stored blocks
-            t_u[i] = hb.usize;
+            t_u[i] = hb.usize;               // footers carry 0xffffffff: hashed, never decoded
         }
         uint8_t *d_tb = (uint8_t *)ws.tables.p;
         CK(cudaMemcpyAsync(ctx->stage_in[b].p, src + s.s0, s.s1 - s.s0, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_tb, h_tables[b].data(), (size_t)cnt * 28, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tb, h_tables[b], (size_t)cnt * 28, cudaMemcpyHostToDevice, st));
         const uint64_t *d_src_off = (const uint64_t *)d_tb, *d_dst_off = d_src_off + cnt;
         const uint32_t *d_c = (const uint32_t *)(d_dst_off + cnt), *d_u = d_c + cnt, *d_x = d_u + cnt;
         uint32_t *d_hash = (uint32_t *)(d_x + cnt);
         int32_t *d_osz = (int32_t *)(d_hash + cnt);
         uint8_t *d_st = (uint8_t *)(d_osz + cnt);
-        // footers: hash every item's payload first (cheap: same kernel as the block verify)
+        // XXH32 of every item's payload (blocks and footers), compared with the headers below
         if ((r = fourmc_xxh32_batch_device(ctx, st, cnt, ctx->stage_in[b].p, d_src_off, d_c, 0, d_hash))) return r;
-        // blocks: footers carry usize 0xffffffff -> marked too large by build_desc, decode nothing
         if ((r = fourmc_lz4_decompress_batch_device(ctx, st, cnt, ctx->stage_in[b].p, d_src_off, d_c, d_u, d_hash, 0,
                                                     ctx->stage_out[b].p, d_dst_off, d_osz, d_st)))
             return r;
-        CK(cudaMemcpyAsync((uint8_t *)out + s.d0, ctx->stage_out[b].p, s.d1 - s.d0, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(status.data() + s.b0, d_st, cnt, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hashes.data() + s.b0, d_hash, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        if (s.d1 > s.d0)
+            CK(cudaMemcpyAsync((uint8_t *)out + s.d0, ctx->stage_out[b].p, s.d1 - s.d0, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status + s.b0, d_st, cnt, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hashes + s.b0, d_hash, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(ctx->aux[0]));
     CK(cudaStreamSynchronize(ctx->aux[1]));

@@ -70,4 +70,27 @@ __device__ __forceinline__ int warp_min(int v)
     return v;
 }
 
+// Byte copy of a short, non-overlapping range with every load issued before the first store, so a
+// lane pays one memory latency per 8 bytes instead of one per byte (warps issue in order: a store
+// that waits for its load's data blocks the loads behind it).
+template <class D, class S>
+__device__ __forceinline__ void copy_batched(D *dst, const S *src, int n)
+{
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint8_t t[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) t[j] = src[i + j];
+#pragma unroll
+        for (int j = 0; j < 8; j++) dst[i + j] = t[j];
+    }
+    if (i < n) {
+        uint8_t t[8];
+#pragma unroll
+        for (int j = 0; j < 7; j++) if (i + j < n) t[j] = src[i + j];
+#pragma unroll
+        for (int j = 0; j < 7; j++) if (i + j < n) dst[i + j] = t[j];
+    }
+}
+
 }  // namespace fm

@@ -29,7 +29,6 @@ namespace fm {
 constexpr int LZ4_CHUNK = 128;            // compressed bytes per D2 work item
 constexpr int LZ4_CHUNK_WORDS = 4;        // tokmap words per chunk
 constexpr int LZ4_MAX_TOK = 43;           // ceil(128 / 3): a sequence is at least 3 bytes
-constexpr int LZ4_COPY_WARPS = 8;
 constexpr int LZ4_LONG = 48;              // copies this long are done by the whole warp
 
 struct BlockDesc {                         // one per block, built on the device
@@ -404,14 +403,17 @@ __device__ __forceinline__ void smem_copy_seq(uint8_t *dst, const uint8_t *src, 
 
 constexpr int LZ4_SPAN = 2048;            // output bytes a warp assembles in shared memory at once
 
-__global__ void __launch_bounds__(LZ4_COPY_WARPS * 32)
+// W = warps per block (1, 2, 4 or 8): the host picks it from the batch size -- many blocks in
+// flight need few warps each (and then hardly ever wait on one another), few blocks need many.
+template <int W>
+__global__ void __launch_bounds__(W * 32)
 lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t *chunk_op,
                 const int32_t *result)
 {
-    __shared__ int s_owed[LZ4_COPY_WARPS];
+    __shared__ int s_owed[W];
     __shared__ int s_ticket;
-    __shared__ uint8_t s_tokpos[LZ4_COPY_WARPS][64];
-    __shared__ __align__(16) uint8_t s_span[LZ4_COPY_WARPS][LZ4_SPAN + 32];
+    __shared__ uint8_t s_tokpos[W][64];
+    __shared__ __align__(16) uint8_t s_span[W][LZ4_SPAN + 32];
 
     const BlockDesc bd = blocks[blockIdx.x];
     if (bd.stored || result[blockIdx.x] < 0) return;
@@ -427,14 +429,32 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
     volatile int *owed = s_owed;
     uint8_t *span = s_span[warp];
 
-    if (threadIdx.x < LZ4_COPY_WARPS) s_owed[threadIdx.x] = 0;
+    if (threadIdx.x < W) s_owed[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_ticket = 0;
-    __syncthreads();
+    if (W > 1) __syncthreads();
 
+    // lowest output position any warp of this block still owes
+    auto high_water = [&]() -> int {
+        if (W == 1) return 0x7fffffff;
+        int v = lane < W ? owed[lane] : 0x7fffffff;
+#pragma unroll
+        for (int s = W / 2; s > 0; s >>= 1) v = min(v, __shfl_xor_sync(FM_FULL, v, s));
+        return __shfl_sync(FM_FULL, v, 0);
+    };
+    auto publish = [&](int pos) {
+        if (W == 1) return;
+        __threadfence_block();                        // our finished bytes before the new mark
+        if (lane == 0) owed[warp] = pos;
+    };
+
+    int kseq = 0;
     for (;;) {
         int k = 0;
-        if (lane == 0) k = atomicAdd(&s_ticket, 1);
-        k = __shfl_sync(FM_FULL, k, 0);
+        if (W == 1) k = kseq++;
+        else {
+            if (lane == 0) k = atomicAdd(&s_ticket, 1);
+            k = __shfl_sync(FM_FULL, k, 0);
+        }
         if (k >= nchunks) break;
 
         const uint4 m = maps[k];
@@ -474,60 +494,57 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
             const int my_op = op0 + incl - outlen;
             const int total = __shfl_sync(FM_FULL, incl, 31);
             const int d = my_op + lit;                // where my match starts
+            const int mstart = d - off;
 
             if (total <= LZ4_SPAN) {
                 // ---------- path A: assemble [op0, op0 + total) in shared memory, flush once ----------
                 const int shift = (int)((uintptr_t)(out + op0) & 15);   // equal 16-byte phases in smem and HBM
                 uint8_t *sp = span + shift - op0;     // sp[x] holds output byte x
-                __threadfence_block();
-                if (lane == 0) owed[warp] = op0;      // nothing below op0 is owed by this warp
+                publish(op0);                         // nothing below op0 is owed by this warp
                 // literals
-                if (active && lit < LZ4_LONG)
-                    for (int i = 0; i < lit; i++) sp[my_op + i] = src[lit_src + i];
+                if (active && lit < LZ4_LONG) copy_batched(sp + my_op, src + lit_src, lit);
                 for (unsigned lm = __ballot_sync(FM_FULL, active && lit >= LZ4_LONG); lm; lm &= lm - 1) {
                     const int l = __ffs(lm) - 1;
                     const int n = __shfl_sync(FM_FULL, lit, l), sp0 = __shfl_sync(FM_FULL, my_op, l);
                     const int ls = __shfl_sync(FM_FULL, lit_src, l);
                     for (int i = lane; i < n; i += 32) sp[sp0 + i] = src[ls + i];
                 }
-                // bytes a match takes from before the span come from HBM, once they exist
-                const int mstart = d - off;
-                const int ext = (ml > 0 && off > 0 && mstart < op0) ? min(ml, op0 - mstart) : 0;
-                int need = ext ? mstart + ext : 0;
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1) need = max(need, __shfl_xor_sync(FM_FULL, need, s));
-                if (need > 0) {
-                    for (;;) {
-                        const int hwm = warp_min(lane < LZ4_COPY_WARPS ? owed[lane] : 0x7fffffff);
-                        if (hwm >= need) break;
-                    }
-                    __threadfence_block();
-                }
-                if (ext > 0) {
-                    if (ext < LZ4_LONG) { for (int i = 0; i < ext; i++) sp[d + i] = out[mstart + i]; }
-                }
-                for (unsigned lm = __ballot_sync(FM_FULL, ext >= LZ4_LONG); lm; lm &= lm - 1) {
-                    const int l = __ffs(lm) - 1;
-                    const int n = __shfl_sync(FM_FULL, ext, l), dd = __shfl_sync(FM_FULL, d, l);
-                    const int ms = __shfl_sync(FM_FULL, mstart, l);
-                    for (int i = lane; i < n; i += 32) sp[dd + i] = out[ms + i];
-                }
-                __syncwarp();
-                // the rest of every match reads bytes of this span: resolve in rounds, lowest first
-                bool pending = ml > ext;
-                if (ml > 0 && off == 0) {             // lz4.c:2300-2303: offset 0 yields zeros
+                // matches.  Bytes from before the span come from HBM once the block-wide mark has
+                // passed them; bytes inside the span come from shared memory once every earlier
+                // match of this warp that could overlap them is done (lowest destination first).
+                bool pending = ml > 0;
+                if (pending && off == 0) {            // lz4.c:2300-2303: offset 0 yields zeros
                     for (int i = 0; i < ml; i++) sp[d + i] = 0;
                     pending = false;
                 }
-                const int need_in = min(mstart + ml, d);          // everything below this must exist
+                const int ext = (pending && mstart < op0) ? min(ml, op0 - mstart) : 0;
+                const int need_ext = ext ? mstart + ext : 0;
+                const int need_in = (ml > ext) ? min(mstart + ml, d) : 0;
+                __syncwarp();
+                int idle = 0;
                 for (;;) {
                     const int low = warp_min(pending ? d : 0x7fffffff);
                     if (low == 0x7fffffff) break;
-                    if (pending && need_in <= low) {
-                        smem_copy_seq(sp + d + ext, sp + mstart + ext, ml - ext);
-                        pending = false;
+                    const int hwm = high_water();
+                    if (W > 1) __threadfence_block();
+                    const bool go = pending && need_ext <= hwm && need_in <= low;
+                    if (go) {
+                        if (ext > 0 && ext < LZ4_LONG) copy_batched(sp + d, (const uint8_t *)out + mstart, ext);
+                        if (ml > ext && ext < LZ4_LONG) smem_copy_seq(sp + d + ext, sp + mstart + ext, ml - ext);
                     }
+                    // long reads from HBM: the whole warp per match, then its in-span remainder
+                    for (unsigned lm = __ballot_sync(FM_FULL, go && ext >= LZ4_LONG); lm; lm &= lm - 1) {
+                        const int l = __ffs(lm) - 1;
+                        const int n = __shfl_sync(FM_FULL, ext, l), dd = __shfl_sync(FM_FULL, d, l);
+                        const int ms = __shfl_sync(FM_FULL, mstart, l), mm = __shfl_sync(FM_FULL, ml, l);
+                        for (int i = lane; i < n; i += 32) sp[dd + i] = out[ms + i];
+                        __syncwarp();
+                        if (lane == l && mm > n) smem_copy_seq(sp + dd + n, sp + ms + n, mm - n);
+                    }
+                    const bool any = __any_sync(FM_FULL, go);
+                    if (go) pending = false;
                     __syncwarp();
+                    if (!any) { if (++idle > 2) __nanosleep(idle > 16 ? 256 : 32); } else idle = 0;
                 }
                 __syncwarp();
                 // flush
@@ -542,49 +559,50 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
                     if (done + lane < total) out[op0 + done + lane] = span[shift + done + lane];
                 }
                 op0 += total;
-                __threadfence_block();
                 __syncwarp();
-                if (lane == 0) owed[warp] = op0;
+                publish(op0);
                 continue;
             }
 
             // ---------- path B: long sequences, copied in place ----------
             op0 += total;
-            if (active && lit < LZ4_LONG)
-                for (int i = 0; i < lit; i++) out[my_op + i] = src[lit_src + i];
+            if (active && lit < LZ4_LONG) copy_batched(out + my_op, src + lit_src, lit);
             for (unsigned long_m = __ballot_sync(FM_FULL, active && lit >= LZ4_LONG); long_m; long_m &= long_m - 1) {
                 const int l = __ffs(long_m) - 1;
                 warp_copy_bytes(out + __shfl_sync(FM_FULL, my_op, l), src + __shfl_sync(FM_FULL, lit_src, l),
                                 __shfl_sync(FM_FULL, lit, l));
             }
             bool pending = active && ml > 0;
-            const int need = (off == 0) ? 0 : min(d - off + ml, d);   // everything below this must exist
+            const int need = (off == 0) ? 0 : min(mstart + ml, d);   // everything below this must exist
+            int idle = 0;
             for (;;) {
                 const int wmin = warp_min(pending ? d : 0x7fffffff);
-                __threadfence_block();                // our finished bytes before the new mark
-                if (lane == 0) owed[warp] = (wmin == 0x7fffffff) ? op0 : wmin;
+                publish(wmin == 0x7fffffff ? op0 : wmin);
                 if (wmin == 0x7fffffff) break;
                 __syncwarp();
-                const int hwm = warp_min(lane < LZ4_COPY_WARPS ? owed[lane] : 0x7fffffff);
+                // alone in the block, everything below our own lowest pending match is complete
+                const int hwm = (W == 1) ? wmin : high_water();
                 __threadfence_block();
                 const bool go = pending && need <= hwm;
                 if (go && ml < LZ4_LONG) {
                     if (off == 0) { for (int i = 0; i < ml; i++) out[d + i] = 0; }
-                    else { for (int i = 0; i < ml; i++) out[d + i] = out[d - off + i]; }
+                    else { for (int i = 0; i < ml; i++) out[d + i] = out[mstart + i]; }
                 }
                 for (unsigned long_m = __ballot_sync(FM_FULL, go && ml >= LZ4_LONG); long_m; long_m &= long_m - 1) {
                     const int l = __ffs(long_m) - 1;
                     warp_copy_match(out, __shfl_sync(FM_FULL, d, l), __shfl_sync(FM_FULL, off, l),
                                     __shfl_sync(FM_FULL, ml, l));
                 }
+                const bool any = __any_sync(FM_FULL, go);
                 if (go) pending = false;
+                __syncwarp();
+                if (!any) { if (++idle > 2) __nanosleep(idle > 16 ? 256 : 32); } else idle = 0;
             }
         }
         __syncwarp();
     }
     // a finished warp must not hold the mark down
-    __threadfence_block();
-    if (lane == 0) owed[warp] = 0x7fffffff;
+    publish(0x7fffffff);
 }
 
 // ---- D0 ------------------------------------------------------------------------------------

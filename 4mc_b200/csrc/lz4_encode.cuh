@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
                 *o++ = (uint8_t)((min(lit, 15) << 4) | min(ml, 15));
                 if (lit >= 15) o = emit_len(o, lit - 15);
                 if (lit > ENC_SLICE) { long_n = lit; long_src = a; long_dst = o; }
-                else { for (int i = 0; i < lit; i++) o[i] = data[a + i]; }
+                else copy_batched(o, data + a, lit);
                 o += lit;
                 *o++ = (uint8_t)(off & 0xff); *o++ = (uint8_t)(off >> 8);
                 if (ml >= 15) o = emit_len(o, ml - 15);

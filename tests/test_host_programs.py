@@ -1,0 +1,120 @@
+"""The host programs on top of the C-ABI: the `4mc` CLI (flags, exit codes, files the reference CLI can
+read and vice versa) and the JNI library driven through a fake JNIEnv (tests/native/jni_mock.c)."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT, golden_bytes, gen_logtext
+
+HOST = os.path.join(ROOT, "4mc_b200", "host")
+CLI = os.path.join(HOST, "4mc")
+JNI = os.path.join(HOST, "libhadoop-4mc.so")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def build_host(pkg):
+    pkg.build()
+    subprocess.run(["make", "-C", HOST, "-s"], check=True)
+
+
+def test_jni_library_exports_the_reference_symbols():
+    """Exactly the 35 Java_* symbols of the shipped reference library (tests/golden/jni_symbols.txt,
+    from `nm -D` of java/hadoop-4mc/src/main/resources/.../linux/amd64/libhadoop-4mc.so)."""
+    want = open(os.path.join(ROOT, "tests", "golden", "jni_symbols.txt")).read().split()
+    out = subprocess.run(["nm", "-D", JNI], capture_output=True, text=True, check=True).stdout
+    have = sorted(l.split()[2] for l in out.splitlines() if " T Java_" in l)
+    assert have == sorted(want) and len(have) == 35
+
+
+def test_jni_table_layout_matches_the_jni_specification():
+    subprocess.run(["gcc", "-O1", "-shared", "-fPIC", "-o", os.path.join(ROOT, "tests", "_build", "jni_mock.so"),
+                    os.path.join(ROOT, "tests", "native", "jni_mock.c"), "-ldl"], check=True)
+    M = C.CDLL(os.path.join(ROOT, "tests", "_build", "jni_mock.so"))
+    offs = (C.c_int * 13)()
+    M.mock_slot_offsets(offs)
+    # slots 6, 14, 23, 94, 95, 100, 101, 109, 110, 167, 222, 223, 230, 8 bytes each
+    assert list(offs) == [8 * s for s in (6, 14, 23, 94, 95, 100, 101, 109, 110, 167, 222, 223, 230)]
+
+
+def test_cli_fails_loudly_without_a_device(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = tmp_path / "in.bin"
+    p.write_bytes(b"hello")
+    r = subprocess.run([CLI, "-f", str(p), str(tmp_path / "o.4mc")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no usable CUDA device" in r.stderr
+    assert subprocess.run([CLI, "-V"], capture_output=True).returncode == 0
+    assert subprocess.run([CLI, "-x"], capture_output=True).returncode == 1          # bad usage -> exit 1
+
+
+# ---------------------------------------------------------------- on the GPU box
+
+@pytest.mark.gpu
+def test_cli_round_trip_and_cross_compatibility(ref_cli, pkg, tmp_path):
+    data = gen_logtext(pkg, 9 * 1024 * 1024 + 1234) + bytes(70000)
+    src = tmp_path / "d.bin"
+    src.write_bytes(data)
+    ours, theirs = tmp_path / "ours.4mc", tmp_path / "theirs.4mc"
+    assert subprocess.run([CLI, "-f", "-q", "-1", str(src), str(ours)]).returncode == 0
+    subprocess.run([ref_cli, "-f", "-q", "-q", "-1", str(src), str(theirs)], check=True)
+    out1, out2, out3 = tmp_path / "o1", tmp_path / "o2", tmp_path / "o3"
+    subprocess.run([ref_cli, "-f", "-q", "-q", "-d", str(ours), str(out1)], check=True)      # reference reads ours
+    assert subprocess.run([CLI, "-f", "-q", "-d", str(theirs), str(out2)]).returncode == 0   # we read the reference's
+    assert subprocess.run([CLI, "-f", "-q", "-d", str(ours), str(out3)]).returncode == 0
+    assert out1.read_bytes() == data and out2.read_bytes() == data and out3.read_bytes() == data
+    # -t (test) and stdin/stdout plumbing
+    assert subprocess.run([CLI, "-q", "-t", str(ours)]).returncode == 0
+    r = subprocess.run([CLI, "-q", "-c", "-d", str(theirs)], capture_output=True)
+    assert r.returncode == 0 and r.stdout == data
+
+
+@pytest.mark.gpu
+def test_cli_exit_codes_match_reference(ref_cli, tmp_path):
+    good = golden_bytes("logtext_128k.l1.4mc")
+    cases = {}
+    b = bytearray(good); b[100] ^= 1; cases["payload"] = bytes(b)
+    b = bytearray(good); b[9] ^= 1; cases["header"] = bytes(b)
+    b = bytearray(good); b[-1] ^= 1; cases["footer"] = bytes(b)
+    cases["truncated"] = good[:20]
+    cases["magic"] = good.replace(b"4MC\0", b"4MZ\0", 1)
+    for name, blob in cases.items():
+        p = tmp_path / (name + ".4mc")
+        p.write_bytes(blob)
+        ours = subprocess.run([CLI, "-f", "-q", "-d", str(p), str(tmp_path / "x")], capture_output=True).returncode
+        ref = subprocess.run([ref_cli, "-f", "-q", "-d", str(p), str(tmp_path / "y")], capture_output=True).returncode
+        assert ours == ref, name
+
+
+@pytest.mark.gpu
+def test_jni_shim_through_fake_jvm(ora, pkg):
+    subprocess.run(["gcc", "-O1", "-shared", "-fPIC", "-o", os.path.join(ROOT, "tests", "_build", "jni_mock.so"),
+                    os.path.join(ROOT, "tests", "native", "jni_mock.c"), "-ldl"], check=True)
+    M = C.CDLL(os.path.join(ROOT, "tests", "_build", "jni_mock.so"))
+    assert M.mock_open(JNI.encode()) == 0
+    assert M.mock_bound(4 * 1024 * 1024) == 4210768
+    data = gen_logtext(pkg, 4 * 1024 * 1024)
+    msg = C.create_string_buffer(512)
+    la, threw = C.c_int(), C.c_int()
+    for which, lvl in ((0, 0), (1, 0), (2, 4), (2, 8)):
+        src = C.create_string_buffer(data, len(data))
+        dst = C.create_string_buffer(4210768)
+        r = M.mock_compress(which, lvl, src, len(data), dst, C.byref(la), C.byref(threw), msg)
+        assert r > 0 and threw.value == 0 and la.value == 0            # uncompressedDirectBufLen reset (jniCompressor.c:94)
+        assert ora.lz4_decompress(dst.raw[:r], len(data)) == (len(data), data)
+        out = C.create_string_buffer(4 * 1024 * 1024)
+        comp = C.create_string_buffer(dst.raw[:r], r)
+        d = M.mock_decompress(comp, r, out, 4 * 1024 * 1024, C.byref(la), C.byref(threw), msg)
+        assert d == len(data) and out.raw[:d] == data and la.value == 0 and threw.value == 0
+    # corrupt block -> InternalError with the reference's message format (jniDecompressor.c:93-97)
+    bad = C.create_string_buffer(bytes.fromhex("1041 0900 C0") + b"0123456789ab", 17)
+    out = C.create_string_buffer(64)
+    d = M.mock_decompress(bad, 17, out, 17, C.byref(la), C.byref(threw), msg)
+    assert d == -5 and threw.value == 1 and msg.value == b"java/lang/InternalError: LZ4_decompress_safe returned: -5"
+    # xxhash32(byte[] buf, int off, int len, int seed) on all four classes
+    buf = C.create_string_buffer(b"xx" + b"Nobody inspects the spammish repetition" + b"yy")
+    for cls in range(4):
+        assert M.mock_xxh(cls, buf, 2, 39, 0) & 0xFFFFFFFF == 0xE2293B2F
+    assert M.mock_zstd_throws(msg) == 1 and b"InternalError" in msg.value
