@@ -532,18 +532,12 @@ int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in
     return dec_blocks(ctx, st, ws, nb, max_chunks, 1, nullptr, (const IndexInfo *)ws.info.p, d_result);
 }
 
-int fourmc_lz4_decompress_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_blocks, const void *d_src,
-                                       const uint64_t *d_src_off, const uint32_t *d_csize, const uint32_t *d_usize,
-                                       const uint32_t *d_xxh, int check_xxh, void *d_dst, const uint64_t *d_dst_off,
-                                       int32_t *d_out_size, uint8_t *d_status)
+// batch decode over caller tables with an explicit workspace (the host pipeline keeps two in flight)
+static int dec_batch(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, const void *d_src,
+                     const uint64_t *d_src_off, const uint32_t *d_csize, const uint32_t *d_usize, const uint32_t *d_xxh,
+                     int check_xxh, void *d_dst, const uint64_t *d_dst_off, int32_t *d_out_size, uint8_t *d_status)
 {
-    if (!ctx || !d_src || !d_src_off || !d_csize || !d_usize || !d_dst_off) return FOURMC_E_ARG;
-    if (check_xxh && !d_xxh) return FOURMC_E_ARG;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = pick(ctx, stream);
-    DecWs &ws = ctx->dec[0];
     int r;
-    const uint32_t nb = n_blocks;
     if ((r = ensure(ctx, ws.desc, (size_t)std::max<uint32_t>(nb, 1) * sizeof(BlockDesc)))) return r;
     if ((r = ensure(ctx, ws.xxh, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
     if ((r = ensure(ctx, ws.status, (size_t)std::max<uint32_t>(nb, 1)))) return r;
@@ -556,6 +550,18 @@ int fourmc_lz4_decompress_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n
     if ((r = dec_blocks(ctx, st, ws, nb, max_chunks, check_xxh, d_out_size, nullptr, nullptr))) return r;
     if (d_status) CK(cudaMemcpyAsync(d_status, ws.status.p, nb, cudaMemcpyDeviceToDevice, st));
     return FOURMC_OK;
+}
+
+int fourmc_lz4_decompress_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_blocks, const void *d_src,
+                                       const uint64_t *d_src_off, const uint32_t *d_csize, const uint32_t *d_usize,
+                                       const uint32_t *d_xxh, int check_xxh, void *d_dst, const uint64_t *d_dst_off,
+                                       int32_t *d_out_size, uint8_t *d_status)
+{
+    if (!ctx || !d_src || !d_src_off || !d_csize || !d_usize || !d_dst_off) return FOURMC_E_ARG;
+    if (check_xxh && !d_xxh) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return dec_batch(ctx, pick(ctx, stream), ctx->dec[0], n_blocks, d_src, d_src_off, d_csize, d_usize, d_xxh, check_xxh,
+                     d_dst, d_dst_off, d_out_size, d_status);
 }
 
 int fourmc_xxh32_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_items, const void *d_base,
@@ -879,8 +885,8 @@ long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
         uint8_t *d_st = (uint8_t *)(d_osz + cnt);
         // XXH32 of every item's payload (blocks and footers), compared with the headers below
         if ((r = fourmc_xxh32_batch_device(ctx, st, cnt, ctx->stage_in[b].p, d_src_off, d_c, 0, d_hash))) return r;
-        if ((r = fourmc_lz4_decompress_batch_device(ctx, st, cnt, ctx->stage_in[b].p, d_src_off, d_c, d_u, d_hash, 0,
-                                                    ctx->stage_out[b].p, d_dst_off, d_osz, d_st)))
+        if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[b].p, d_src_off, d_c, d_u, d_hash, 0,
+                           ctx->stage_out[b].p, d_dst_off, d_osz, d_st)))
             return r;
         if (s.d1 > s.d0)
             CK(cudaMemcpyAsync((uint8_t *)out + s.d0, ctx->stage_out[b].p, s.d1 - s.d0, cudaMemcpyDeviceToHost, st));

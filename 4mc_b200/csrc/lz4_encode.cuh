@@ -40,7 +40,9 @@ constexpr int ENC_SLICE = 132;
 constexpr int ENC_HASH_BITS = 14;
 constexpr int ENC_MAXREC = ENC_SLICE / 4 + 1;    // inner records of one slice
 constexpr int ENC_PAD = 64;
-constexpr size_t ENC_SMEM = ENC_REGION + ENC_PAD + (sizeof(uint16_t) << ENC_HASH_BITS);
+constexpr int ENC_STAGE = 48 * 1024;             // output staging: the (dead) hash table + 16 KiB
+constexpr size_t ENC_SMEM = ENC_REGION + ENC_PAD + ENC_STAGE;
+static_assert((sizeof(uint16_t) << ENC_HASH_BITS) <= ENC_STAGE, "the hash table lives inside the staging area");
 
 static_assert(ENC_THREADS * ENC_SLICE >= ENC_REGION, "slices must cover the region");
 
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
     uint16_t *table = (uint16_t *)(smem + ENC_REGION + ENC_PAD);
     __shared__ int s_scan[ENC_WARPS];
     __shared__ uint32_t s_work;
+    __shared__ int s_flush;
     __shared__ __align__(8) uint64_t s_bar;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -172,12 +175,21 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
         }
         __syncthreads();
 
-        // ---- index: first occurrence of every 4-byte hash (descending sweep, later stores win)
+        // ---- index: first occurrence of every 4-byte hash.  Descending sweep, 4 consecutive
+        // positions per thread (two word loads, three funnel shifts); within a thread and between
+        // steps the lower position is stored last, within a step the order is left to the race.
         {
             const int last = rlen - 4;                             // last position with 4 bytes
-            for (int base = ((rlen - 1) / ENC_THREADS) * ENC_THREADS; base >= 0; base -= ENC_THREADS) {
-                const int p = base + tid;
-                if (p <= last) table[enc_hash(smem_read4(data32, p))] = (uint16_t)p;
+            constexpr int STEP = ENC_THREADS * 4;
+            for (int base = ((rlen - 1) / STEP) * STEP; base >= 0; base -= STEP) {
+                const int p = base + 4 * tid;
+                if (p <= last) {
+                    const uint32_t w0 = data32[p >> 2], w1 = data32[(p >> 2) + 1];
+                    if (p + 3 <= last) table[enc_hash(__funnelshift_r(w0, w1, 24))] = (uint16_t)(p + 3);
+                    if (p + 2 <= last) table[enc_hash(__funnelshift_r(w0, w1, 16))] = (uint16_t)(p + 2);
+                    if (p + 1 <= last) table[enc_hash(__funnelshift_r(w0, w1, 8))] = (uint16_t)(p + 1);
+                    table[enc_hash(w0)] = (uint16_t)p;
+                }
                 __syncthreads();
             }
         }
@@ -191,8 +203,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
         if (ss < rlen) {
             const int se = min(ss + ENC_SLICE, rlen);
             int p = ss, anchor = ss;
+            uint32_t w_lo = data32[p >> 2], w_hi = data32[(p >> 2) + 1];   // rolling 8-byte window at p
             while (p < se && p <= mf_limit) {
-                const uint32_t v = smem_read4(data32, p);
+                const uint32_t v = __funnelshift_r(w_lo, w_hi, (p & 3) * 8);
                 const int c = (int)table[enc_hash(v)];
                 if (c < p && smem_read4(data32, c) == v) {
                     int len = 4;
@@ -209,10 +222,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
                         if (l_len) rec[nrec++] = enc_pack(l_st - ss, l_len, l_off);
                         l_st = st; l_len = len; l_off = st - m;
                         p = st + len; anchor = p;
+                        w_lo = data32[p >> 2]; w_hi = data32[(p >> 2) + 1];
                         continue;
                     }
                 }
                 p++;
+                if ((p & 3) == 0) { w_lo = w_hi; w_hi = data32[(p >> 2) + 1]; }
             }
         }
 
@@ -260,13 +275,21 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
         const int out_off = cta_excl_scan<false>(bytes, s_scan, &total_bytes);
         const int seq_before = cta_excl_scan<false>(myseq, s_scan, &total_seq);
 
-        // ---- emit.  Only a slice's first literal run can be long (it may reach back over
-        // match-free slices); those are copied by the whole warp afterwards.
+        // ---- emit into the staging area (the hash table is dead now), flushed below with 128-bit
+        // stores; sequences beyond its capacity (poorly compressible regions) go straight to HBM.
+        // Only a slice's first literal run can be long (it may reach back over match-free slices);
+        // those are copied by the whole warp afterwards.
         uint8_t *slot = P.scratch + (size_t)rg * ENC_SLOT;
+        uint8_t *stage = (uint8_t *)table;
+        __syncthreads();                                            // every thread is done with the table
+        const bool staged = out_off + bytes <= ENC_STAGE;
+        if (tid == 0) s_flush = min(total_bytes, ENC_STAGE);
+        __syncthreads();
+        if (!staged && bytes > 0) atomicMin(&s_flush, out_off);     // the staged prefix ends at the first direct writer
         int long_n = 0, long_src = 0;
         uint8_t *long_dst = nullptr;
         {
-            uint8_t *o = slot + out_off;
+            uint8_t *o = (staged ? stage : slot) + out_off;
             int a = anchor0;
             for (int k = 0; k <= nrec; k++) {
                 int st, len, off;
@@ -295,6 +318,14 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
             const int sp = __shfl_sync(FM_FULL, long_src, l);
             uint8_t *dp = (uint8_t *)__shfl_sync(FM_FULL, (unsigned long long)long_dst, l);
             for (int i = lane; i < n; i += 32) dp[i] = data[sp + i];
+        }
+        __syncthreads();
+        {
+            const int nflush = s_flush;
+            const uint4 *sv = (const uint4 *)stage;
+            uint4 *dv = (uint4 *)slot;
+            for (int i = tid; i < (nflush >> 4); i += ENC_THREADS) dv[i] = sv[i];
+            for (int i = (nflush & ~15) + tid; i < nflush; i += ENC_THREADS) slot[i] = stage[i];
         }
         if (tid == 0) {
             RegionMeta *mt = &P.meta[rg];
