@@ -69,11 +69,11 @@ constexpr int D1_HALF = 2048;             // bytes per ring half
 constexpr int D1_RING = 2 * D1_HALF;
 constexpr int D1_WARPS = 4;               // blocks per CTA
 constexpr int D1_SUB = 64;                // positions per lane per half (32 lanes x 64 = one half)
-constexpr int D1_A_WORDS = (D1_HALF + 2 * 32 + 8) / 2;     // u16 table, 2 entries of padding per sub-chunk
-constexpr int D1_B_WORDS = D1_HALF + 32 + 8;               // u32 table, 1 entry of padding per sub-chunk
-constexpr int D1_WARP_SMEM = D1_RING + D1_A_WORDS * 4 + D1_B_WORDS * 4 + 64 * 4 + 64 * 2;
+constexpr int D1_X_STRIDE = D1_SUB + 4;                    // u8 exit table, 4 bytes of padding per sub-chunk
+constexpr int D1_S_STRIDE = D1_SUB + 2;                    // u16 output table, 1 word of padding per sub-chunk
+constexpr int D1_WARP_SMEM = D1_RING + 32 * D1_X_STRIDE + 32 * D1_S_STRIDE * 2 + 32 * 4 + 32 * 2;
 constexpr int D1_SMEM = D1_WARPS * ((D1_WARP_SMEM + 15) & ~15);
-constexpr int D1_SPECIAL = 0x8000;
+constexpr int D1_SPECIAL = 0x80;           // exit-table flag: the chain stops at a token with a continued length
 constexpr int D1_NONE = 0xffff;
 
 // bytes of the compressed block through this warp's shared-memory ring; positions outside the
@@ -120,11 +120,10 @@ __device__ __forceinline__ SeqDec d1_decode_slow(const RingReader &rd, int ip, i
 // D1.  One WARP per block.  All lanes stream the payload through a double-buffered ring.
 //
 // BULK phase (all of the block except its last few sequences), one 2 KiB half at a time:
-//   A  every byte position is decoded AS IF a token started there (length of that sequence in the
-//      stream, bytes it produces) -- 64 positions per lane, no dependencies;
-//   B  each lane folds its own 64-position sub-chunk back to front into an "exit function":
-//      for every entry position, where the chain leaves the sub-chunk and how many bytes it
-//      produced on the way;
+//   B  each lane reads every byte position of its own 64-byte sub-chunk AS IF a token started
+//      there and folds the sub-chunk back to front into an "exit function": for every entry
+//      position, where the chain leaves the sub-chunk and how many bytes it produced on the way
+//      (straight-line code over 16 registers; the only memory traffic is the table itself);
 //   C  lane 0 walks the real chain with ONE table lookup per sub-chunk instead of one dependent
 //      step per sequence (32 hops per half instead of ~400 sequences);
 //   D  every lane re-walks its sub-chunk from its real entry: sets the token bits, checks the
@@ -147,10 +146,10 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
     if (bd.stored) { if (lane == 0) result[b] = (int32_t)bd.usize; return; }
 
     uint8_t *ring = d1_smem + (size_t)warp * ((D1_WARP_SMEM + 15) & ~15);
-    uint16_t *A = (uint16_t *)(ring + D1_RING);                    // seq length -> exit position
-    uint32_t *B = (uint32_t *)(ring + D1_RING + D1_A_WORDS * 4);   // seq output -> output until exit
-    uint32_t *s_op = B + D1_B_WORDS;                               // per sub-chunk: op at its entry
-    uint16_t *s_entry = (uint16_t *)(s_op + 64);                   // per sub-chunk: entry position
+    uint8_t *X = ring + D1_RING;                                   // [32][D1_X_STRIDE] exit of the sub-chunk from each entry
+    uint16_t *S = (uint16_t *)(X + 32 * D1_X_STRIDE);              // [32][D1_S_STRIDE] bytes produced on the way
+    uint32_t *s_op = (uint32_t *)(S + 32 * D1_S_STRIDE);           // per sub-chunk: op at its entry
+    uint16_t *s_entry = (uint16_t *)(s_op + 32);                   // per sub-chunk: entry position
 
     const uintptr_t a = (uintptr_t)bd.src;
     const uint4 *base = (const uint4 *)(a & ~(uintptr_t)15);
@@ -174,8 +173,6 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
         uint4 *q = (uint4 *)(ring + (h & 1) * D1_HALF);
         q[lane] = r0; q[lane + 32] = r1; q[lane + 64] = r2; q[lane + 96] = r3;
     };
-    auto idxA = [](int j) { return j + 2 * (j >> 6); };   // padded: sub-chunks start in distinct banks
-    auto idxB = [](int j) { return j + (j >> 6); };
 
     ParseState st;
     TokSink sink;
@@ -202,36 +199,28 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
             rd.ring = ring; rd.src = bd.src; rd.d = d;
             rd.lo = base_q - d; rd.span = min(base_q + D1_RING - d, csize) - rd.lo;
 
-            // ---- A: every position as a token (at most one continuation byte per field)
-#pragma unroll 4
-            for (int i = 0; i < D1_SUB; i++) {
-                const int j = i * 32 + lane;
-                const int q = base_q + j;
-                const unsigned tok = ring[q & (D1_RING - 1)];
-                int lit = (int)(tok >> 4), ml = (int)(tok & 15), e = 1;
-                bool special = false;
-                if (lit == 15) { const unsigned x = ring[(q + 1) & (D1_RING - 1)]; special = x == 255; lit += (int)x; e = 2; }
-                if (ml == 15) { const unsigned x = ring[(q + e + lit + 2) & (D1_RING - 1)]; special |= x == 255; ml += (int)x; e++; }
-                A[idxA(j)] = special ? (uint16_t)0 : (uint16_t)(e + lit + 2);
-                B[idxB(j)] = (uint32_t)(lit + ml + 4);
-            }
-            __syncwarp();
-            // ---- B: exit function of my sub-chunk, back to front, in place
+            // ---- B: exit function of my 64-position sub-chunk, back to front.  Each position is
+            // read AS IF a token started there: a sequence without continued lengths is 3 + lit
+            // bytes long and produces lit + ml + 4 bytes; a token with a length nibble of 15 stops
+            // the fold (the chain walk decodes that sequence byte by byte).
             {
-                const int s0 = lane * D1_SUB, s1 = s0 + D1_SUB;
-#pragma unroll 4
-                for (int j = s1 - 1; j >= s0; j--) {
-                    const int sl = (int)A[idxA(j)];
-                    uint32_t os = B[idxB(j)];
-                    int ex;
-                    if (sl == 0) { ex = j | D1_SPECIAL; os = 0; }
-                    else {
-                        const int n = j + sl;
-                        if (n < s1) { ex = (int)A[idxA(n)]; os += B[idxB(n)]; }
-                        else ex = n;
-                    }
-                    A[idxA(j)] = (uint16_t)ex;
-                    B[idxB(j)] = os;
+                const uint4 *mine = (const uint4 *)(ring + ((base_q + lane * D1_SUB) & (D1_RING - 1)));
+                uint32_t w[16];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { const uint4 v = mine[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+                uint8_t *xm = X + lane * D1_X_STRIDE;
+                uint16_t *sm = S + lane * D1_S_STRIDE;
+#pragma unroll
+                for (int jj = D1_SUB - 1; jj >= 0; jj--) {
+                    const unsigned tok = (w[jj >> 2] >> ((jj & 3) * 8)) & 0xffu;
+                    const int lit = (int)(tok >> 4), ml = (int)(tok & 15);
+                    const int n = jj + 3 + lit;
+                    int ex, os = lit + ml + 4;
+                    if (lit == 15 || ml == 15) { ex = jj | D1_SPECIAL; os = 0; }
+                    else if (n < D1_SUB) { ex = (int)xm[n]; os += (int)sm[n]; }
+                    else ex = n;
+                    xm[jj] = (uint8_t)ex;
+                    sm[jj] = (uint16_t)os;
                 }
             }
             s_entry[lane] = (uint16_t)D1_NONE;
@@ -239,17 +228,18 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
             // ---- C: lane 0 hops sub-chunk to sub-chunk along the real chain
             int e = e_q - base_q, op = e_op;
             if (lane == 0) {
+                int last_sc = -1;
                 while (e < D1_HALF) {
-                    const int sc = e >> 6;
-                    if (s_entry[sc] == D1_NONE) { s_entry[sc] = (uint16_t)e; s_op[sc] = (uint32_t)op; }
-                    const int x = (int)A[idxA(e)];
-                    op += (int)B[idxB(e)];
+                    const int sc = e >> 6, jj = e & (D1_SUB - 1);
+                    if (sc != last_sc) { s_entry[sc] = (uint16_t)e; s_op[sc] = (uint32_t)op; last_sc = sc; }
+                    const int x = (int)X[sc * D1_X_STRIDE + jj];
+                    op += (int)S[sc * D1_S_STRIDE + jj];
                     if (x & D1_SPECIAL) {
-                        const SeqDec sd = d1_decode_slow(rd, base_q + (x & 0x7fff) - d, clean_ip);
+                        const SeqDec sd = d1_decode_slow(rd, base_q + sc * D1_SUB + (x & (D1_SUB - 1)) - d, clean_ip);
                         if (!sd.clean) break;             // phase D finds it too and ends the bulk phase
                         op += sd.lit + sd.ml;
                         e = sd.next + d - base_q;
-                    } else e = x;
+                    } else e = sc * D1_SUB + x;
                 }
             }
             e = __shfl_sync(FM_FULL, e, 0); op = __shfl_sync(FM_FULL, op, 0);

@@ -61,35 +61,30 @@ extern "C" int d1_emul(const uint8_t *src, int csize, int cap, int d, uint32_t *
         std::vector<int> A(HALF), Bv(HALF);
         while (bulk) {
             const int k = e_q >> 11, base_q = k * HALF;
-            for (int j = 0; j < HALF; j++) {                       // phase A
-                const int q = base_q + j;
-                const unsigned tok = rd.at_q(q);
-                int lit = (int)(tok >> 4), ml = (int)(tok & 15), e = 1; bool special = false;
-                if (lit == 15) { unsigned x = rd.at_q(q + 1); special = x == 255; lit += (int)x; e = 2; }
-                if (ml == 15) { unsigned x = rd.at_q(q + e + lit + 2); special |= x == 255; ml += (int)x; e++; }
-                A[j] = special ? 0 : e + lit + 2; Bv[j] = lit + ml + 4;
-            }
-            for (int lane = 0; lane < 32; lane++) {                // phase B
-                const int s0 = lane * SUB, s1 = s0 + SUB;
-                for (int j = s1 - 1; j >= s0; j--) {
-                    const int sl = A[j]; int os = Bv[j], ex;
-                    if (sl == 0) { ex = j | SPECIAL; os = 0; }
-                    else { const int n = j + sl; if (n < s1) { ex = A[n]; os += Bv[n]; } else ex = n; }
-                    A[j] = ex; Bv[j] = os;
+            for (int lane = 0; lane < 32; lane++) {                // phase B (per sub-chunk, local exits)
+                for (int jj = SUB - 1; jj >= 0; jj--) {
+                    const unsigned tok = rd.at_q(base_q + lane * SUB + jj);
+                    const int lit = (int)(tok >> 4), ml = (int)(tok & 15), n = jj + 3 + lit;
+                    int ex, os = lit + ml + 4;
+                    if (lit == 15 || ml == 15) { ex = jj | 0x80; os = 0; }
+                    else if (n < SUB) { ex = A[lane * SUB + n]; os += Bv[lane * SUB + n]; }
+                    else ex = n;
+                    A[lane * SUB + jj] = ex; Bv[lane * SUB + jj] = os;
                 }
             }
             int entry[32], eop[32];
             for (int i = 0; i < 32; i++) entry[i] = NONE;
             int e = e_q - base_q, op = e_op;                       // phase C
+            int last_sc = -1;
             while (e < HALF) {
-                const int sc = e >> 6;
-                if (entry[sc] == NONE) { entry[sc] = e; eop[sc] = op; }
-                const int x = A[e]; op += Bv[e];
-                if (x & SPECIAL) {
-                    const SeqDec sd = decode_slow(rd, base_q + (x & 0x7fff) - d, clean_ip);
+                const int sc = e >> 6, jj = e & (SUB - 1);
+                if (sc != last_sc) { entry[sc] = e; eop[sc] = op; last_sc = sc; }
+                const int x = A[sc * SUB + jj]; op += Bv[sc * SUB + jj];
+                if (x & 0x80) {
+                    const SeqDec sd = decode_slow(rd, base_q + sc * SUB + (x & (SUB - 1)) - d, clean_ip);
                     if (!sd.clean) break;
                     op += sd.lit + sd.ml; e = sd.next + d - base_q;
-                } else e = x;
+                } else e = sc * SUB + x;
             }
             int pu = 0x7fffffff, pv = 0x7fffffff, pu_op = 0, pv_next = 0;   // phase D
             int first_op[32];
