@@ -38,17 +38,19 @@ struct DecWs {
 
 }  // namespace
 
+constexpr int FM_PIPE_MAX = 4;
+
 struct fourmc_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;       // default stream of the context
-    cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t aux[FM_PIPE_MAX] = {};     // host-buffer pipelines: one stream + buffer set per slice in flight
+    cudaEvent_t ev[FM_PIPE_MAX] = {};
     std::string err;
     uint64_t launches = 0;
-    EncWs enc[2];
-    DecWs dec[2];
-    DevBuf stage_in[2], stage_out[2];    // device staging for the host-pointer entry points
+    EncWs enc[FM_PIPE_MAX];
+    DecWs dec[FM_PIPE_MAX];
+    DevBuf stage_in[FM_PIPE_MAX], stage_out[FM_PIPE_MAX];    // device staging for the host-pointer entry points
     void *pinned = nullptr;              // small pinned scratch for scalars
     size_t pinned_cap = 0;
     bool region_attr_set = false;
@@ -153,9 +155,21 @@ int slice_blocks()
     static int v = 0;
     if (!v) {
         const char *e = getenv("FOURMC_SLICE_BLOCKS");
-        v = e ? atoi(e) : 256;
+        v = e ? atoi(e) : 128;
         if (v < 1) v = 1;
         if (v > 4096) v = 4096;
+    }
+    return v;
+}
+
+int pipe_depth()
+{
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("FOURMC_PIPE");
+        v = e ? atoi(e) : 4;
+        if (v < 2) v = 2;
+        if (v > FM_PIPE_MAX) v = FM_PIPE_MAX;
     }
     return v;
 }
@@ -349,7 +363,7 @@ int fourmc_ctx_create(fourmc_ctx **out, int device)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return FOURMC_E_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FOURMC_E_CUDA; }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < FM_PIPE_MAX; i++) {
         if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming) != cudaSuccess) {
             fourmc_ctx_destroy(ctx);
@@ -365,7 +379,7 @@ void fourmc_ctx_destroy(fourmc_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < FM_PIPE_MAX; i++) {
         EncWs &e = ctx->enc[i];
         release(e.scratch); release(e.meta); release(e.plan); release(e.lens); release(e.off); release(e.misc);
         DecWs &d = ctx->dec[i];
@@ -721,17 +735,19 @@ long long fourmc_4mc_compress_host(fourmc_ctx *ctx, int level, const void *in, s
     // all block lengths of the file, on the device, for the footer
     DevBuf &all_lens = ctx->dec[1].tables;
     if ((r = ensure(ctx, all_lens, (size_t)std::max<uint32_t>(nb, 1) * 4 + 64 + 32 + 4 * (size_t)nb))) return r;
-    uint64_t *h_span = (uint64_t *)ctx->pinned;          // [0], [1]: span size of the slice in flight per buffer
+    const int np = pipe_depth();
+    uint64_t *h_span = (uint64_t *)ctx->pinned;          // span size of the slice in flight, per pipeline slot
     size_t pos = 12;                                     // output position of the next span
     const size_t cap_in = std::min(n, sl_bytes) + 64, cap_out = std::min(n, sl_bytes) + 12 * sl_blocks + 64;
-    for (int i = 0; i < 2 && (size_t)i < std::max<size_t>(nslices, 1); i++) {
+    for (int i = 0; i < np && (size_t)i < std::max<size_t>(nslices, 1); i++) {
         if ((r = ensure(ctx, ctx->stage_in[i], cap_in))) return r;
         if ((r = ensure(ctx, ctx->stage_out[i], cap_out))) return r;
     }
-    // software pipeline: slice s is uploaded and compressed on aux[s&1] while slice s-1 downloads
-    for (size_t s = 0; s <= nslices; s++) {
+    // software pipeline: slice s is uploaded and compressed on its slot's stream while earlier
+    // slices download; spans are appended in order (each needs the sizes of all before it)
+    for (size_t s = 0; s < nslices + (size_t)np - 1; s++) {
         if (s < nslices) {
-            const int b = (int)(s & 1);
+            const int b = (int)(s % np);
             cudaStream_t st = ctx->aux[b];
             const size_t off = s * sl_bytes, len = std::min(sl_bytes, n - off);
             CK(cudaMemcpyAsync(ctx->stage_in[b].p, (const uint8_t *)in + off, len, cudaMemcpyHostToDevice, st));
@@ -741,18 +757,17 @@ long long fourmc_4mc_compress_host(fourmc_ctx *ctx, int level, const void *in, s
             CK(cudaMemcpyAsync(&h_span[b], (uint8_t *)ctx->enc[b].misc.p + 8, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(ctx->ev[b], st));
         }
-        if (s > 0) {
-            const int b = (int)((s - 1) & 1);
+        if (s + 1 >= (size_t)np && s + 1 - np < nslices) {
+            const int b = (int)((s + 1 - np) % np);
             cudaStream_t st = ctx->aux[b];
             CK(cudaEventSynchronize(ctx->ev[b]));
             const size_t span = (size_t)h_span[b];
             CK(cudaMemcpyAsync((uint8_t *)out + pos, ctx->stage_out[b].p, span, cudaMemcpyDeviceToHost, st));
             pos += span;
-            // the buffer pair is reused by slice s+1: its upload is queued on the same stream, in order
+            // the slot is reused by slice s+1: its upload is queued on the same stream, in order
         }
     }
-    CK(cudaStreamSynchronize(ctx->aux[0]));
-    CK(cudaStreamSynchronize(ctx->aux[1]));
+    for (int i = 0; i < np; i++) CK(cudaStreamSynchronize(ctx->aux[i]));
     // header + EOS + footer, assembled on the device from the gathered lengths
     cudaStream_t st = ctx->stream;
     uint8_t *d_hdr = (uint8_t *)all_lens.p + (((size_t)std::max<uint32_t>(nb, 1) * 4 + 15) & ~(size_t)15);
@@ -848,14 +863,16 @@ long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
     // everything the device reads from / writes to the host besides the payload lives in pinned
     // memory, so that no copy blocks the host and the two slice pipelines really overlap
     const size_t tb_host = (max_cnt * 28 + 63) & ~(size_t)63;
-    const size_t pin_need = 4096 + 2 * tb_host + blocks.size() * 5 + 64;
+    const size_t pin_need = 4096 + FM_PIPE_MAX * tb_host + blocks.size() * 5 + 64;
     if ((r = pinned_scratch(ctx, pin_need))) return r;
     uint8_t *pin = (uint8_t *)ctx->pinned + 4096;
-    uint8_t *h_tables[2] = {pin, pin + tb_host};
-    uint32_t *hashes = (uint32_t *)(pin + 2 * tb_host);
+    const int np = pipe_depth();
+    uint8_t *h_tables[FM_PIPE_MAX];
+    for (int i = 0; i < FM_PIPE_MAX; i++) h_tables[i] = pin + (size_t)i * tb_host;
+    uint32_t *hashes = (uint32_t *)(pin + FM_PIPE_MAX * tb_host);
     uint8_t *status = (uint8_t *)(hashes + blocks.size());
     for (size_t k = 0; k < slices.size(); k++) {
-        const int b = (int)(k & 1);
+        const int b = (int)(k % np);
         const Slice &s = slices[k];
         cudaStream_t st = ctx->aux[b];
         const uint32_t cnt = (uint32_t)(s.b1 - s.b0);
@@ -893,8 +910,7 @@ long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
         CK(cudaMemcpyAsync(status + s.b0, d_st, cnt, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(hashes + s.b0, d_hash, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaStreamSynchronize(ctx->aux[0]));
-    CK(cudaStreamSynchronize(ctx->aux[1]));
+    for (int i = 0; i < np; i++) CK(cudaStreamSynchronize(ctx->aux[i]));
     // verdict in stream order: checksum first (:637/:645), then the decoder (:662)
     for (size_t i = 0; i < blocks.size(); i++) {
         if (hashes[i] != blocks[i].xxh) return FOURMC_E_CONTENT;

@@ -392,6 +392,7 @@ __device__ __forceinline__ void smem_copy_seq(uint8_t *dst, const uint8_t *src, 
 }
 
 constexpr int LZ4_SPAN = 2048;            // output bytes a warp assembles in shared memory at once
+constexpr int LZ4_SCR = 80;               // scratch bytes per lane (64 used; 80 keeps 128-bit stores conflict-free)
 
 // W = warps per block (1, 2, 4 or 8): the host picks it from the batch size -- many blocks in
 // flight need few warps each (and then hardly ever wait on one another), few blocks need many.
@@ -404,6 +405,7 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
     __shared__ int s_ticket;
     __shared__ uint8_t s_tokpos[W][64];
     __shared__ __align__(16) uint8_t s_span[W][LZ4_SPAN + 32];
+    __shared__ __align__(16) uint8_t s_scr[W][32 * LZ4_SCR];      // per lane: 4 aligned 16-byte chunks of a match source
 
     const BlockDesc bd = blocks[blockIdx.x];
     if (bd.stored || result[blockIdx.x] < 0) return;
@@ -519,7 +521,21 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
                     if (W > 1) __threadfence_block();
                     const bool go = pending && need_ext <= hwm && need_in <= low;
                     if (go) {
-                        if (ext > 0 && ext < LZ4_LONG) copy_batched(sp + d, (const uint8_t *)out + mstart, ext);
+                        if (ext > 0 && ext < LZ4_LONG) {
+                            // the source is somewhere in HBM/L2: fetch it with (at most four) aligned
+                            // 128-bit loads instead of one load per byte -- every load of a scattered
+                            // address costs the L1 data pipe a wavefront per lane
+                            const uint8_t *gs = out + mstart;
+                            const int so = (int)((uintptr_t)gs & 15);
+                            const uint4 *gb = (const uint4 *)(gs - so);
+                            const int nch = (so + ext + 15) >> 4;
+                            uint4 *scr = (uint4 *)(s_scr[warp] + lane * LZ4_SCR);
+                            const uint4 z = make_uint4(0, 0, 0, 0);
+                            const uint4 q0 = ldg_v4(gb), q1 = nch > 1 ? ldg_v4(gb + 1) : z;
+                            const uint4 q2 = nch > 2 ? ldg_v4(gb + 2) : z, q3 = nch > 3 ? ldg_v4(gb + 3) : z;
+                            scr[0] = q0; scr[1] = q1; scr[2] = q2; scr[3] = q3;
+                            copy_batched(sp + d, (const uint8_t *)scr + so, ext);
+                        }
                         if (ml > ext && ext < LZ4_LONG) smem_copy_seq(sp + d + ext, sp + mstart + ext, ml - ext);
                     }
                     // long reads from HBM: the whole warp per match, then its in-span remainder

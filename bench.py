@@ -343,14 +343,21 @@ def main_ours(args):
         h_out = torch.empty(en, dtype=torch.uint8, pin_memory=True)
         torch.cuda.synchronize()
 
+        e2e_t = [0.0, 0.0]
+
         def e2e_step():
+            t_a = time.perf_counter()
             c = ctx.compress_host_ptr(h_in.data_ptr(), en, h_comp.data_ptr(), ecap)
+            t_b = time.perf_counter()
             d = ctx.decompress_host_ptr(h_comp.data_ptr(), c, h_out.data_ptr(), en)
+            e2e_t[0] += t_b - t_a
+            e2e_t[1] += time.perf_counter() - t_b
             assert d == en
             return c
         for _ in range(max(1, args.warmup)):
             e2e_step()
         barrier()
+        e2e_t[0] = e2e_t[1] = 0.0
         t0 = time.perf_counter()
         ec = 0
         for _ in range(args.steps):
@@ -359,7 +366,8 @@ def main_ours(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         assert bool(torch.equal(h_out[:1 << 20], h_in[:1 << 20])) and bool(torch.equal(h_out[-(1 << 20):], h_in[-(1 << 20):]))
         e2e = {"value": world * en * args.steps / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": en + ec,
-               "d2h_bytes_per_step": ec + en, "bytes_per_step": en, "ms_per_step": dt / args.steps * 1e3}
+               "d2h_bytes_per_step": ec + en, "bytes_per_step": en, "ms_per_step": dt / args.steps * 1e3,
+               "compress_GBps": world * en * args.steps / e2e_t[0] / 1e9, "decompress_GBps": world * en * args.steps / e2e_t[1] / 1e9}
         del h_in, h_comp, h_out
 
     cpu = None
