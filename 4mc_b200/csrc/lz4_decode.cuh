@@ -213,10 +213,16 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
 #pragma unroll
                 for (int jj = D1_SUB - 1; jj >= 0; jj--) {
                     const unsigned tok = (w[jj >> 2] >> ((jj & 3) * 8)) & 0xffu;
-                    const int lit = (int)(tok >> 4), ml = (int)(tok & 15);
-                    const int n = jj + 3 + lit;
+                    const int lit = (int)(tok >> 4);
+                    int ml = (int)(tok & 15), n = jj + 3 + lit;
+                    bool special = lit == 15;
+                    if (ml == 15 && !special) {       // one continuation byte is common (matches of 19+): fold it in
+                        const unsigned x = ring[(base_q + lane * D1_SUB + n) & (D1_RING - 1)];
+                        special = x == 255;
+                        ml += (int)x; n++;
+                    }
                     int ex, os = lit + ml + 4;
-                    if (lit == 15 || ml == 15) { ex = jj | D1_SPECIAL; os = 0; }
+                    if (special) { ex = jj | D1_SPECIAL; os = 0; }
                     else if (n < D1_SUB) { ex = (int)xm[n]; os += (int)sm[n]; }
                     else ex = n;
                     xm[jj] = (uint8_t)ex;
@@ -256,15 +262,22 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
                         const int ip = base_q + p - d;
                         int lit, mlen, off, next;
                         const unsigned tok = ring[(base_q + p) & (D1_RING - 1)];
-                        if ((tok >> 4) == 15 || (tok & 15) == 15) {
-                            const SeqDec sd = d1_decode_slow(rd, ip, clean_ip);
-                            if (!sd.clean) { uncl = p; uncl_op = o; break; }
-                            lit = sd.lit; mlen = sd.ml; off = sd.off; next = sd.next;
-                        } else {
+                        bool slow = (tok >> 4) == 15;
+                        if (!slow) {
                             lit = (int)(tok >> 4); mlen = (int)(tok & 15) + 4;
                             const int qo = base_q + p + 1 + lit;
                             off = (int)ring[qo & (D1_RING - 1)] | ((int)ring[(qo + 1) & (D1_RING - 1)] << 8);
                             next = ip + lit + 3;
+                            if (mlen == 19) {                 // continued match length: one more byte, usually the last
+                                const unsigned x = ring[(qo + 2) & (D1_RING - 1)];
+                                slow = x == 255;
+                                mlen += (int)x; next++;
+                            }
+                        }
+                        if (slow) {
+                            const SeqDec sd = d1_decode_slow(rd, ip, clean_ip);
+                            if (!sd.clean) { uncl = p; uncl_op = o; break; }
+                            lit = sd.lit; mlen = sd.ml; off = sd.off; next = sd.next;
                         }
                         if (next > clean_ip || o + lit + mlen >= clean_op) { uncl = p; uncl_op = o; break; }
                         if (off > o + lit) { viol = p; viol_next = next; break; }         // lz4.c:2041/:2065

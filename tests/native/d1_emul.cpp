@@ -64,9 +64,11 @@ extern "C" int d1_emul(const uint8_t *src, int csize, int cap, int d, uint32_t *
             for (int lane = 0; lane < 32; lane++) {                // phase B (per sub-chunk, local exits)
                 for (int jj = SUB - 1; jj >= 0; jj--) {
                     const unsigned tok = rd.at_q(base_q + lane * SUB + jj);
-                    const int lit = (int)(tok >> 4), ml = (int)(tok & 15), n = jj + 3 + lit;
+                    const int lit = (int)(tok >> 4); int ml = (int)(tok & 15), n = jj + 3 + lit;
+                    bool special = lit == 15;
+                    if (ml == 15 && !special) { const unsigned x = rd.at_q(base_q + lane * SUB + n); special = x == 255; ml += (int)x; n++; }
                     int ex, os = lit + ml + 4;
-                    if (lit == 15 || ml == 15) { ex = jj | 0x80; os = 0; }
+                    if (special) { ex = jj | 0x80; os = 0; }
                     else if (n < SUB) { ex = A[lane * SUB + n]; os += Bv[lane * SUB + n]; }
                     else ex = n;
                     A[lane * SUB + jj] = ex; Bv[lane * SUB + jj] = os;
@@ -96,15 +98,18 @@ extern "C" int d1_emul(const uint8_t *src, int csize, int cap, int d, uint32_t *
                 while (p < s1) {
                     const int ip = base_q + p - d; int lit, mlen, off, next;
                     const unsigned tok = rd.at_q(base_q + p);
-                    if ((tok >> 4) == 15 || (tok & 15) == 15) {
-                        const SeqDec sd = decode_slow(rd, ip, clean_ip);
-                        if (!sd.clean) { if (p < pu) { pu = p; pu_op = o; } break; }
-                        lit = sd.lit; mlen = sd.ml; off = sd.off; next = sd.next;
-                    } else {
+                    bool slow = (tok >> 4) == 15;
+                    if (!slow) {
                         lit = (int)(tok >> 4); mlen = (int)(tok & 15) + 4;
                         const int qo = base_q + p + 1 + lit;
                         off = (int)rd.at_q(qo) | ((int)rd.at_q(qo + 1) << 8);
                         next = ip + lit + 3;
+                        if (mlen == 19) { const unsigned x = rd.at_q(qo + 2); slow = x == 255; mlen += (int)x; next++; }
+                    }
+                    if (slow) {
+                        const SeqDec sd = decode_slow(rd, ip, clean_ip);
+                        if (!sd.clean) { if (p < pu) { pu = p; pu_op = o; } break; }
+                        lit = sd.lit; mlen = sd.ml; off = sd.off; next = sd.next;
                     }
                     if (next > clean_ip || o + lit + mlen >= clean_op) { if (p < pu) { pu = p; pu_op = o; } break; }
                     if (off > o + lit) { if (p < pv) { pv = p; pv_next = next; } break; }
