@@ -69,11 +69,11 @@ constexpr int D1_HALF = 2048;             // bytes per ring half
 constexpr int D1_RING = 2 * D1_HALF;
 constexpr int D1_WARPS = 4;               // blocks per CTA
 constexpr int D1_SUB = 64;                // positions per lane per half (32 lanes x 64 = one half)
-constexpr int D1_X_STRIDE = D1_SUB + 4;                    // u8 exit table, 4 bytes of padding per sub-chunk
+constexpr int D1_X_STRIDE = D1_SUB + 2;                    // u16 exit table, 1 word of padding per sub-chunk
 constexpr int D1_S_STRIDE = D1_SUB + 2;                    // u16 output table, 1 word of padding per sub-chunk
-constexpr int D1_WARP_SMEM = D1_RING + 32 * D1_X_STRIDE + 32 * D1_S_STRIDE * 2 + 32 * 4 + 32 * 2;
+constexpr int D1_WARP_SMEM = D1_RING + 32 * D1_X_STRIDE * 2 + 32 * D1_S_STRIDE * 2 + 32 * 4 + 32 * 2;
 constexpr int D1_SMEM = D1_WARPS * ((D1_WARP_SMEM + 15) & ~15);
-constexpr int D1_SPECIAL = 0x80;           // exit-table flag: the chain stops at a token with a continued length
+constexpr int D1_SPECIAL = 0x8000;         // exit-table flag: the chain stops at a token with a long continued length
 constexpr int D1_NONE = 0xffff;
 
 // bytes of the compressed block through this warp's shared-memory ring; positions outside the
@@ -146,8 +146,8 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
     if (bd.stored) { if (lane == 0) result[b] = (int32_t)bd.usize; return; }
 
     uint8_t *ring = d1_smem + (size_t)warp * ((D1_WARP_SMEM + 15) & ~15);
-    uint8_t *X = ring + D1_RING;                                   // [32][D1_X_STRIDE] exit of the sub-chunk from each entry
-    uint16_t *S = (uint16_t *)(X + 32 * D1_X_STRIDE);              // [32][D1_S_STRIDE] bytes produced on the way
+    uint16_t *X = (uint16_t *)(ring + D1_RING);                    // [32][D1_X_STRIDE] exit of the sub-chunk from each entry
+    uint16_t *S = X + 32 * D1_X_STRIDE;                            // [32][D1_S_STRIDE] bytes produced on the way
     uint32_t *s_op = (uint32_t *)(S + 32 * D1_S_STRIDE);           // per sub-chunk: op at its entry
     uint16_t *s_entry = (uint16_t *)(s_op + 32);                   // per sub-chunk: entry position
 
@@ -208,16 +208,25 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
                 uint32_t w[16];
 #pragma unroll
                 for (int i = 0; i < 4; i++) { const uint4 v = mine[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
-                uint8_t *xm = X + lane * D1_X_STRIDE;
+                uint16_t *xm = X + lane * D1_X_STRIDE;
                 uint16_t *sm = S + lane * D1_S_STRIDE;
+                const int sub_q = base_q + lane * D1_SUB;
 #pragma unroll
                 for (int jj = D1_SUB - 1; jj >= 0; jj--) {
                     const unsigned tok = (w[jj >> 2] >> ((jj & 3) * 8)) & 0xffu;
-                    const int lit = (int)(tok >> 4);
-                    int ml = (int)(tok & 15), n = jj + 3 + lit;
-                    bool special = lit == 15;
-                    if (ml == 15 && !special) {       // one continuation byte is common (matches of 19+): fold it in
-                        const unsigned x = ring[(base_q + lane * D1_SUB + n) & (D1_RING - 1)];
+                    int lit = (int)(tok >> 4), ml = (int)(tok & 15), n = jj + 3;
+                    bool special = false;
+                    // a length continued by ONE byte is folded in (literal runs of 15+ and matches of
+                    // 19+ are common); longer continuations stop the fold
+                    if (lit == 15) {
+                        const unsigned x = (jj + 1 < D1_SUB) ? ((w[(jj + 1) >> 2 & 15] >> (((jj + 1) & 3) * 8)) & 0xffu)
+                                                            : (unsigned)ring[(sub_q + D1_SUB) & (D1_RING - 1)];
+                        special = x == 255;
+                        lit += (int)x; n++;
+                    }
+                    n += lit;
+                    if (ml == 15 && !special) {
+                        const unsigned x = ring[(sub_q + n) & (D1_RING - 1)];
                         special = x == 255;
                         ml += (int)x; n++;
                     }
@@ -225,7 +234,7 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
                     if (special) { ex = jj | D1_SPECIAL; os = 0; }
                     else if (n < D1_SUB) { ex = (int)xm[n]; os += (int)sm[n]; }
                     else ex = n;
-                    xm[jj] = (uint8_t)ex;
+                    xm[jj] = (uint16_t)ex;
                     sm[jj] = (uint16_t)os;
                 }
             }
@@ -241,7 +250,7 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
                     const int x = (int)X[sc * D1_X_STRIDE + jj];
                     op += (int)S[sc * D1_S_STRIDE + jj];
                     if (x & D1_SPECIAL) {
-                        const SeqDec sd = d1_decode_slow(rd, base_q + sc * D1_SUB + (x & (D1_SUB - 1)) - d, clean_ip);
+                        const SeqDec sd = d1_decode_slow(rd, base_q + sc * D1_SUB + (x & (D1_SUB - 1)) - d, clean_ip);   // flag | position 0..63
                         if (!sd.clean) break;             // phase D finds it too and ends the bulk phase
                         op += sd.lit + sd.ml;
                         e = sd.next + d - base_q;
@@ -262,17 +271,25 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
                         const int ip = base_q + p - d;
                         int lit, mlen, off, next;
                         const unsigned tok = ring[(base_q + p) & (D1_RING - 1)];
-                        bool slow = (tok >> 4) == 15;
-                        if (!slow) {
+                        bool slow = false;
+                        {
+                            int qo = base_q + p + 1;
                             lit = (int)(tok >> 4); mlen = (int)(tok & 15) + 4;
-                            const int qo = base_q + p + 1 + lit;
-                            off = (int)ring[qo & (D1_RING - 1)] | ((int)ring[(qo + 1) & (D1_RING - 1)] << 8);
-                            next = ip + lit + 3;
-                            if (mlen == 19) {                 // continued match length: one more byte, usually the last
-                                const unsigned x = ring[(qo + 2) & (D1_RING - 1)];
+                            if (lit == 15) {                  // continued literal length: one more byte, usually the last
+                                const unsigned x = ring[qo & (D1_RING - 1)];
                                 slow = x == 255;
-                                mlen += (int)x; next++;
+                                lit += (int)x; qo++;
                             }
+                            qo += lit;
+                            // up to 269 literals ahead: still inside the two staged halves
+                            off = (int)ring[qo & (D1_RING - 1)] | ((int)ring[(qo + 1) & (D1_RING - 1)] << 8);
+                            qo += 2;
+                            if (mlen == 19 && !slow) {        // continued match length
+                                const unsigned x = ring[qo & (D1_RING - 1)];
+                                slow = x == 255;
+                                mlen += (int)x; qo++;
+                            }
+                            next = qo - d;
                         }
                         if (slow) {
                             const SeqDec sd = d1_decode_slow(rd, ip, clean_ip);

@@ -64,11 +64,13 @@ extern "C" int d1_emul(const uint8_t *src, int csize, int cap, int d, uint32_t *
             for (int lane = 0; lane < 32; lane++) {                // phase B (per sub-chunk, local exits)
                 for (int jj = SUB - 1; jj >= 0; jj--) {
                     const unsigned tok = rd.at_q(base_q + lane * SUB + jj);
-                    const int lit = (int)(tok >> 4); int ml = (int)(tok & 15), n = jj + 3 + lit;
-                    bool special = lit == 15;
+                    int lit = (int)(tok >> 4), ml = (int)(tok & 15), n = jj + 3;
+                    bool special = false;
+                    if (lit == 15) { const unsigned x = rd.at_q(base_q + lane * SUB + jj + 1); special = x == 255; lit += (int)x; n++; }
+                    n += lit;
                     if (ml == 15 && !special) { const unsigned x = rd.at_q(base_q + lane * SUB + n); special = x == 255; ml += (int)x; n++; }
                     int ex, os = lit + ml + 4;
-                    if (special) { ex = jj | 0x80; os = 0; }
+                    if (special) { ex = jj | 0x8000; os = 0; }
                     else if (n < SUB) { ex = A[lane * SUB + n]; os += Bv[lane * SUB + n]; }
                     else ex = n;
                     A[lane * SUB + jj] = ex; Bv[lane * SUB + jj] = os;
@@ -82,7 +84,7 @@ extern "C" int d1_emul(const uint8_t *src, int csize, int cap, int d, uint32_t *
                 const int sc = e >> 6, jj = e & (SUB - 1);
                 if (sc != last_sc) { entry[sc] = e; eop[sc] = op; last_sc = sc; }
                 const int x = A[sc * SUB + jj]; op += Bv[sc * SUB + jj];
-                if (x & 0x80) {
+                if (x & 0x8000) {
                     const SeqDec sd = decode_slow(rd, base_q + sc * SUB + (x & (SUB - 1)) - d, clean_ip);
                     if (!sd.clean) break;
                     op += sd.lit + sd.ml; e = sd.next + d - base_q;
@@ -98,13 +100,16 @@ extern "C" int d1_emul(const uint8_t *src, int csize, int cap, int d, uint32_t *
                 while (p < s1) {
                     const int ip = base_q + p - d; int lit, mlen, off, next;
                     const unsigned tok = rd.at_q(base_q + p);
-                    bool slow = (tok >> 4) == 15;
-                    if (!slow) {
+                    bool slow = false;
+                    {
+                        int qo = base_q + p + 1;
                         lit = (int)(tok >> 4); mlen = (int)(tok & 15) + 4;
-                        const int qo = base_q + p + 1 + lit;
+                        if (lit == 15) { const unsigned x = rd.at_q(qo); slow = x == 255; lit += (int)x; qo++; }
+                        qo += lit;
                         off = (int)rd.at_q(qo) | ((int)rd.at_q(qo + 1) << 8);
-                        next = ip + lit + 3;
-                        if (mlen == 19) { const unsigned x = rd.at_q(qo + 2); slow = x == 255; mlen += (int)x; next++; }
+                        qo += 2;
+                        if (mlen == 19 && !slow) { const unsigned x = rd.at_q(qo); slow = x == 255; mlen += (int)x; qo++; }
+                        next = qo - d;
                     }
                     if (slow) {
                         const SeqDec sd = decode_slow(rd, ip, clean_ip);
