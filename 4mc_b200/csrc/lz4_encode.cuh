@@ -11,8 +11,10 @@
 //       index   16384-entry table of the FIRST position of each 4-byte hash in the region,
 //               order-independent (descending sweep, later stores win), so all threads build it
 //               at once; any earlier occurrence is a usable LZ4 match candidate
-//       parse   every thread greedily parses its own 132-byte SLICE (132 = 33 words: slices
-//               start in distinct shared-memory banks); matches may run past the slice end
+//       parse   every thread owns a 132-byte SLICE (132 = 33 words: slices start in distinct
+//               shared-memory banks).  Pass 1 tests EVERY position of the slice against the table
+//               (uniform work, one bit per position); pass 2 walks greedily over the set bits only,
+//               extending matches forwards and backwards -- they may run past the slice end
 //       stitch  two CTA-wide max-scans: matches of later slices are trimmed to what earlier
 //               slices left uncovered, and every slice learns where its first literal run starts
 //       emit    prefix-sum of encoded sizes, then every thread writes its own sequences
@@ -184,10 +186,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
             for (int base = ((rlen - 1) / STEP) * STEP; base >= 0; base -= STEP) {
                 const int p = base + 4 * tid;
                 if (p <= last) {
+                    // every second position is enough: a repeat first seen at an odd position is
+                    // found one byte later and the backward extension recovers that byte
                     const uint32_t w0 = data32[p >> 2], w1 = data32[(p >> 2) + 1];
-                    if (p + 3 <= last) table[enc_hash(__funnelshift_r(w0, w1, 24))] = (uint16_t)(p + 3);
                     if (p + 2 <= last) table[enc_hash(__funnelshift_r(w0, w1, 16))] = (uint16_t)(p + 2);
-                    if (p + 1 <= last) table[enc_hash(__funnelshift_r(w0, w1, 8))] = (uint16_t)(p + 1);
                     table[enc_hash(w0)] = (uint16_t)p;
                 }
                 __syncthreads();
@@ -202,32 +204,56 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
         const int ss = tid * ENC_SLICE;
         if (ss < rlen) {
             const int se = min(ss + ENC_SLICE, rlen);
-            int p = ss, anchor = ss;
-            uint32_t w_lo = data32[p >> 2], w_hi = data32[(p >> 2) + 1];   // rolling 8-byte window at p
-            while (p < se && p <= mf_limit) {
-                const uint32_t v = __funnelshift_r(w_lo, w_hi, (p & 3) * 8);
-                const int c = (int)table[enc_hash(v)];
-                if (c < p && smem_read4(data32, c) == v) {
-                    int len = 4;
-                    const int maxlen = match_limit - p;
-                    while (len < maxlen) {
-                        const uint32_t x = smem_read4(data32, p + len) ^ smem_read4(data32, c + len);
-                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
-                        len += 4;
+            // pass 1 -- every position of the slice, no skipping: does the table hold an earlier
+            // position with the same four bytes?  One bit per position (uniform work for all lanes).
+            unsigned long long cand[3] = {0ull, 0ull, 0ull};
+            {
+                const int stop = min(se, mf_limit + 1);
+                uint32_t w_lo = data32[ss >> 2], w_hi = data32[(ss >> 2) + 1];     // ss is word aligned
+#pragma unroll
+                for (int g = 0; g < 3; g++) {
+                    unsigned long long m = 0;
+                    const int p0 = ss + g * 64, cnt = min(64, stop - p0);
+                    for (int b = 0; b < cnt; b++) {
+                        const int p = p0 + b;
+                        const uint32_t v = __funnelshift_r(w_lo, w_hi, (p & 3) * 8);
+                        const int c = (int)table[enc_hash(v)];
+                        if (c < p && smem_read4(data32, c) == v) m |= 1ull << b;
+                        if ((p & 3) == 3) { w_lo = w_hi; w_hi = data32[(p >> 2) + 2]; }
                     }
-                    len = min(len, maxlen);
-                    int st = p, m = c;
-                    while (st > anchor && m > 0 && data[st - 1] == data[m - 1]) { st--; m--; len++; }
-                    if (len >= P.min_match) {
-                        if (l_len) rec[nrec++] = enc_pack(l_st - ss, l_len, l_off);
-                        l_st = st; l_len = len; l_off = st - m;
-                        p = st + len; anchor = p;
-                        w_lo = data32[p >> 2]; w_hi = data32[(p >> 2) + 1];
-                        continue;
-                    }
+                    cand[g] = m;
                 }
-                p++;
-                if ((p & 3) == 0) { w_lo = w_hi; w_hi = data32[(p >> 2) + 1]; }
+            }
+            // pass 2 -- the greedy walk only visits positions whose bit is set
+            int p = ss, anchor = ss;
+            for (;;) {
+                // next candidate at or after p
+                int rel = p - ss, nxt = -1;
+#pragma unroll
+                for (int g = 0; g < 3; g++) {
+                    unsigned long long m = cand[g];
+                    const int sh = rel - g * 64;
+                    if (sh >= 64) m = 0; else if (sh > 0) m &= ~0ull << sh;
+                    if (nxt < 0 && m) nxt = g * 64 + __ffsll((long long)m) - 1;
+                }
+                if (nxt < 0) break;
+                p = ss + nxt;
+                const int c = (int)table[enc_hash(smem_read4(data32, p))];
+                int len = 4;
+                const int maxlen = match_limit - p;
+                while (len < maxlen) {
+                    const uint32_t x = smem_read4(data32, p + len) ^ smem_read4(data32, c + len);
+                    if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                    len += 4;
+                }
+                len = min(len, maxlen);
+                int st = p, m = c;
+                while (st > anchor && m > 0 && data[st - 1] == data[m - 1]) { st--; m--; len++; }
+                if (len >= P.min_match) {
+                    if (l_len) rec[nrec++] = enc_pack(l_st - ss, l_len, l_off);
+                    l_st = st; l_len = len; l_off = st - m;
+                    p = st + len; anchor = p;
+                } else p++;
             }
         }
 

@@ -28,7 +28,7 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_off, int min_match,
     // index: descending sweep in steps of THREADS; within a step the order is unspecified on
     // the GPU -- emulate "highest thread wins" (any order is legal)
     for (int base = ((rlen - 1) / THREADS) * THREADS; base >= 0; base -= THREADS)
-        for (int t = 0; t < THREADS; t++) { int p = base + t; if (p <= rlen - 4) table[hsh(rd4(data.data(), p))] = (uint16_t)p; }
+        for (int t = THREADS - 1; t >= 0; t--) { int p = base + t; if (p <= rlen - 4 && (p & 1) == 0) table[hsh(rd4(data.data(), p))] = (uint16_t)p; }   // even positions only
     std::vector<std::vector<Seq>> inner(THREADS);
     std::vector<Seq> last(THREADS, Seq{0, 0, 0});
     const uint8_t *d = data.data();
