@@ -34,6 +34,9 @@ struct EncWs {
 
 struct DecWs {
     DevBuf desc, xxh, status, tokmap, chunkop, result, info, tables, outsize, final_;
+    // the checksum pass runs beside the parse on its own stream (both only read the payloads)
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
 };
 
 }  // namespace
@@ -231,6 +234,15 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
 
 // ---- decode --------------------------------------------------------------------------------
 
+int ensure_side(fourmc_ctx *ctx, DecWs &ws)
+{
+    if (ws.side) return FOURMC_OK;
+    CK(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ws.fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ws.join, cudaEventDisableTiming));
+    return FOURMC_OK;
+}
+
 // Runs verify + D1 + D0 + D2 + finalize over n_blocks descriptors already in ws.desc / ws.xxh /
 // ws.status.  max_chunks bounds the chunk indices used by the descriptors.
 int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t max_chunks, int check_xxh,
@@ -245,8 +257,13 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
         const BlockDesc *desc = (const BlockDesc *)ws.desc.p;
         uint8_t *status = (uint8_t *)ws.status.p;
         if (check_xxh) {
-            KL("xxh_verify_kernel", st, xxh_verify_kernel<<<(nb + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, st>>>(
+            int rs;
+            if ((rs = ensure_side(ctx, ws))) return rs;
+            CK(cudaEventRecord(ws.fork, st));
+            CK(cudaStreamWaitEvent(ws.side, ws.fork, 0));
+            KL("xxh_verify_kernel", ws.side, xxh_verify_kernel<<<(nb + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, ws.side>>>(
                 desc, (const uint32_t *)ws.xxh.p, nb, status));
+            CK(cudaEventRecord(ws.join, ws.side));
         }
         static bool d1_attr = false;
         if (!d1_attr) {
@@ -265,7 +282,7 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             if (forced < 0) { const char *e = getenv("FOURMC_D2_WARPS"); forced = e ? atoi(e) : 0; }
             int w = forced;
             if (w != 1 && w != 2 && w != 4 && w != 8) {
-                const uint32_t want = (uint32_t)ctx->sm_count * 48;        // resident warps to aim for
+                const uint32_t want = (uint32_t)ctx->sm_count * 24;        // resident warps to aim for (measured, profiles/)
                 w = nb * 1 >= want ? 1 : nb * 2 >= want ? 2 : nb * 4 >= want ? 4 : 8;
             }
             const uint32_t *tm = (const uint32_t *)ws.tokmap.p, *co = (const uint32_t *)ws.chunkop.p;
@@ -276,6 +293,7 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             else KL("lz4_copy_kernel", st, lz4_copy_kernel<8><<<nb, 256, 0, st>>>(desc, tm, co, rs));
         }
     }
+    if (nb && check_xxh && ws.join) CK(cudaStreamWaitEvent(st, ws.join, 0));
     KL("finalize_kernel", st, finalize_kernel<<<1, SCAN_THREADS, 0, st>>>((const BlockDesc *)ws.desc.p, (const int32_t *)ws.result.p, nb,
                                                 (uint8_t *)ws.status.p, d_out_size, d_info, d_result));
     return FOURMC_OK;
@@ -385,6 +403,9 @@ void fourmc_ctx_destroy(fourmc_ctx *ctx)
         DecWs &d = ctx->dec[i];
         release(d.desc); release(d.xxh); release(d.status); release(d.tokmap); release(d.chunkop);
         release(d.result); release(d.info); release(d.tables); release(d.outsize); release(d.final_);
+        if (d.side) cudaStreamDestroy(d.side);
+        if (d.fork) cudaEventDestroy(d.fork);
+        if (d.join) cudaEventDestroy(d.join);
         release(ctx->stage_in[i]); release(ctx->stage_out[i]);
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -900,11 +921,17 @@ long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
         uint32_t *d_hash = (uint32_t *)(d_x + cnt);
         int32_t *d_osz = (int32_t *)(d_hash + cnt);
         uint8_t *d_st = (uint8_t *)(d_osz + cnt);
-        // XXH32 of every item's payload (blocks and footers), compared with the headers below
-        if ((r = fourmc_xxh32_batch_device(ctx, st, cnt, ctx->stage_in[b].p, d_src_off, d_c, 0, d_hash))) return r;
+        // XXH32 of every item's payload (blocks and footers), compared with the headers below; it
+        // runs beside the decode on the slot's side stream
+        if ((r = ensure_side(ctx, ws))) return r;
+        CK(cudaEventRecord(ws.fork, st));
+        CK(cudaStreamWaitEvent(ws.side, ws.fork, 0));
+        if ((r = fourmc_xxh32_batch_device(ctx, ws.side, cnt, ctx->stage_in[b].p, d_src_off, d_c, 0, d_hash))) return r;
+        CK(cudaEventRecord(ws.join, ws.side));
         if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[b].p, d_src_off, d_c, d_u, d_hash, 0,
                            ctx->stage_out[b].p, d_dst_off, d_osz, d_st)))
             return r;
+        CK(cudaStreamWaitEvent(st, ws.join, 0));
         if (s.d1 > s.d0)
             CK(cudaMemcpyAsync((uint8_t *)out + s.d0, ctx->stage_out[b].p, s.d1 - s.d0, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(status + s.b0, d_st, cnt, cudaMemcpyDeviceToHost, st));

@@ -563,7 +563,7 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
                             const uint4 z = make_uint4(0, 0, 0, 0);
                             const uint4 q0 = ldg_v4(gb), q1 = nch > 1 ? ldg_v4(gb + 1) : z;
                             const uint4 q2 = nch > 2 ? ldg_v4(gb + 2) : z, q3 = nch > 3 ? ldg_v4(gb + 3) : z;
-                            scr[0] = q0; scr[1] = q1; scr[2] = q2; scr[3] = q3;
+                            scr[0] = q0; if (nch > 1) scr[1] = q1; if (nch > 2) scr[2] = q2; if (nch > 3) scr[3] = q3;
                             copy_batched(sp + d, (const uint8_t *)scr + so, ext);
                         }
                         if (ml > ext && ext < LZ4_LONG) smem_copy_seq(sp + d + ext, sp + mstart + ext, ml - ext);
