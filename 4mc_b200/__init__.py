@@ -79,6 +79,10 @@ def lib() -> C.CDLL:
         "fourmc_4mc_decompress_device": (i32, [vp, vp, vp, sz, vp, sz, vp]),
         "fourmc_lz4_decompress_batch_device": (i32, [vp, vp, u32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
         "fourmc_xxh32_batch_device": (i32, [vp, vp, u32, vp, vp, vp, u32, vp]),
+        "fourmc_4mz_decompress_host": (C.c_longlong, [vp, vp, sz, vp, sz]),
+        "fourmc_4mz_decoded_size_host": (C.c_longlong, [vp, sz]),
+        "fourmc_4mz_decompress_device": (i32, [vp, vp, vp, sz, vp, sz, vp]),
+        "fourmc_zstd_decompress": (C.c_longlong, [vp, vp, sz, vp, sz]),
         "fourmc_gen_device": (i32, [vp, vp, i32, u64, u64, u64, vp]),
         "fourmc_gen_host": (i32, [i32, u64, u64, u64, vp]),
     }
@@ -196,6 +200,30 @@ class Context:
         out = C.create_string_buffer(max(cap, 1))
         return int(lib().fourmc_4mc_decompress_host(self._h, b, len(b), out, cap))
 
+    # ---- 4mz (zstd blocks): decoding ----
+    def zstd_decompress(self, data, capacity: int):
+        """Returns (decoded size or negative zstd-style error, decoded bytes): ZSTD_decompress on one block."""
+        out = C.create_string_buffer(max(capacity, 1))
+        rc = int(lib().fourmc_zstd_decompress(self._h, _buf(data), len(data), out, capacity))
+        if rc in (E_CUDA, E_ARG) and self.last_error():
+            raise FourMcError(rc, self.last_error())
+        return rc, out.raw[:max(rc, 0)]
+
+    def decompress_4mz(self, stream) -> bytes:
+        b = _buf(stream)
+        cap = max(int(lib().fourmc_4mz_decoded_size_host(b, len(b))), 0)
+        out = C.create_string_buffer(max(cap, 1))
+        rc = lib().fourmc_4mz_decompress_host(self._h, b, len(b), out, cap)
+        self._check(rc)
+        return out.raw[:rc]
+
+    def decompress_4mz_rc(self, stream, capacity: int) -> int:
+        b = _buf(stream)
+        out = C.create_string_buffer(max(capacity, 1))
+        return int(lib().fourmc_4mz_decompress_host(self._h, b, len(b), out, capacity))
+
+    def decompress_4mz_device(self, d_in: int, n: int, d_out: int, out_capacity: int, d_result: int, stream=None):
+        self._check(lib().fourmc_4mz_decompress_device(self._h, stream, d_in, n, d_out, out_capacity, d_result))
 
     # ---- device-resident calls: raw device pointers (ints) and an optional CUDA stream handle ----
     def gen_device(self, d_out: int, n_pages: int, seed: int = 0x4D43, first_page: int = 0, kind: int = 0, stream=None):
@@ -265,6 +293,35 @@ class Lz4Decompressor:
 
     def xxhash32(self, buf, off: int, length: int, seed: int) -> int:
         return self.ctx.xxh32(bytes(buf[off:off + length]), seed)
+
+
+class ZstdDecompressor:
+    """Mirror of ZstdDecompressor's natives (ZstdDecompressor.java; native/jniZstdDecompressor.c:67-120)."""
+
+    def __init__(self, ctx: Context, direct_buffer_size: int = BLOCKSIZE):
+        self.ctx, self.direct_buffer_size = ctx, direct_buffer_size
+
+    def decompress_bytes_direct(self, compressed) -> bytes:
+        rc, out = self.ctx.zstd_decompress(compressed, self.direct_buffer_size)
+        if rc < 0:
+            raise FourMcError(rc, f"ZSTD_decompress returned: {rc}")         # jniZstdDecompressor.c:95-99
+        return out
+
+    def xxhash32(self, buf, off: int, length: int, seed: int) -> int:
+        return self.ctx.xxh32(bytes(buf[off:off + length]), seed)
+
+
+class FourMzCodec:
+    """Whole-stream 4mz reader: FourMzCodec.java / native/4mc.c:709-857.  Writing is not built."""
+
+    def __init__(self, ctx: Context, level: int = 1):
+        self.ctx, self.level = ctx, level
+
+    def compress(self, data) -> bytes:
+        raise FourMcError(E_UNSUPPORTED, "4mz compression is not implemented")
+
+    def decompress(self, stream) -> bytes:
+        return self.ctx.decompress_4mz(stream)
 
 
 class FourMcCodec:

@@ -18,6 +18,7 @@
 #include "lz4_decode.cuh"
 #include "lz4_encode.cuh"
 #include "xxh32.cuh"
+#include "zstd_decode.cuh"
 
 using namespace fm;
 
@@ -33,7 +34,7 @@ struct EncWs {
 };
 
 struct DecWs {
-    DevBuf desc, xxh, status, tokmap, chunkop, result, info, tables, outsize, final_;
+    DevBuf desc, xxh, status, tokmap, chunkop, result, info, tables, outsize, final_, zwork;
     // the checksum pass runs beside the parse on its own stream (both only read the payloads)
     cudaStream_t side = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
@@ -57,6 +58,7 @@ struct fourmc_ctx {
     void *pinned = nullptr;              // small pinned scratch for scalars
     size_t pinned_cap = 0;
     bool region_attr_set = false;
+    DevBuf ztables;                      // fmz::Tables (constant decode tables), uploaded once
     // optional per-kernel timing (fourmc_timing_enable): CUDA event pairs around every launch
     bool timing = false;
     std::vector<cudaEvent_t> tev;        // pool: [2i] start, [2i+1] stop
@@ -245,10 +247,24 @@ int ensure_side(fourmc_ctx *ctx, DecWs &ws)
 
 // Runs verify + D1 + D0 + D2 + finalize over n_blocks descriptors already in ws.desc / ws.xxh /
 // ws.status.  max_chunks bounds the chunk indices used by the descriptors.
+enum { CODEC_LZ4 = 0, CODEC_ZSTD = 1 };
+
+int ensure_ztables(fourmc_ctx *ctx)
+{
+    if (ctx->ztables.p) return FOURMC_OK;
+    int r;
+    if ((r = ensure(ctx, ctx->ztables, sizeof(fmz::Tables)))) return r;
+    fmz::Tables T;
+    fmz::make_tables(T);                 // format constants only (base values, extra bits, default distributions)
+    CK(cudaMemcpy(ctx->ztables.p, &T, sizeof(T), cudaMemcpyHostToDevice));
+    return FOURMC_OK;
+}
+
 int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t max_chunks, int check_xxh,
-               int32_t *d_out_size, const IndexInfo *d_info, long long *d_result)
+               int32_t *d_out_size, const IndexInfo *d_info, long long *d_result, int codec = CODEC_LZ4)
 {
     int r;
+    if (codec == CODEC_ZSTD) max_chunks = 0;
     if ((r = ensure(ctx, ws.tokmap, (max_chunks + 1) * LZ4_CHUNK_WORDS * 4))) return r;
     if ((r = ensure(ctx, ws.chunkop, (max_chunks + 1) * 4))) return r;
     if ((r = ensure(ctx, ws.result, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
@@ -270,13 +286,19 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             CK(cudaFuncSetAttribute(lz4_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D1_SMEM));
             d1_attr = true;
         }
+        if (codec == CODEC_ZSTD) {
+            if ((r = ensure_ztables(ctx))) return r;
+            if ((r = ensure(ctx, ws.zwork, (size_t)nb * sizeof(fmz::Work)))) return r;
+            KL("zstd_frames_kernel", st, zstd_frames_kernel<<<(nb + 31) / 32, 32, 0, st>>>(desc, nb, (fmz::Work *)ws.zwork.p,
+                                                           (const fmz::Tables *)ctx->ztables.p, (int32_t *)ws.result.p));
+        } else
         KL("lz4_parse_kernel", st, lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, D1_SMEM, st>>>(desc, nb, (uint32_t *)ws.tokmap.p, (uint32_t *)ws.chunkop.p,
                                                        (int32_t *)ws.result.p));
         for (uint32_t b0 = 0; b0 < nb; b0 += 32768) {
             const uint32_t cnt = std::min<uint32_t>(32768, nb - b0);
             KL("lz4_stored_kernel", st, lz4_stored_kernel<<<dim3(32, cnt), 256, 0, st>>>(desc + b0, cnt));
         }
-        {
+        if (codec == CODEC_LZ4) {
             // warps per block: enough to fill the chip when blocks are few, few when blocks are many
             static int forced = -1;
             if (forced < 0) { const char *e = getenv("FOURMC_D2_WARPS"); forced = e ? atoi(e) : 0; }
@@ -402,7 +424,7 @@ void fourmc_ctx_destroy(fourmc_ctx *ctx)
         release(e.scratch); release(e.meta); release(e.plan); release(e.lens); release(e.off); release(e.misc);
         DecWs &d = ctx->dec[i];
         release(d.desc); release(d.xxh); release(d.status); release(d.tokmap); release(d.chunkop);
-        release(d.result); release(d.info); release(d.tables); release(d.outsize); release(d.final_);
+        release(d.result); release(d.info); release(d.tables); release(d.outsize); release(d.final_); release(d.zwork);
         if (d.side) cudaStreamDestroy(d.side);
         if (d.fork) cudaEventDestroy(d.fork);
         if (d.join) cudaEventDestroy(d.join);
@@ -410,6 +432,7 @@ void fourmc_ctx_destroy(fourmc_ctx *ctx)
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     }
+    release(ctx->ztables);
     for (auto e : ctx->tev) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -523,8 +546,8 @@ int fourmc_4mc_compress_device(fourmc_ctx *ctx, void *stream, int level, const v
     return FOURMC_OK;
 }
 
-int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n, void *d_out,
-                                 size_t out_capacity, long long *d_result)
+static int decompress_device_impl(fourmc_ctx *ctx, void *stream, int codec, const void *d_in, size_t n, void *d_out,
+                                  size_t out_capacity, long long *d_result)
 {
     if (!ctx || !d_in || !d_result) return FOURMC_E_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -562,15 +585,28 @@ int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in
     CK(cudaMemsetAsync(ws.xxh.p, 0, (size_t)std::max<uint32_t>(nb, 1) * 4, st));
     KL("read_index_kernel", st, read_index_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint8_t *)d_in, n, nb, (uint8_t *)d_out, out_capacity,
                                                   (BlockDesc *)ws.desc.p, (uint32_t *)ws.xxh.p, (uint8_t *)ws.status.p,
-                                                  (IndexInfo *)ws.info.p));
+                                                  (IndexInfo *)ws.info.p, codec == CODEC_ZSTD ? FOURMC_MAGIC_4MZ : FOURMC_MAGIC_4MC));
     const size_t max_chunks = n / LZ4_CHUNK + 2 * (size_t)nb + 2;
-    return dec_blocks(ctx, st, ws, nb, max_chunks, 1, nullptr, (const IndexInfo *)ws.info.p, d_result);
+    return dec_blocks(ctx, st, ws, nb, max_chunks, 1, nullptr, (const IndexInfo *)ws.info.p, d_result, codec);
+}
+
+int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n, void *d_out,
+                                 size_t out_capacity, long long *d_result)
+{
+    return decompress_device_impl(ctx, stream, CODEC_LZ4, d_in, n, d_out, out_capacity, d_result);
+}
+
+int fourmc_4mz_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n, void *d_out,
+                                 size_t out_capacity, long long *d_result)
+{
+    return decompress_device_impl(ctx, stream, CODEC_ZSTD, d_in, n, d_out, out_capacity, d_result);
 }
 
 // batch decode over caller tables with an explicit workspace (the host pipeline keeps two in flight)
 static int dec_batch(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, const void *d_src,
                      const uint64_t *d_src_off, const uint32_t *d_csize, const uint32_t *d_usize, const uint32_t *d_xxh,
-                     int check_xxh, void *d_dst, const uint64_t *d_dst_off, int32_t *d_out_size, uint8_t *d_status)
+                     int check_xxh, void *d_dst, const uint64_t *d_dst_off, int32_t *d_out_size, uint8_t *d_status,
+                     int codec = CODEC_LZ4)
 {
     int r;
     if ((r = ensure(ctx, ws.desc, (size_t)std::max<uint32_t>(nb, 1) * sizeof(BlockDesc)))) return r;
@@ -582,7 +618,7 @@ static int dec_batch(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, c
     if (check_xxh) CK(cudaMemcpyAsync(ws.xxh.p, d_xxh, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
     // every compressed block has csize <= 4 MiB: bound the chunk count by that
     const size_t max_chunks = (size_t)nb * (FOURMC_BLOCKSIZE / LZ4_CHUNK + 2);
-    if ((r = dec_blocks(ctx, st, ws, nb, max_chunks, check_xxh, d_out_size, nullptr, nullptr))) return r;
+    if ((r = dec_blocks(ctx, st, ws, nb, max_chunks, check_xxh, d_out_size, nullptr, nullptr, codec))) return r;
     if (d_status) CK(cudaMemcpyAsync(d_status, ws.status.p, nb, cudaMemcpyDeviceToDevice, st));
     return FOURMC_OK;
 }
@@ -809,17 +845,18 @@ struct HostBlock { uint64_t src_off, dst_off; uint32_t csize, usize, xxh; };
 // payload work.  Returns FOURMC_OK or the container error the serial reader would hit first,
 // together with the blocks seen before it (they are decoded first, so that an earlier block error
 // takes precedence).  *walk_err_at = number of blocks preceding the container error.
-static int walk_streams(const uint8_t *in, size_t n, std::vector<HostBlock> &blocks, uint64_t *total_out)
+static int walk_streams(const uint8_t *in, size_t n, std::vector<HostBlock> &blocks, uint64_t *total_out,
+                        uint32_t magic = FOURMC_MAGIC_4MC, uint32_t hdr_ck = 0xA4B73443u)
 {
     size_t pos = 0;
     uint64_t opos = 0;
     while (pos < n) {
         if (n - pos < 4) return FOURMC_E_CONTENT;                                  // :868
-        if (be32(in + pos) != FOURMC_MAGIC_4MC) return FOURMC_E_CONTENT;           // :873
+        if (be32(in + pos) != magic) return FOURMC_E_CONTENT;                      // :873
         if (n - pos < 12) return FOURMC_E_CONTENT;                                 // :577
         if (be32(in + pos + 4) != FOURMC_VERSION) return FOURMC_E_CONTENT;         // :583
-        // header checksum (:584): XXH32 of "4MC\0" + version 1 is the constant 0xA4B73443
-        if (be32(in + pos + 8) != 0xA4B73443u) return FOURMC_E_CONTENT;
+        // header checksum (:584): XXH32 of magic + version 1 is a constant (0xA4B73443 4mc, 0x289A1C9A 4mz)
+        if (be32(in + pos + 8) != hdr_ck) return FOURMC_E_CONTENT;
         pos += 12;
         for (;;) {
             if (n - pos < 12) { *total_out = opos; return FOURMC_E_INPUT; }       // :610
@@ -847,23 +884,28 @@ static int walk_streams(const uint8_t *in, size_t n, std::vector<HostBlock> &blo
     return FOURMC_OK;
 }
 
-long long fourmc_4mc_decoded_size_host(const void *in, size_t n)
+static long long decoded_size_impl(const void *in, size_t n, int codec)
 {
     if (!in && n) return FOURMC_E_ARG;
     std::vector<HostBlock> blocks;
     uint64_t total = 0;
-    const int e = walk_streams((const uint8_t *)in, n, blocks, &total);
+    const int e = walk_streams((const uint8_t *)in, n, blocks, &total, codec == CODEC_ZSTD ? FOURMC_MAGIC_4MZ : FOURMC_MAGIC_4MC,
+                               codec == CODEC_ZSTD ? 0x289A1C9Au : 0xA4B73443u);
     return e ? e : (long long)total;
 }
 
-long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, void *out, size_t out_capacity)
+long long fourmc_4mc_decoded_size_host(const void *in, size_t n) { return decoded_size_impl(in, n, CODEC_LZ4); }
+long long fourmc_4mz_decoded_size_host(const void *in, size_t n) { return decoded_size_impl(in, n, CODEC_ZSTD); }
+
+static long long decompress_host_impl(fourmc_ctx *ctx, int codec, const void *in, size_t n, void *out, size_t out_capacity)
 {
     if (!ctx || (!in && n) || (!out && out_capacity)) return FOURMC_E_ARG;
     CK(cudaSetDevice(ctx->device));
     const uint8_t *src = (const uint8_t *)in;
     std::vector<HostBlock> blocks;
     uint64_t total = 0;
-    const int walk_err = walk_streams(src, n, blocks, &total);
+    const int walk_err = walk_streams(src, n, blocks, &total, codec == CODEC_ZSTD ? FOURMC_MAGIC_4MZ : FOURMC_MAGIC_4MC,
+                                      codec == CODEC_ZSTD ? 0x289A1C9Au : 0xA4B73443u);
     if (total > out_capacity) return fail(ctx, FOURMC_E_OUTPUT, "destination too small");
     // slices of consecutive blocks; footers travel as hash-only items
     const size_t sl_blocks = (size_t)slice_blocks();
@@ -929,7 +971,7 @@ long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
         if ((r = fourmc_xxh32_batch_device(ctx, ws.side, cnt, ctx->stage_in[b].p, d_src_off, d_c, 0, d_hash))) return r;
         CK(cudaEventRecord(ws.join, ws.side));
         if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[b].p, d_src_off, d_c, d_u, d_hash, 0,
-                           ctx->stage_out[b].p, d_dst_off, d_osz, d_st)))
+                           ctx->stage_out[b].p, d_dst_off, d_osz, d_st, codec)))
             return r;
         CK(cudaStreamWaitEvent(st, ws.join, 0));
         if (s.d1 > s.d0)
@@ -946,6 +988,51 @@ long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
     }
     if (walk_err) return walk_err;
     return (long long)total;
+}
+
+long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, void *out, size_t out_capacity)
+{
+    return decompress_host_impl(ctx, CODEC_LZ4, in, n, out, out_capacity);
+}
+
+long long fourmc_4mz_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, void *out, size_t out_capacity)
+{
+    return decompress_host_impl(ctx, CODEC_ZSTD, in, n, out, out_capacity);
+}
+
+// ZSTD_decompress on one block (native/4mc.c:810, native/jniZstdDecompressor.c): decoded size, or a
+// negative value when ZSTD_isError() would be true for the reference.
+long long fourmc_zstd_decompress(fourmc_ctx *ctx, const void *src, size_t compressed_size, void *dst, size_t dst_capacity)
+{
+    if (!ctx || !src || (!dst && dst_capacity)) return FOURMC_E_ARG;
+    if (compressed_size > (size_t)(8 << 20) || dst_capacity > (size_t)(1 << 30))
+        return fail(ctx, FOURMC_E_ARG, "per-block calls take at most one 4 MiB block");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DecWs &ws = ctx->dec[0];
+    int r;
+    if ((r = ensure(ctx, ctx->stage_in[0], compressed_size + 64))) return r;
+    if ((r = ensure(ctx, ctx->stage_out[0], dst_capacity + 64))) return r;
+    if ((r = ensure(ctx, ws.desc, sizeof(BlockDesc)))) return r;
+    if ((r = ensure(ctx, ws.status, 16))) return r;
+    if ((r = ensure(ctx, ws.outsize, 16))) return r;
+    if ((r = pinned_scratch(ctx, 4096))) return r;
+    if (compressed_size) CK(cudaMemcpyAsync(ctx->stage_in[0].p, src, compressed_size, cudaMemcpyHostToDevice, st));
+    BlockDesc *hd = (BlockDesc *)ctx->pinned;
+    hd->src = (const uint8_t *)ctx->stage_in[0].p; hd->dst = (uint8_t *)ctx->stage_out[0].p;
+    hd->csize = (uint32_t)compressed_size; hd->usize = (uint32_t)dst_capacity; hd->chunk_base = 0; hd->stored = 0;
+    CK(cudaMemcpyAsync(ws.desc.p, hd, sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ws.status.p, 0, 16, st));
+    if ((r = dec_blocks(ctx, st, ws, 1, 0, 0, (int32_t *)ws.outsize.p, nullptr, nullptr, CODEC_ZSTD))) return r;
+    int32_t *hr = (int32_t *)((uint8_t *)ctx->pinned + 256);
+    CK(cudaMemcpyAsync(hr, ws.outsize.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int32_t res = *hr;
+    if (res > 0) {
+        CK(cudaMemcpyAsync(dst, ctx->stage_out[0].p, (size_t)res, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return res;
 }
 
 }  // extern "C"

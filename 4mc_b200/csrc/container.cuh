@@ -107,7 +107,7 @@ struct IndexInfo {              // device-side summary of one parsed stream
 // re-derives it and fails if they disagree.
 __global__ void __launch_bounds__(SCAN_THREADS)
 read_index_kernel(const uint8_t *in, uint64_t n, uint32_t n_blocks_host, uint8_t *out, uint64_t out_cap,
-                  BlockDesc *desc, uint32_t *xxh_expect, uint8_t *status, IndexInfo *info)
+                  BlockDesc *desc, uint32_t *xxh_expect, uint8_t *status, IndexInfo *info, uint32_t magic)
 {
     __shared__ __align__(16) uint32_t s_stage[XXH_WARP_SMEM_WORDS];
     __shared__ unsigned long long tmp[32];
@@ -142,11 +142,11 @@ read_index_kernel(const uint8_t *in, uint64_t n, uint32_t n_blocks_host, uint8_t
     __syncthreads();
     if (threadIdx.x == 0) {
         int e = FOURMC_OK;
-        if (ld_be32(in) != FOURMC_MAGIC_4MC) e = FOURMC_E_CONTENT;
+        if (ld_be32(in) != magic) e = FOURMC_E_CONTENT;
         else if (ld_be32(in + 4) != FOURMC_VERSION) e = FOURMC_E_CONTENT;
         else if (ld_be32(in + 8) != xxh32_thread(in, 8, 0)) e = FOURMC_E_CONTENT;
         else if (ld_be32(foot) != fsize || ld_be32(foot + 4) != 1) e = FOURMC_E_CONTENT;
-        else if (ld_be32(in + n - 8) != FOURMC_MAGIC_4MC) e = FOURMC_E_CONTENT;
+        else if (ld_be32(in + n - 8) != magic) e = FOURMC_E_CONTENT;
         else if (ld_be32(in + n - 4) != s_foot_hash) e = FOURMC_E_CONTENT;
         s_err = e;
     }

@@ -3,7 +3,7 @@
  *
  * Flag-, message-level- and exit-code-compatible with the reference CLI (native/4mccli.c:170-361,
  * native/4mc.c:135-161,220-386,896-934): -1..-4 level, -d decode, -t test, -c stdout, -f overwrite,
- * -v / -q verbosity, -V version, -h help, -z zstd (4mz: not implemented by this build -> exit 1),
+ * -v / -q verbosity, -V version, -h help, -z zstd (4mz: decoding only; -z compression -> exit 1),
  * "stdin" / "stdout" / "null" file names, automatic .4mc output names when stdout is a terminal.
  * Exit codes: 1 generic, 2 input, 3 output, 4 content.  All compression, checksum and index work is
  * done by the GPU through the C-ABI; this file only moves bytes between files and host memory.
@@ -31,7 +31,7 @@ static int usage(void)
 {
     fprintf(stderr, "Usage :\n      %s [arg] [input] [output]\n\n", prog);
     fprintf(stderr, "input   : a filename\n          with no FILE, or when FILE is - or stdin, read standard input\n");
-    fprintf(stderr, "Arguments :\n -z     : zstd compression (not available in this build) \n -1     : Fast compression (default) \n"
+    fprintf(stderr, "Arguments :\n -z     : zstd compression (this build decodes 4mz only) \n -1     : Fast compression (default) \n"
                     " -2     : Medium compression \n -3     : High compression \n -4     : Ultra compression \n"
                     " -d     : decompression (default for %s and %s exts)\n -f     : overwrite output without prompting \n"
                     " -V     : display Version number and exit\n -v     : verbose mode\n -q     : quiet mode\n"
@@ -149,7 +149,7 @@ int main(int argc, char **argv)
     }
     if (!strcmp(in_name, "stdin") && !strcmp(out_name, "stdout") && display == 2) display = 1;
     if (!strcmp(out_name, "stdout") && isatty(1) && !force_stdout) badusage();
-    if (zstd) DIE(1, "4mz (zstd) is not implemented by this build; LZ4 (.4mc) only");
+    if (zstd && !decode) DIE(1, "4mz (zstd) compression is not implemented by this build; it decodes 4mz and writes 4mc");
 
     clock_t t0 = clock();
     size_t n = 0;
@@ -172,13 +172,14 @@ int main(int argc, char **argv)
             (unsigned long long)c, n ? (double)c / n * 100 : 0.0, c ? (double)n / c : 0.0);
         free(out);
     } else {
-        long long sz = fourmc_4mc_decoded_size_host(in, n);
+        SAY(3, zstd ? "Compression: ZSTD\n" : "Compression: LZ4\n");
+        long long sz = zstd ? fourmc_4mz_decoded_size_host(in, n) : fourmc_4mc_decoded_size_host(in, n);
         size_t cap = sz > 0 ? (size_t)sz : 0;
         /* on a malformed container still decode what precedes the damage, like the serial reader */
         if (sz < 0) cap = n * 4 + (64 << 20);
         unsigned char *out = (unsigned char *)malloc(cap ? cap : 1);
         if (!out) DIE(1, "Allocation error : not enough memory");
-        long long d = fourmc_4mc_decompress_host(ctx, in, n, out, cap);
+        long long d = zstd ? fourmc_4mz_decompress_host(ctx, in, n, out, cap) : fourmc_4mc_decompress_host(ctx, in, n, out, cap);
         if (d < 0) {
             int code = d == FOURMC_E_INPUT ? 2 : d == FOURMC_E_OUTPUT ? 3 : d == FOURMC_E_CONTENT ? 4 : 1;
             DIE(code, "%s", code == 4 ? "Decoding Failed ! Corrupted input detected !" :

@@ -6,9 +6,11 @@
  *
  * Block path (18 symbols): Lz4Compressor / Lz4Decompressor natives run on the GPU
  *   <- native/jniCompressor.c:57-194, native/jniDecompressor.c:56-118.
- * ZstdCompressor / ZstdDecompressor block natives and the zstd streaming natives (17 symbols) are
- * exported so that class initialisation succeeds, and throw java.lang.InternalError when used:
- * 4mz is outside this build's scope.  The xxhash32 natives of all four classes work.
+ * ZstdDecompressor.decompressBytesDirect (4mz reading) runs on the GPU
+ *   <- native/jniZstdDecompressor.c:58-120.
+ * ZstdCompressor block natives and the zstd streaming natives are exported so that class
+ * initialisation succeeds, and throw java.lang.InternalError when used (4mz writing and the
+ * streaming ZstCodec are not built).  The xxhash32 natives of all four classes work.
  *
  * Same conventions as the reference: field ids cached by initIDs; input = first *DirectBufLen bytes
  * of the direct buffer; on success the length field is reset to 0; on failure InternalError is
@@ -146,7 +148,7 @@ JNIEXPORT jint JNICALL PKG(Lz4Decompressor, decompressBytesDirect)(JNIEnv *env, 
 JNIEXPORT jint JNICALL PKG(Lz4Decompressor, xxhash32)(JNIEnv *env, jclass cls, jbyteArray b, jint off, jint len, jint seed)
 { (void)cls; return xxhash32_common(env, b, off, len, seed); }
 
-/* ---- ZSTD block natives: exported, not implemented (4mz is out of this build's scope) ---------- */
+/* ---- ZSTD block natives: the decompressor is implemented, the compressor is exported only ------- */
 
 static jint unsupported(JNIEnv *env, const char *what)
 {
@@ -164,8 +166,37 @@ JNIEXPORT jint JNICALL PKG(ZstdCompressor, compressBound)(JNIEnv *env, jclass cl
 { (void)env; (void)cls; return n + (n >> 8) + (n < (128 << 10) ? (((128 << 10) - n) >> 11) : 0); }   /* ZSTD_COMPRESSBOUND, zstd.h:204 */
 JNIEXPORT jint JNICALL PKG(ZstdCompressor, xxhash32)(JNIEnv *env, jclass cls, jbyteArray b, jint off, jint len, jint seed)
 { (void)cls; return xxhash32_common(env, b, off, len, seed); }
-JNIEXPORT void JNICALL PKG(ZstdDecompressor, initIDs)(JNIEnv *env, jclass cls) { (void)env; (void)cls; }
-JNIEXPORT jint JNICALL PKG(ZstdDecompressor, decompressBytesDirect)(JNIEnv *env, jobject self) { (void)self; return unsupported(env, "ZSTD_decompress"); }
+/* ZstdDecompressor: native/jniZstdDecompressor.c:58-101 -- implemented (4mz reading) */
+static jfieldID z_compressedDirectBuf, z_compressedDirectBufLen, z_uncompressedDirectBuf, z_directBufferSize;
+
+JNIEXPORT void JNICALL PKG(ZstdDecompressor, initIDs)(JNIEnv *env, jclass cls)
+{   /* :58-65 */
+    z_compressedDirectBuf = (*env)->GetFieldID(env, cls, "compressedDirectBuf", "Ljava/nio/Buffer;");
+    z_compressedDirectBufLen = (*env)->GetFieldID(env, cls, "compressedDirectBufLen", "I");
+    z_uncompressedDirectBuf = (*env)->GetFieldID(env, cls, "uncompressedDirectBuf", "Ljava/nio/Buffer;");
+    z_directBufferSize = (*env)->GetFieldID(env, cls, "directBufferSize", "I");
+}
+JNIEXPORT jint JNICALL PKG(ZstdDecompressor, decompressBytesDirect)(JNIEnv *env, jobject self)
+{   /* :68-101 */
+    jobject cb = (*env)->GetObjectField(env, self, z_compressedDirectBuf);
+    jint clen = (*env)->GetIntField(env, self, z_compressedDirectBufLen);
+    jobject ub = (*env)->GetObjectField(env, self, z_uncompressedDirectBuf);
+    jint cap = (*env)->GetIntField(env, self, z_directBufferSize);
+    char *dst = (char *)(*env)->GetDirectBufferAddress(env, ub);
+    const char *src = (const char *)(*env)->GetDirectBufferAddress(env, cb);
+    if (dst == 0 || src == 0) return 0;
+    fourmc_ctx *ctx = ctx_get(env);
+    if (!ctx) return 0;
+    int r = (int)fourmc_zstd_decompress(ctx, src, (size_t)(unsigned)clen, dst, (size_t)(unsigned)cap);
+    if (r >= 0) {
+        (*env)->SetIntField(env, self, z_compressedDirectBufLen, 0);
+    } else {
+        char msg[EXC_LEN];
+        snprintf(msg, sizeof msg, "LZ4_decompress_safe returned: %d", r);      /* the reference's own text, :96 */
+        throw_ie(env, msg);
+    }
+    return r;
+}
 JNIEXPORT jint JNICALL PKG(ZstdDecompressor, xxhash32)(JNIEnv *env, jclass cls, jbyteArray b, jint off, jint len, jint seed)
 { (void)cls; return xxhash32_common(env, b, off, len, seed); }
 

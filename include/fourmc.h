@@ -159,6 +159,19 @@ int fourmc_xxh32_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_items,
                               const void *d_base, const uint64_t *d_off, const uint32_t *d_len,
                               uint32_t seed, uint32_t *d_out);
 
+/* ---- 4mz (zstd blocks): decoding only in this build ------------------------------------------ */
+/* Same contracts as the 4mc calls above, for streams with the "4MZ\0" magic whose compressed blocks
+ * are zstd frames: native/4mc.c:709-857 (decodeFourMZ), :810 ZSTD_decompress.  Writing 4mz
+ * (native/4mc.c:389-553) is not implemented: the writers return FOURMC_E_UNSUPPORTED. */
+long long fourmc_4mz_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, void *out, size_t out_capacity);
+long long fourmc_4mz_decoded_size_host(const void *in, size_t n);
+int fourmc_4mz_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n,
+                                 void *d_out, size_t out_capacity, long long *d_result);
+/* ZSTD_decompress on one block (host pointers): native/4mc.c:810, native/jniZstdDecompressor.c.
+ * Returns the decoded size, or a negative value where ZSTD_isError() is true for the reference. */
+long long fourmc_zstd_decompress(fourmc_ctx *ctx, const void *src, size_t compressed_size,
+                                 void *dst, size_t dst_capacity);
+
 /* ---- synthetic inputs, bit-identical on host and device ---------------------- */
 
 /* kind 0 = log-text.  Fills pages [first_page, first_page + n_pages) of 4096 bytes each. */

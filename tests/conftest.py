@@ -146,13 +146,15 @@ def gen_logtext(pkg, nbytes, seed=0x4D43, first_page=0):
     return buf.raw[:nbytes]
 
 
-def build_native(name, sources, extra=()):
-    """Compiles a test-only native helper into tests/_build/<name>.so with g++."""
+def build_native(name, sources, extra=(), deps=()):
+    """Compiles a test-only native helper into tests/_build/<name>.so with g++ (`deps`: headers that
+    also trigger a rebuild)."""
     out_dir = os.path.join(ROOT, "tests", "_build")
     os.makedirs(out_dir, exist_ok=True)
     out = os.path.join(out_dir, name + ".so")
     srcs = [os.path.join(ROOT, s) for s in sources]
-    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+    watch = srcs + [os.path.join(ROOT, d) for d in deps]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in watch):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out] + srcs + list(extra), check=True)
     return C.CDLL(out)
 

@@ -127,6 +127,81 @@ def main():
     json.dump(ks, open(os.path.join(HERE, "lz4_decode.json"), "w"), indent=0)
     print("golden:", len(xs), "xxh32 vectors,", len(ks), "lz4 decode vectors")
 
+    # ---- 4mz containers from the reference CLI (-z: zstd levels 1 / 3 / 6 / 12, native/4mc.c:389-553)
+    for lvl in (1, 2, 3, 4):
+        cli(["-z", f"-{lvl}"], os.path.join(HERE, "logtext_128k.bin"), os.path.join(HERE, f"logtext_128k.z{lvl}.4mz"))
+    for name, data in (("empty", b""), ("A", b"A"), ("zeros_4m1", bytes(4 * 1024 * 1024 + 1))):
+        w("_tmp.bin", data)
+        cli(["-z", "-1"], tmp, os.path.join(HERE, f"{name}.4mz"))
+    cli(["-z", "-1"], os.path.join(HERE, "random_70000.bin"), os.path.join(HERE, "random_70000.4mz"))
+    # 1.25 MiB of generator text (regenerated by the tests, not stored): ten 128 KiB zstd blocks per
+    # frame, so treeless literals and repeat-mode sequence tables occur
+    w("_tmp.bin", gen_logtext(1280 * 1024, first_page=64))
+    for lvl in (1, 2):
+        cli(["-z", f"-{lvl}"], tmp, os.path.join(HERE, f"logtext_1280k.z{lvl}.4mz"))
+    os.remove(tmp)
+
+    # ---- zstd frame known answers: ZSTD_compress at several levels, decoded by ZSTD_decompress with
+    # several capacities, plus mutated frames (accept / reject and the decoded bytes must match)
+    R.ZSTD_compress.restype = C.c_size_t
+    R.ZSTD_compress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]
+    R.ZSTD_decompress.restype = C.c_size_t
+    R.ZSTD_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    R.ZSTD_isError.restype = C.c_uint
+    R.ZSTD_isError.argtypes = [C.c_size_t]
+    R.ZSTD_compressBound.restype = C.c_size_t
+    R.ZSTD_compressBound.argtypes = [C.c_size_t]
+
+    def zcomp(src, lvl):
+        cap = R.ZSTD_compressBound(len(src))
+        out = C.create_string_buffer(cap)
+        n = R.ZSTD_compress(out, cap, src, len(src), lvl)
+        return out.raw[:n]
+
+    def zdec(src, cap):
+        out = C.create_string_buffer(max(cap, 1) + 64)
+        r = R.ZSTD_decompress(out, cap, src, len(src))
+        if R.ZSTD_isError(r):
+            return int(r) - (1 << 64), 0
+        return int(r), R.XXH32(out.raw[:r], r, 0)
+
+    skew = bytes(min(255, int(rng.expovariate(0.08))) for _ in range(40000))     # many symbols, Huffman weights via FSE
+    zsamples = [text[:n] for n in (0, 1, 2, 9, 50, 300, 1000, 3000, 20000)] + \
+               [rnd[:2000], bytes(3000), bytes(200000), b"ab" * 5000, text[1000:1300] * 40, skew[:20000], skew[:700],
+                text[:15000] + rnd[:5000] + text[40000:50000]]
+    zs = []
+    for sm in zsamples:
+        for lvl in (1, 3, 6, 12, 19):
+            comp = zcomp(sm, lvl)
+            n = len(sm)
+            zs.append({"hex": comp.hex(), "runs": [[cap, *zdec(comp, cap)] for cap in sorted({n, n + 1, max(n - 1, 0), n + (1 << 20)})]})
+            if len(comp) > 6000 or lvl not in (1, 3, 19):
+                continue
+            for _ in range(40):
+                m = bytearray(comp)
+                for _k in range(rng.choice((1, 1, 2))):
+                    kind = rng.randrange(4)
+                    if kind == 0:
+                        m[rng.randrange(len(m))] = rng.getrandbits(8)
+                    elif kind == 1 and len(m) > 1:
+                        m = m[:rng.randrange(1, len(m) + 1)]
+                    elif kind == 2:
+                        m[rng.randrange(len(m))] ^= 1 << rng.randrange(8)
+                    else:
+                        i = rng.randrange(len(m))
+                        m[i:i] = bytes([rng.getrandbits(8)])
+                m = bytes(m)
+                cap = rng.choice([n, n + 37, n + (1 << 20)])
+                zs.append({"hex": m.hex(), "runs": [[cap, *zdec(m, cap)]]})
+    # two frames back to back and a skippable frame in front (zstd_decompress.c:989-1100)
+    two = zcomp(text[:5000], 3) + zcomp(text[5000:9000], 1)
+    skip = bytes.fromhex("502a4d18") + (7).to_bytes(4, "little") + b"skipped" + zcomp(text[:777], 1)
+    for comp, n in ((two, 9000), (skip, 777)):
+        zs.append({"hex": comp.hex(), "runs": [[cap, *zdec(comp, cap)] for cap in (n, n - 1, n + 100)]})
+    json.dump(zs, open(os.path.join(HERE, "zstd_decode.json"), "w"), indent=0)
+    runs = [r for z in zs for r in z["runs"]]
+    print("golden:", len(zs), "zstd frames,", len(runs), "decode runs,", sum(1 for r in runs if r[1] < 0), "of them rejected")
+
 
 if __name__ == "__main__":
     main()

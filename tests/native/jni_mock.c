@@ -53,6 +53,7 @@ int mock_open(const char *libpath)
     if (!g_lib) { fprintf(stderr, "%s\n", dlerror()); return -1; }
     ((void (*)(JNIEnv *, jclass))sym("Java_com_fing_compression_fourmc_Lz4Compressor_initIDs"))(&g_env, NULL);
     ((void (*)(JNIEnv *, jclass))sym("Java_com_fing_compression_fourmc_Lz4Decompressor_initIDs"))(&g_env, NULL);
+    ((void (*)(JNIEnv *, jclass))sym("Java_com_fing_compression_fourmc_ZstdDecompressor_initIDs"))(&g_env, NULL);
     return 0;
 }
 
@@ -97,11 +98,20 @@ int mock_xxh(int cls, unsigned char *buf, int off, int len, int seed)
 
 int mock_bound(int n) { return ((jint (*)(JNIEnv *, jclass, jint))sym("Java_com_fing_compression_fourmc_Lz4Compressor_compressBound"))(&g_env, NULL, n); }
 
+int mock_zstd_decompress(unsigned char *in, int c, unsigned char *out, int cap, int *len_after, int *threw, char *msg)
+{
+    FakeObj o = {out, 0, in, c, cap};
+    g_threw = 0; g_exc[0] = 0;
+    int r = ((jint (*)(JNIEnv *, jobject))sym("Java_com_fing_compression_fourmc_ZstdDecompressor_decompressBytesDirect"))(&g_env, &o);
+    *len_after = o.compressedDirectBufLen; *threw = g_threw; strcpy(msg, g_exc);
+    return r;
+}
+
 int mock_zstd_throws(char *msg)
 {
     FakeObj o = {0, 0, 0, 0, 0};
     g_threw = 0;
-    ((jint (*)(JNIEnv *, jobject))sym("Java_com_fing_compression_fourmc_ZstdDecompressor_decompressBytesDirect"))(&g_env, &o);
+    ((jint (*)(JNIEnv *, jobject))sym("Java_com_fing_compression_fourmc_ZstdCompressor_compressBytesDirect"))(&g_env, &o);
     strcpy(msg, g_exc);
     return g_threw;
 }

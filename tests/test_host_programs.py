@@ -6,7 +6,7 @@ import subprocess
 
 import pytest
 
-from conftest import ROOT, golden_bytes, gen_logtext
+from conftest import ROOT, golden_bytes, golden_json, gen_logtext
 
 HOST = os.path.join(ROOT, "4mc_b200", "host")
 CLI = os.path.join(HOST, "4mc")
@@ -117,4 +117,15 @@ def test_jni_shim_through_fake_jvm(ora, pkg):
     buf = C.create_string_buffer(b"xx" + b"Nobody inspects the spammish repetition" + b"yy")
     for cls in range(4):
         assert M.mock_xxh(cls, buf, 2, 39, 0) & 0xFFFFFFFF == 0xE2293B2F
+    # ZstdDecompressor.decompressBytesDirect (native/jniZstdDecompressor.c:68-101) on reference-made frames
+    frame = next(z for z in golden_json("zstd_decode.json") if len(z["hex"]) > 4000 and z["runs"][0][1] > 0)
+    comp = bytes.fromhex(frame["hex"])
+    cap, ret, xxh = next(r for r in frame["runs"] if r[1] > 0)
+    out = C.create_string_buffer(4 * 1024 * 1024)
+    d = M.mock_zstd_decompress(C.create_string_buffer(comp, len(comp)), len(comp), out, 4 * 1024 * 1024, C.byref(la), C.byref(threw), msg)
+    assert d == ret and ora.xxh32(out.raw[:d]) == xxh and la.value == 0 and threw.value == 0
+    bad = comp[:len(comp) // 2]
+    d = M.mock_zstd_decompress(C.create_string_buffer(bad, len(bad)), len(bad), out, 4 * 1024 * 1024, C.byref(la), C.byref(threw), msg)
+    assert d < 0 and threw.value == 1 and msg.value == b"java/lang/InternalError: LZ4_decompress_safe returned: %d" % d
+    # the zstd compressor natives resolve but are not built
     assert M.mock_zstd_throws(msg) == 1 and b"InternalError" in msg.value
