@@ -165,20 +165,40 @@ def test_gpu_4mz_container_errors(ctx, pkg):
         pkg.FourMzCodec(ctx).compress(b"abc")
 
 
+def assemble_4mz(ora, blocks):
+    """One 4mz stream from (usize, csize, payload) records."""
+    body, deltas, off, prev = b"", [], 12, 0
+    for u, c, payload in blocks:
+        body += u.to_bytes(4, "big") + c.to_bytes(4, "big") + ora.xxh32(payload).to_bytes(4, "big") + payload
+        deltas.append(off - prev)
+        prev = off
+        off += 12 + c
+    n = len(blocks)
+    foot = (20 + 4 * n).to_bytes(4, "big") + (1).to_bytes(4, "big") + b"".join(d.to_bytes(4, "big") for d in deltas)
+    foot += (20 + 4 * n).to_bytes(4, "big") + bytes.fromhex("344d5a00")
+    return bytes.fromhex("344d5a00 00000001 289a1c9a") + body + bytes(12) + foot + ora.xxh32(foot).to_bytes(4, "big")
+
+
 @pytest.mark.gpu
-def test_gpu_4mz_device_call_many_blocks(ctx, pkg, ref_cli, tmp_path):
-    """A multi-block 4mz written by the reference CLI here is only available in the build container;
-    on the GPU box the same check runs on the committed 1.25 MiB fixture repeated as streams."""
+def test_gpu_4mz_device_call_many_blocks(ctx, pkg, ora):
+    """The device-resident call takes ONE stream (found through its footer index): a multi-block
+    stream is assembled from the blocks the reference CLI wrote into the committed fixtures."""
     import torch
-    streams = golden_bytes("logtext_1280k.z1.4mz") * 3 + golden_bytes("zeros_4m1.4mz")
-    want = gen_logtext(pkg, 1280 * 1024, first_page=64) * 3 + bytes(4 * MIB + 1)
-    d_in = torch.frombuffer(bytearray(streams), dtype=torch.uint8).cuda()
+    one = walk_4mz(golden_bytes("logtext_1280k.z1.4mz"))
+    zeros = walk_4mz(golden_bytes("zeros_4m1.4mz"))
+    rnd = walk_4mz(golden_bytes("random_70000.4mz"))
+    blocks = one * 3 + zeros[:1] + rnd + one * 2
+    stream = assemble_4mz(ora, blocks)
+    text = gen_logtext(pkg, 1280 * 1024, first_page=64)
+    want = text * 3 + bytes(4 * MIB) + golden_bytes("random_70000.bin") + text * 2
+    assert ctx.decompress_4mz(stream) == want
+    d_in = torch.frombuffer(bytearray(stream), dtype=torch.uint8).cuda()
     d_out = torch.zeros(len(want) + 64, dtype=torch.uint8, device="cuda")
-    d_res = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_res = torch.zeros(2, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
-    ctx.decompress_4mz_device(d_in.data_ptr(), len(streams), d_out.data_ptr(), len(want), d_res.data_ptr())
+    ctx.decompress_4mz_device(d_in.data_ptr(), len(stream), d_out.data_ptr(), len(want), d_res.data_ptr())
     ctx.sync()
-    assert int(d_res.item()) == len(want)
+    assert d_res.tolist() == [len(want), -1]
     assert bytes(d_out[:len(want)].cpu().numpy()) == want
 
 
