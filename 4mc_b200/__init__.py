@@ -83,6 +83,12 @@ def lib() -> C.CDLL:
         "fourmc_4mz_decoded_size_host": (C.c_longlong, [vp, sz]),
         "fourmc_4mz_decompress_device": (i32, [vp, vp, vp, sz, vp, sz, vp]),
         "fourmc_zstd_decompress": (C.c_longlong, [vp, vp, sz, vp, sz]),
+        "fourmc_zstd_compress": (C.c_longlong, [vp, i32, vp, sz, vp, sz]),
+        "fourmc_zstd_compress_bound": (sz, [sz]),
+        "fourmc_4mz_compress_host": (C.c_longlong, [vp, i32, vp, sz, vp, sz]),
+        "fourmc_4mz_compress_device": (i32, [vp, vp, i32, vp, sz, vp, sz, vp, vp]),
+        "fourmc_4mz_compress_span_device": (i32, [vp, vp, i32, vp, sz, vp, sz, vp, vp]),
+        "fourmc_4mz_build_index_device": (i32, [vp, vp, vp, u32, vp, vp]),
         "fourmc_gen_device": (i32, [vp, vp, i32, u64, u64, u64, vp]),
         "fourmc_gen_host": (i32, [i32, u64, u64, u64, vp]),
     }
@@ -200,7 +206,40 @@ class Context:
         out = C.create_string_buffer(max(cap, 1))
         return int(lib().fourmc_4mc_decompress_host(self._h, b, len(b), out, cap))
 
-    # ---- 4mz (zstd blocks): decoding ----
+    # ---- 4mz (zstd blocks) ----
+    def zstd_compress(self, data, level: int = 1, capacity: int | None = None):
+        """ZSTD_compress on one block: the frame, or None when it does not fit in `capacity`
+        (the reference returns dstSize_tooSmall there and 4mc stores the block, native/4mc.c:469)."""
+        n = len(data)
+        cap = int(lib().fourmc_zstd_compress_bound(n)) if capacity is None else capacity
+        out = C.create_string_buffer(max(cap, 1))
+        rc = int(lib().fourmc_zstd_compress(self._h, level, _buf(data), n, out, cap))
+        if rc == -70:
+            return None
+        self._check(rc)
+        return out.raw[:rc]
+
+    def compress_4mz(self, data, level: int = 1) -> bytes:
+        n = len(data)
+        cap = lib().fourmc_4mc_bound(n)
+        out = C.create_string_buffer(cap)
+        rc = lib().fourmc_4mz_compress_host(self._h, level, _buf(data), n, out, cap)
+        self._check(rc)
+        return out.raw[:rc]
+
+    def compress_4mz_device(self, d_in: int, n: int, d_out: int, out_capacity: int, d_out_size: int,
+                            d_block_lens: int | None = None, level: int = 1, stream=None):
+        self._check(lib().fourmc_4mz_compress_device(self._h, stream, level, d_in, n, d_out, out_capacity,
+                                                     d_out_size, d_block_lens))
+
+    def compress_4mz_span_device(self, d_in: int, n: int, d_span: int, span_capacity: int, d_span_size: int,
+                                 d_block_lens: int | None = None, level: int = 1, stream=None):
+        self._check(lib().fourmc_4mz_compress_span_device(self._h, stream, level, d_in, n, d_span, span_capacity,
+                                                          d_span_size, d_block_lens))
+
+    def build_index_4mz_device(self, d_block_lens: int, n_blocks: int, d_header: int | None, d_tail: int, stream=None):
+        self._check(lib().fourmc_4mz_build_index_device(self._h, stream, d_block_lens, n_blocks, d_header, d_tail))
+
     def zstd_decompress(self, data, capacity: int):
         """Returns (decoded size or negative zstd-style error, decoded bytes): ZSTD_decompress on one block."""
         out = C.create_string_buffer(max(capacity, 1))
@@ -295,6 +334,26 @@ class Lz4Decompressor:
         return self.ctx.xxh32(bytes(buf[off:off + length]), seed)
 
 
+class ZstdCompressor:
+    """Mirror of ZstdCompressor's natives (ZstdCompressor.java; native/jniZstdCompressor.c:59-199)."""
+
+    def __init__(self, ctx: Context, level: int = 1):
+        self.ctx, self.level = ctx, level
+
+    @staticmethod
+    def compress_bound(n: int) -> int:
+        return int(lib().fourmc_zstd_compress_bound(n))
+
+    def compress_bytes_direct(self, uncompressed) -> bytes:
+        out = self.ctx.zstd_compress(uncompressed, self.level)
+        if out is None:
+            raise FourMcError(-70, "ZSTD_compress returned: dstSize_tooSmall")   # jniZstdCompressor.c:95-100
+        return out
+
+    def xxhash32(self, buf, off: int, length: int, seed: int) -> int:
+        return self.ctx.xxh32(bytes(buf[off:off + length]), seed)
+
+
 class ZstdDecompressor:
     """Mirror of ZstdDecompressor's natives (ZstdDecompressor.java; native/jniZstdDecompressor.c:67-120)."""
 
@@ -312,13 +371,13 @@ class ZstdDecompressor:
 
 
 class FourMzCodec:
-    """Whole-stream 4mz reader: FourMzCodec.java / native/4mc.c:709-857.  Writing is not built."""
+    """Whole-stream 4mz codec: FourMzCodec.java / native/4mc.c:389-553 (writer), :709-857 (reader)."""
 
     def __init__(self, ctx: Context, level: int = 1):
         self.ctx, self.level = ctx, level
 
     def compress(self, data) -> bytes:
-        raise FourMcError(E_UNSUPPORTED, "4mz compression is not implemented")
+        return self.ctx.compress_4mz(data, self.level)
 
     def decompress(self, stream) -> bytes:
         return self.ctx.decompress_4mz(stream)

@@ -19,6 +19,7 @@
 #include "lz4_encode.cuh"
 #include "xxh32.cuh"
 #include "zstd_decode.cuh"
+#include "zstd_encode.cuh"
 
 using namespace fm;
 
@@ -30,7 +31,8 @@ struct DevBuf {
 };
 
 struct EncWs {
-    DevBuf scratch, meta, plan, lens, off, misc;   // misc: [0] work counter (u32), [8] span (u64), [16] total (u64)
+    DevBuf scratch, meta, plan, lens, off, misc;   // misc: [0] work counter (u32), [8] span (u64), [16] total (u64), [24] carry (u64)
+    DevBuf zout, zrout;                            // 4mz: entropy-stage output slots and their sizes
 };
 
 struct DecWs {
@@ -189,6 +191,19 @@ int level_min_match(int level)
     return 5;
 }
 
+enum { CODEC_LZ4 = 0, CODEC_ZSTD = 1 };
+
+int ensure_ztables(fourmc_ctx *ctx)
+{
+    if (ctx->ztables.p) return FOURMC_OK;
+    int r;
+    if ((r = ensure(ctx, ctx->ztables, sizeof(fmz::Tables)))) return r;
+    fmz::Tables T;
+    fmz::make_tables(T);                 // format constants only (base values, extra bits, default distributions)
+    CK(cudaMemcpy(ctx->ztables.p, &T, sizeof(T), cudaMemcpyHostToDevice));
+    return FOURMC_OK;
+}
+
 // ---- encode --------------------------------------------------------------------------------
 
 // d_in[0..n) -> block records back to back at d_span (block b at d_span + off[b], off[0] = base).
@@ -212,7 +227,8 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     if ((r = ensure(ctx, ws.off, (size_t)nb * 8))) return r;
     if ((r = ensure(ctx, ws.misc, 64))) return r;
     if (!ctx->region_attr_set) {
-        CK(cudaFuncSetAttribute(lz4_region_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
         ctx->region_attr_set = true;
     }
     CK(cudaMemsetAsync(ws.misc.p, 0, 64, st));
@@ -221,8 +237,9 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     P.scratch = (uint8_t *)ws.scratch.p; P.meta = (RegionMeta *)ws.meta.p;
     P.work_counter = (uint32_t *)ws.misc.p;
     P.min_match = level_min_match(level);
+    P.slot_bytes = ENC_SLOT;
     const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
-    KL("lz4_region_kernel", st, lz4_region_kernel<<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
+    KL("lz4_region_kernel", st, lz4_region_kernel<false><<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
     uint32_t *lens = d_block_lens_out ? d_block_lens_out : (uint32_t *)ws.lens.p;
     KL("lz4_block_size_kernel", st, lz4_block_size_kernel<<<(nb + 127) / 128, 128, 0, st>>>((const RegionMeta *)ws.meta.p, nb, n,
                                                            (BlockPlan *)ws.plan.p, lens, raw_limit));
@@ -232,6 +249,87 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
                                                              (const RegionMeta *)ws.meta.p, (const BlockPlan *)ws.plan.p,
                                                              (const uint64_t *)ws.off.p, d_out_base, raw_limit >= 0 ? 1 : 0));
     return FOURMC_OK;
+}
+
+// ---- 4mz encode ------------------------------------------------------------------------------
+
+__global__ void init_carry_kernel(uint8_t *misc, uint64_t base)
+{
+    *(uint32_t *)misc = 0; *(uint64_t *)(misc + 8) = 0; *(uint64_t *)(misc + 16) = 0; *(uint64_t *)(misc + 24) = base;
+}
+
+int zgroup_blocks()
+{
+    const char *e = getenv("FOURMC_ZGROUP");       // read per call: the tests shrink it to exercise the carry
+    int v = e ? atoi(e) : 512;
+    if (v < 1) v = 1;
+    if (v > 4096) v = 4096;
+    return v;
+}
+
+// Same contract as enc_span, for zstd frames.  Blocks are processed in groups so that the
+// per-region scratch (sequence arrays in, block bodies out: 160 KiB per 64 KiB region) stays
+// bounded; each group appends to the stream through a device-side carry (no host round trip).
+int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8_t *d_in, size_t n,
+                  uint8_t *d_out_base, uint64_t base, uint32_t *d_block_lens_out, int64_t raw_limit)
+{
+    const uint32_t nb = blocks_of(n);
+    int r;
+    if ((r = ensure(ctx, ws.misc, 64))) return r;
+    if (nb == 0) { CK(cudaMemsetAsync(ws.misc.p, 0, 64, st)); return FOURMC_OK; }
+    if ((r = ensure_ztables(ctx))) return r;
+    const uint32_t G = std::min<uint32_t>(nb, (uint32_t)zgroup_blocks());
+    const uint32_t greg = G * ENC_REGIONS_PER_BLOCK;
+    if ((r = ensure(ctx, ws.scratch, (size_t)greg * fmz::ZE_IN_SLOT))) return r;
+    if ((r = ensure(ctx, ws.zout, (size_t)greg * fmz::ZE_OUT_SLOT))) return r;
+    if ((r = ensure(ctx, ws.zrout, (size_t)greg * sizeof(fmz::ZRegionOut)))) return r;
+    if ((r = ensure(ctx, ws.meta, (size_t)greg * sizeof(RegionMeta)))) return r;
+    if ((r = ensure(ctx, ws.plan, (size_t)nb * sizeof(BlockPlan)))) return r;
+    if ((r = ensure(ctx, ws.lens, (size_t)nb * 4))) return r;
+    if ((r = ensure(ctx, ws.off, (size_t)nb * 8))) return r;
+    if (!ctx->region_attr_set) {
+        CK(cudaFuncSetAttribute(lz4_region_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        ctx->region_attr_set = true;
+    }
+    uint8_t *misc = (uint8_t *)ws.misc.p;
+    KL("init_carry_kernel", st, init_carry_kernel<<<1, 1, 0, st>>>(misc, base));
+    uint32_t *lens = d_block_lens_out ? d_block_lens_out : (uint32_t *)ws.lens.p;
+    for (uint32_t g0 = 0; g0 < nb; g0 += G) {
+        const uint32_t gb = std::min<uint32_t>(G, nb - g0);
+        const size_t goff = (size_t)g0 * FOURMC_BLOCKSIZE;
+        const size_t gn = std::min<size_t>(n - goff, (size_t)gb * FOURMC_BLOCKSIZE);
+        const uint32_t nreg = gb * ENC_REGIONS_PER_BLOCK;
+        if (g0) CK(cudaMemsetAsync(misc, 0, 4, st));
+        EncParams P;
+        P.in = d_in + goff; P.n = gn; P.n_regions = nreg;
+        P.scratch = (uint8_t *)ws.scratch.p; P.meta = (RegionMeta *)ws.meta.p;
+        P.work_counter = (uint32_t *)misc;
+        P.min_match = level_min_match(level);
+        P.slot_bytes = fmz::ZE_IN_SLOT;
+        const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
+        KL("lz4_region_kernel", st, lz4_region_kernel<true><<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
+        ZEncParams Z;
+        Z.meta = (const RegionMeta *)ws.meta.p; Z.scratch_in = (const uint8_t *)ws.scratch.p;
+        Z.scratch_out = (uint8_t *)ws.zout.p; Z.rout = (fmz::ZRegionOut *)ws.zrout.p;
+        Z.tables = (const fmz::Tables *)ctx->ztables.p; Z.n = gn; Z.n_regions = nreg;
+        KL("zstd_entropy_kernel", st, zstd_entropy_kernel<<<nreg, fmz::ZE_THREADS, 0, st>>>(Z));
+        KL("zstd_block_size_kernel", st, zstd_block_size_kernel<<<(gb + 127) / 128, 128, 0, st>>>(
+            (const fmz::ZRegionOut *)ws.zrout.p, gb, gn, (BlockPlan *)ws.plan.p + g0, lens + g0, raw_limit));
+        KL("scan_lens_carry_kernel", st, scan_lens_carry_kernel<<<1, SCAN_THREADS, 0, st>>>(
+            lens + g0, gb, (uint64_t *)(misc + 24), (uint64_t *)ws.off.p + g0, (uint64_t *)(misc + 8)));
+        KL("zstd_block_write_kernel", st, zstd_block_write_kernel<<<gb, ENC_WRITE_THREADS, 0, st>>>(
+            d_in + goff, (const uint8_t *)ws.zout.p, (const fmz::ZRegionOut *)ws.zrout.p, (const BlockPlan *)ws.plan.p + g0,
+            (const uint64_t *)ws.off.p + g0, d_out_base, raw_limit >= 0 ? 1 : 0));
+    }
+    return FOURMC_OK;
+}
+
+int enc_span_codec(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int codec, int level, const uint8_t *d_in, size_t n,
+                   uint8_t *d_out_base, uint64_t base, uint32_t *d_block_lens_out, int64_t raw_limit)
+{
+    return codec == CODEC_ZSTD ? enc_span_zstd(ctx, st, ws, level, d_in, n, d_out_base, base, d_block_lens_out, raw_limit)
+                               : enc_span(ctx, st, ws, level, d_in, n, d_out_base, base, d_block_lens_out, raw_limit);
 }
 
 // ---- decode --------------------------------------------------------------------------------
@@ -247,18 +345,6 @@ int ensure_side(fourmc_ctx *ctx, DecWs &ws)
 
 // Runs verify + D1 + D0 + D2 + finalize over n_blocks descriptors already in ws.desc / ws.xxh /
 // ws.status.  max_chunks bounds the chunk indices used by the descriptors.
-enum { CODEC_LZ4 = 0, CODEC_ZSTD = 1 };
-
-int ensure_ztables(fourmc_ctx *ctx)
-{
-    if (ctx->ztables.p) return FOURMC_OK;
-    int r;
-    if ((r = ensure(ctx, ctx->ztables, sizeof(fmz::Tables)))) return r;
-    fmz::Tables T;
-    fmz::make_tables(T);                 // format constants only (base values, extra bits, default distributions)
-    CK(cudaMemcpy(ctx->ztables.p, &T, sizeof(T), cudaMemcpyHostToDevice));
-    return FOURMC_OK;
-}
 
 int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t max_chunks, int check_xxh,
                int32_t *d_out_size, const IndexInfo *d_info, long long *d_result, int codec = CODEC_LZ4)
@@ -421,7 +507,7 @@ void fourmc_ctx_destroy(fourmc_ctx *ctx)
     cudaDeviceSynchronize();
     for (int i = 0; i < FM_PIPE_MAX; i++) {
         EncWs &e = ctx->enc[i];
-        release(e.scratch); release(e.meta); release(e.plan); release(e.lens); release(e.off); release(e.misc);
+        release(e.scratch); release(e.meta); release(e.plan); release(e.lens); release(e.off); release(e.misc); release(e.zout); release(e.zrout);
         DecWs &d = ctx->dec[i];
         release(d.desc); release(d.xxh); release(d.status); release(d.tokmap); release(d.chunkop);
         release(d.result); release(d.info); release(d.tables); release(d.outsize); release(d.final_); release(d.zwork);
@@ -496,9 +582,8 @@ size_t fourmc_4mc_bound(size_t n)
 
 // ---- device-resident ---------------------------------------------------------------------------
 
-int fourmc_4mc_compress_span_device(fourmc_ctx *ctx, void *stream, int level, const void *d_in, size_t n,
-                                    void *d_span, size_t span_capacity, uint64_t *d_span_size,
-                                    uint32_t *d_block_lens)
+static int compress_span_impl(fourmc_ctx *ctx, void *stream, int codec, int level, const void *d_in, size_t n,
+                              void *d_span, size_t span_capacity, uint64_t *d_span_size, uint32_t *d_block_lens)
 {
     if (!ctx || (!d_in && n) || !d_span) return FOURMC_E_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -506,26 +591,50 @@ int fourmc_4mc_compress_span_device(fourmc_ctx *ctx, void *stream, int level, co
     if (span_capacity < n + 12ull * nb) return fail(ctx, FOURMC_E_OUTPUT, "span capacity below the all-stored bound");
     cudaStream_t st = pick(ctx, stream);
     EncWs &ws = ctx->enc[0];
-    int r = enc_span(ctx, st, ws, level, (const uint8_t *)d_in, n, (uint8_t *)d_span, 0, d_block_lens, -1);
+    int r = enc_span_codec(ctx, st, ws, codec, level, (const uint8_t *)d_in, n, (uint8_t *)d_span, 0, d_block_lens, -1);
     if (r) return r;
     if (d_span_size)
         CK(cudaMemcpyAsync(d_span_size, (uint8_t *)ws.misc.p + 8, 8, cudaMemcpyDeviceToDevice, st));
     return FOURMC_OK;
 }
 
-int fourmc_4mc_build_index_device(fourmc_ctx *ctx, void *stream, const uint32_t *d_block_lens, uint32_t n_blocks,
-                                  void *d_header, void *d_tail)
+int fourmc_4mc_compress_span_device(fourmc_ctx *ctx, void *stream, int level, const void *d_in, size_t n,
+                                    void *d_span, size_t span_capacity, uint64_t *d_span_size, uint32_t *d_block_lens)
+{
+    return compress_span_impl(ctx, stream, CODEC_LZ4, level, d_in, n, d_span, span_capacity, d_span_size, d_block_lens);
+}
+
+int fourmc_4mz_compress_span_device(fourmc_ctx *ctx, void *stream, int level, const void *d_in, size_t n,
+                                    void *d_span, size_t span_capacity, uint64_t *d_span_size, uint32_t *d_block_lens)
+{
+    return compress_span_impl(ctx, stream, CODEC_ZSTD, level, d_in, n, d_span, span_capacity, d_span_size, d_block_lens);
+}
+
+static int build_index_impl(fourmc_ctx *ctx, void *stream, uint32_t magic, const uint32_t *d_block_lens, uint32_t n_blocks,
+                            void *d_header, void *d_tail)
 {
     if (!ctx || !d_tail || (n_blocks && !d_block_lens)) return FOURMC_E_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
-    KL("write_index_kernel", st, write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(d_block_lens, n_blocks, 12, FOURMC_MAGIC_4MC, (uint8_t *)d_header,
+    KL("write_index_kernel", st, write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(d_block_lens, n_blocks, 12, magic, (uint8_t *)d_header,
                                                    (uint8_t *)d_tail, nullptr, nullptr));
     return FOURMC_OK;
 }
 
-int fourmc_4mc_compress_device(fourmc_ctx *ctx, void *stream, int level, const void *d_in, size_t n, void *d_out,
-                               size_t out_capacity, uint64_t *d_out_size, uint32_t *d_block_lens)
+int fourmc_4mc_build_index_device(fourmc_ctx *ctx, void *stream, const uint32_t *d_block_lens, uint32_t n_blocks,
+                                  void *d_header, void *d_tail)
+{
+    return build_index_impl(ctx, stream, FOURMC_MAGIC_4MC, d_block_lens, n_blocks, d_header, d_tail);
+}
+
+int fourmc_4mz_build_index_device(fourmc_ctx *ctx, void *stream, const uint32_t *d_block_lens, uint32_t n_blocks,
+                                  void *d_header, void *d_tail)
+{
+    return build_index_impl(ctx, stream, FOURMC_MAGIC_4MZ, d_block_lens, n_blocks, d_header, d_tail);
+}
+
+static int compress_device_impl(fourmc_ctx *ctx, void *stream, int codec, int level, const void *d_in, size_t n, void *d_out,
+                                size_t out_capacity, uint64_t *d_out_size, uint32_t *d_block_lens)
 {
     if (!ctx || (!d_in && n) || !d_out) return FOURMC_E_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -537,13 +646,26 @@ int fourmc_4mc_compress_device(fourmc_ctx *ctx, void *stream, int level, const v
     if ((r = ensure(ctx, ws.lens, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
     uint32_t *lens = d_block_lens ? d_block_lens : (uint32_t *)ws.lens.p;
     // block b's header lands at d_out + 12 + sum of earlier record lengths
-    if ((r = enc_span(ctx, st, ws, level, (const uint8_t *)d_in, n, (uint8_t *)d_out, 12, lens, -1))) return r;
-    KL("write_index_kernel", st, write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, 12, FOURMC_MAGIC_4MC, (uint8_t *)d_out, (uint8_t *)d_out + 12,
+    if ((r = enc_span_codec(ctx, st, ws, codec, level, (const uint8_t *)d_in, n, (uint8_t *)d_out, 12, lens, -1))) return r;
+    KL("write_index_kernel", st, write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, 12, codec == CODEC_ZSTD ? FOURMC_MAGIC_4MZ : FOURMC_MAGIC_4MC,
+                                                   (uint8_t *)d_out, (uint8_t *)d_out + 12,
                                                    (const uint64_t *)((uint8_t *)ws.misc.p + 8),
                                                    (uint64_t *)((uint8_t *)ws.misc.p + 16)));
     if (d_out_size)
         CK(cudaMemcpyAsync(d_out_size, (uint8_t *)ws.misc.p + 16, 8, cudaMemcpyDeviceToDevice, st));
     return FOURMC_OK;
+}
+
+int fourmc_4mc_compress_device(fourmc_ctx *ctx, void *stream, int level, const void *d_in, size_t n, void *d_out,
+                               size_t out_capacity, uint64_t *d_out_size, uint32_t *d_block_lens)
+{
+    return compress_device_impl(ctx, stream, CODEC_LZ4, level, d_in, n, d_out, out_capacity, d_out_size, d_block_lens);
+}
+
+int fourmc_4mz_compress_device(fourmc_ctx *ctx, void *stream, int level, const void *d_in, size_t n, void *d_out,
+                               size_t out_capacity, uint64_t *d_out_size, uint32_t *d_block_lens)
+{
+    return compress_device_impl(ctx, stream, CODEC_ZSTD, level, d_in, n, d_out, out_capacity, d_out_size, d_block_lens);
 }
 
 static int decompress_device_impl(fourmc_ctx *ctx, void *stream, int codec, const void *d_in, size_t n, void *d_out,
@@ -737,6 +859,44 @@ int fourmc_lz4_compress(fourmc_ctx *ctx, int level, const void *src, int src_siz
     return (int)c;
 }
 
+size_t fourmc_zstd_compress_bound(size_t n) { return fmz::ze_compress_bound(n); }     // native/zstd/zstd.h:204
+
+// ZSTD_compress(dst, cap, src, n, level) on one block: native/4mc.c:467, native/jniZstdCompressor.c:93.
+// Returns the frame size, or ZSTD's dstSize_tooSmall (-70) when the frame does not fit.
+long long fourmc_zstd_compress(fourmc_ctx *ctx, int level, const void *src, size_t src_size, void *dst, size_t dst_capacity)
+{
+    if (!ctx || (!src && src_size) || !dst) return FOURMC_E_ARG;
+    if (src_size > FOURMC_BLOCKSIZE) return fail(ctx, FOURMC_E_ARG, "per-block calls take at most 4 MiB (native/4mc.c:116)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int r;
+    if (src_size == 0) {                                          // frame header + one empty raw block
+        if (dst_capacity < (size_t)fmz::ZE_FRAME_HDR + 3) return fmz::ERR_DSTSIZE;
+        fmz::ze_write_frame_header((uint8_t *)dst, 0);
+        fmz::ze_write_block_header((uint8_t *)dst + fmz::ZE_FRAME_HDR, true, 0, 0);
+        return fmz::ZE_FRAME_HDR + 3;
+    }
+    const size_t bound = src_size + 3 * ENC_REGIONS_PER_BLOCK + fmz::ZE_FRAME_HDR + 64;
+    if ((r = ensure(ctx, ctx->stage_in[0], src_size + 64))) return r;
+    if ((r = ensure(ctx, ctx->stage_out[0], bound + 64))) return r;
+    if ((r = pinned_scratch(ctx, 4096))) return r;
+    CK(cudaMemcpyAsync(ctx->stage_in[0].p, src, src_size, cudaMemcpyHostToDevice, st));
+    EncWs &ws = ctx->enc[0];
+    uint8_t *rec = (uint8_t *)ctx->stage_out[0].p + 4;            // payload (record + 12) 16-byte aligned
+    if ((r = enc_span_zstd(ctx, st, ws, level, (const uint8_t *)ctx->stage_in[0].p, src_size, rec, 0, nullptr,
+                           (int64_t)std::min<size_t>(dst_capacity, bound))))
+        return r;
+    uint32_t *h = (uint32_t *)ctx->pinned;
+    CK(cudaMemcpyAsync(h, ws.plan.p, sizeof(BlockPlan), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const BlockPlan *p = (const BlockPlan *)h;
+    if (p->stored) return fmz::ERR_DSTSIZE;
+    const uint32_t c = p->payload;
+    CK(cudaMemcpyAsync(dst, rec + 12, c, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return (long long)c;
+}
+
 int fourmc_lz4_decompress_safe(fourmc_ctx *ctx, const void *src, int compressed_size, void *dst, int dst_capacity)
 {
     if (!ctx) return FOURMC_E_ARG;
@@ -778,7 +938,7 @@ int fourmc_lz4_decompress_safe(fourmc_ctx *ctx, const void *src, int compressed_
 
 // ---- whole stream, host buffers ----------------------------------------------------------------
 
-long long fourmc_4mc_compress_host(fourmc_ctx *ctx, int level, const void *in, size_t n, void *out, size_t out_capacity)
+static long long compress_host_impl(fourmc_ctx *ctx, int codec, int level, const void *in, size_t n, void *out, size_t out_capacity)
 {
     if (!ctx || (!in && n) || !out) return FOURMC_E_ARG;
     if (out_capacity < fourmc_4mc_bound(n)) return fail(ctx, FOURMC_E_OUTPUT, "output capacity below fourmc_4mc_bound(n)");
@@ -808,8 +968,8 @@ long long fourmc_4mc_compress_host(fourmc_ctx *ctx, int level, const void *in, s
             cudaStream_t st = ctx->aux[b];
             const size_t off = s * sl_bytes, len = std::min(sl_bytes, n - off);
             CK(cudaMemcpyAsync(ctx->stage_in[b].p, (const uint8_t *)in + off, len, cudaMemcpyHostToDevice, st));
-            if ((r = enc_span(ctx, st, ctx->enc[b], level, (const uint8_t *)ctx->stage_in[b].p, len,
-                              (uint8_t *)ctx->stage_out[b].p, 0, (uint32_t *)all_lens.p + s * sl_blocks, -1)))
+            if ((r = enc_span_codec(ctx, st, ctx->enc[b], codec, level, (const uint8_t *)ctx->stage_in[b].p, len,
+                                    (uint8_t *)ctx->stage_out[b].p, 0, (uint32_t *)all_lens.p + s * sl_blocks, -1)))
                 return r;
             CK(cudaMemcpyAsync(&h_span[b], (uint8_t *)ctx->enc[b].misc.p + 8, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaEventRecord(ctx->ev[b], st));
@@ -829,12 +989,22 @@ long long fourmc_4mc_compress_host(fourmc_ctx *ctx, int level, const void *in, s
     cudaStream_t st = ctx->stream;
     uint8_t *d_hdr = (uint8_t *)all_lens.p + (((size_t)std::max<uint32_t>(nb, 1) * 4 + 15) & ~(size_t)15);
     uint8_t *d_tail = d_hdr + 16;
-    if ((r = fourmc_4mc_build_index_device(ctx, st, (const uint32_t *)all_lens.p, nb, d_hdr, d_tail))) return r;
+    if ((r = build_index_impl(ctx, st, codec == CODEC_ZSTD ? FOURMC_MAGIC_4MZ : FOURMC_MAGIC_4MC, (const uint32_t *)all_lens.p, nb, d_hdr, d_tail))) return r;
     const size_t tail_bytes = 12 + 20 + 4 * (size_t)nb;
     CK(cudaMemcpyAsync(out, d_hdr, 12, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync((uint8_t *)out + pos, d_tail, tail_bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return (long long)(pos + tail_bytes);
+}
+
+long long fourmc_4mc_compress_host(fourmc_ctx *ctx, int level, const void *in, size_t n, void *out, size_t out_capacity)
+{
+    return compress_host_impl(ctx, CODEC_LZ4, level, in, n, out, out_capacity);
+}
+
+long long fourmc_4mz_compress_host(fourmc_ctx *ctx, int level, const void *in, size_t n, void *out, size_t out_capacity)
+{
+    return compress_host_impl(ctx, CODEC_ZSTD, level, in, n, out, out_capacity);
 }
 
 namespace {

@@ -63,6 +63,7 @@ struct EncParams {
     RegionMeta *meta;        // n_regions
     uint32_t *work_counter;  // zeroed before launch
     int min_match;           // >= 4
+    uint32_t slot_bytes;     // scratch bytes per region (ENC_SLOT; fmz::ZE_IN_SLOT for sequence output)
 };
 
 __device__ __forceinline__ uint32_t enc_hash(uint32_t v) { return (v * 2654435761u) >> (32 - ENC_HASH_BITS); }
@@ -112,6 +113,11 @@ __device__ __forceinline__ uint32_t enc_pack(int st_rel, int len, int off)
     return ((uint32_t)st_rel << 24) | ((uint32_t)len << 16) | (uint32_t)off;
 }
 
+// ZSEQ = false: LZ4 sequences as bytes (4mc).  ZSEQ = true: the same parse, emitted as
+// (literal length, match length, offset) arrays plus the gathered literals for the zstd entropy
+// stage (zstd_encode.cuh): slot = u16 ll[n] | u16 ml[n] | u16 off[n] | literals, n rounded up to 8;
+// RegionMeta.body_bytes then holds the literal count (tail literals included).
+template <bool ZSEQ>
 __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -301,11 +307,53 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
         const int out_off = cta_excl_scan<false>(bytes, s_scan, &total_bytes);
         const int seq_before = cta_excl_scan<false>(myseq, s_scan, &total_seq);
 
+        uint8_t *slot = P.scratch + (size_t)rg * P.slot_bytes;
+        if constexpr (ZSEQ) {
+            // ---- emit sequence arrays + gathered literals straight to HBM
+            int mbytes = l_len;
+            for (int k = 0; k < nrec; k++) mbytes += (int)((rec[k] >> 16) & 255);
+            int total_matched;
+            const int matched_before = cta_excl_scan<false>(mbytes, s_scan, &total_matched);
+            const uint32_t stride = ((uint32_t)total_seq + 7u) & ~7u;
+            uint16_t *zll = (uint16_t *)slot, *zml = zll + stride, *zoff = zml + stride;
+            uint8_t *zlit = (uint8_t *)(zoff + stride);
+            int long_n = 0, long_src = 0;
+            uint8_t *long_dst = nullptr;
+            {
+                int a = anchor0, lp = anchor0 - matched_before, idx = seq_before;
+                for (int k = 0; k <= nrec; k++) {
+                    int st, len, off;
+                    if (k < nrec) {
+                        const uint32_t r = rec[k];
+                        st = ss + (int)(r >> 24); len = (int)((r >> 16) & 255); off = (int)(r & 0xffffu);
+                    } else {
+                        if (!l_len) break;
+                        st = l_st; len = l_len; off = l_off;
+                    }
+                    const int lit = st - a;
+                    zll[idx] = (uint16_t)lit; zml[idx] = (uint16_t)len; zoff[idx] = (uint16_t)off;
+                    if (lit > ENC_SLICE) { long_n = lit; long_src = a; long_dst = zlit + lp; }
+                    else copy_batched(zlit + lp, data + a, lit);
+                    lp += lit; a = st + len; idx++;
+                }
+            }
+            for (unsigned mm = __ballot_sync(FM_FULL, long_n > 0); mm; mm &= mm - 1) {
+                const int l = __ffs(mm) - 1;
+                const int n = __shfl_sync(FM_FULL, long_n, l);
+                const int sp = __shfl_sync(FM_FULL, long_src, l);
+                uint8_t *dp = (uint8_t *)__shfl_sync(FM_FULL, (unsigned long long)long_dst, l);
+                for (int i = lane; i < n; i += 32) dp[i] = data[sp + i];
+            }
+            {   // literals after the region's last match
+                uint8_t *dp = zlit + (total_anchor - total_matched);
+                for (int i = total_anchor + tid; i < rlen; i += ENC_THREADS) dp[i - total_anchor] = data[i];
+            }
+            total_bytes = rlen - total_matched;
+        } else {
         // ---- emit into the staging area (the hash table is dead now), flushed below with 128-bit
         // stores; sequences beyond its capacity (poorly compressible regions) go straight to HBM.
         // Only a slice's first literal run can be long (it may reach back over match-free slices);
         // those are copied by the whole warp afterwards.
-        uint8_t *slot = P.scratch + (size_t)rg * ENC_SLOT;
         uint8_t *stage = (uint8_t *)table;
         __syncthreads();                                            // every thread is done with the table
         const bool staged = out_off + bytes <= ENC_STAGE;
@@ -352,6 +400,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
             uint4 *dv = (uint4 *)slot;
             for (int i = tid; i < (nflush >> 4); i += ENC_THREADS) dv[i] = sv[i];
             for (int i = (nflush & ~15) + tid; i < nflush; i += ENC_THREADS) slot[i] = stage[i];
+        }
         }
         if (tid == 0) {
             RegionMeta *mt = &P.meta[rg];

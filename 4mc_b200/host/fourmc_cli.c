@@ -3,7 +3,7 @@
  *
  * Flag-, message-level- and exit-code-compatible with the reference CLI (native/4mccli.c:170-361,
  * native/4mc.c:135-161,220-386,896-934): -1..-4 level, -d decode, -t test, -c stdout, -f overwrite,
- * -v / -q verbosity, -V version, -h help, -z zstd (4mz: decoding only; -z compression -> exit 1),
+ * -v / -q verbosity, -V version, -h help, -z zstd (4mz),
  * "stdin" / "stdout" / "null" file names, automatic .4mc output names when stdout is a terminal.
  * Exit codes: 1 generic, 2 input, 3 output, 4 content.  All compression, checksum and index work is
  * done by the GPU through the C-ABI; this file only moves bytes between files and host memory.
@@ -31,7 +31,7 @@ static int usage(void)
 {
     fprintf(stderr, "Usage :\n      %s [arg] [input] [output]\n\n", prog);
     fprintf(stderr, "input   : a filename\n          with no FILE, or when FILE is - or stdin, read standard input\n");
-    fprintf(stderr, "Arguments :\n -z     : zstd compression (this build decodes 4mz only) \n -1     : Fast compression (default) \n"
+    fprintf(stderr, "Arguments :\n -z     : zstd compression (4mz) \n -1     : Fast compression (default) \n"
                     " -2     : Medium compression \n -3     : High compression \n -4     : Ultra compression \n"
                     " -d     : decompression (default for %s and %s exts)\n -f     : overwrite output without prompting \n"
                     " -V     : display Version number and exit\n -v     : verbose mode\n -q     : quiet mode\n"
@@ -149,7 +149,6 @@ int main(int argc, char **argv)
     }
     if (!strcmp(in_name, "stdin") && !strcmp(out_name, "stdout") && display == 2) display = 1;
     if (!strcmp(out_name, "stdout") && isatty(1) && !force_stdout) badusage();
-    if (zstd && !decode) DIE(1, "4mz (zstd) compression is not implemented by this build; it decodes 4mz and writes 4mc");
 
     clock_t t0 = clock();
     size_t n = 0;
@@ -159,12 +158,13 @@ int main(int argc, char **argv)
     if (fourmc_ctx_create(&ctx, -1) != FOURMC_OK) DIE(1, "lib4mcgpu: no usable CUDA device (there is no CPU fallback)");
 
     if (!decode) {
-        SAY(2, "Compression: LZ4\n");
-        if ((display == 2) && (level > 1)) display = 3;                       /* 4mc.c:241 */
+        SAY(2, zstd ? "Compression: ZSTD\n" : "Compression: LZ4\n");                /* 4mc.c:241, :410 */
+        if ((display == 2) && (level > 1)) display = 3;
         size_t cap = fourmc_4mc_bound(n);
         unsigned char *out = (unsigned char *)malloc(cap);
         if (!out) DIE(1, "Allocation error : not enough memory");
-        long long c = fourmc_4mc_compress_host(ctx, level < 1 ? 1 : level, in, n, out, cap);
+        long long c = zstd ? fourmc_4mz_compress_host(ctx, level < 1 ? 1 : level, in, n, out, cap)
+                           : fourmc_4mc_compress_host(ctx, level < 1 ? 1 : level, in, n, out, cap);
         if (c < 0) DIE(c == FOURMC_E_OUTPUT ? 3 : 1, "Compression failed: %s", fourmc_last_error(ctx));
         if (fwrite(out, 1, (size_t)c, fo) != (size_t)c) DIE(3, "Write error : cannot write compressed block");
         SAY(2, "Compressed (%s) %llu bytes into %llu bytes ==> %.2f%% (Ratio=%.3f)\n",

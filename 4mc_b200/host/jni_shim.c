@@ -6,11 +6,10 @@
  *
  * Block path (18 symbols): Lz4Compressor / Lz4Decompressor natives run on the GPU
  *   <- native/jniCompressor.c:57-194, native/jniDecompressor.c:56-118.
- * ZstdDecompressor.decompressBytesDirect (4mz reading) runs on the GPU
- *   <- native/jniZstdDecompressor.c:58-120.
- * ZstdCompressor block natives and the zstd streaming natives are exported so that class
- * initialisation succeeds, and throw java.lang.InternalError when used (4mz writing and the
- * streaming ZstCodec are not built).  The xxhash32 natives of all four classes work.
+ * ZstdCompressor / ZstdDecompressor natives (4mz writing and reading) run on the GPU
+ *   <- native/jniZstdCompressor.c:59-199, native/jniZstdDecompressor.c:58-120.
+ * The zstd STREAMING natives (17 symbols) are exported so that class initialisation succeeds, and
+ * throw java.lang.InternalError when used (the streaming ZstCodec is out of scope).
  *
  * Same conventions as the reference: field ids cached by initIDs; input = first *DirectBufLen bytes
  * of the direct buffer; on success the length field is reset to 0; on failure InternalError is
@@ -148,20 +147,53 @@ JNIEXPORT jint JNICALL PKG(Lz4Decompressor, decompressBytesDirect)(JNIEnv *env, 
 JNIEXPORT jint JNICALL PKG(Lz4Decompressor, xxhash32)(JNIEnv *env, jclass cls, jbyteArray b, jint off, jint len, jint seed)
 { (void)cls; return xxhash32_common(env, b, off, len, seed); }
 
-/* ---- ZSTD block natives: the decompressor is implemented, the compressor is exported only ------- */
+/* ---- ZSTD block natives (4mz); the streaming zstd natives below are exported only ------------------ */
 
 static jint unsupported(JNIEnv *env, const char *what)
 {
     char msg[EXC_LEN];
-    snprintf(msg, sizeof msg, "%s: 4mz / zstd is not implemented by lib4mcgpu (LZ4 codecs only)", what);
+    snprintf(msg, sizeof msg, "%s: zstd streaming is not implemented by lib4mcgpu (block codecs only)", what);
     throw_ie(env, msg);
     return 0;
 }
 
-JNIEXPORT void JNICALL PKG(ZstdCompressor, initIDs)(JNIEnv *env, jclass cls) { (void)env; (void)cls; }
-JNIEXPORT jint JNICALL PKG(ZstdCompressor, compressBytesDirect)(JNIEnv *env, jobject self) { (void)self; return unsupported(env, "ZSTD_compress"); }
-JNIEXPORT jint JNICALL PKG(ZstdCompressor, compressBytesDirectMC)(JNIEnv *env, jobject self) { (void)self; return unsupported(env, "ZSTD_compress"); }
-JNIEXPORT jint JNICALL PKG(ZstdCompressor, compressBytesDirectHC)(JNIEnv *env, jobject self, jint l) { (void)self; (void)l; return unsupported(env, "ZSTD_compress"); }
+/* ZstdCompressor: native/jniZstdCompressor.c:59-175 -- implemented (4mz writing) */
+static jfieldID zc_uncompressedDirectBuf, zc_uncompressedDirectBufLen, zc_compressedDirectBuf, zc_directBufferSize;
+
+JNIEXPORT void JNICALL PKG(ZstdCompressor, initIDs)(JNIEnv *env, jclass cls)
+{   /* :59-70 */
+    zc_uncompressedDirectBuf = (*env)->GetFieldID(env, cls, "uncompressedDirectBuf", "Ljava/nio/ByteBuffer;");
+    zc_uncompressedDirectBufLen = (*env)->GetFieldID(env, cls, "uncompressedDirectBufLen", "I");
+    zc_compressedDirectBuf = (*env)->GetFieldID(env, cls, "compressedDirectBuf", "Ljava/nio/ByteBuffer;");
+    zc_directBufferSize = (*env)->GetFieldID(env, cls, "directBufferSize", "I");
+}
+
+static jint zstd_compress_common(JNIEnv *env, jobject self, int level)
+{
+    jobject ub = (*env)->GetObjectField(env, self, zc_uncompressedDirectBuf);
+    jint ulen = (*env)->GetIntField(env, self, zc_uncompressedDirectBufLen);
+    jobject cb = (*env)->GetObjectField(env, self, zc_compressedDirectBuf);
+    const char *src = (const char *)(*env)->GetDirectBufferAddress(env, ub);
+    char *dst = (char *)(*env)->GetDirectBufferAddress(env, cb);
+    if (src == 0 || dst == 0) return 0;                                        /* :87-89 */
+    fourmc_ctx *ctx = ctx_get(env);
+    if (!ctx) return 0;
+    /* the reference passes a 1 GiB capacity "enforced before in Java code" (:93): the Java side sizes
+     * compressedDirectBuf with compressBound(directBufferSize) */
+    long long r = fourmc_zstd_compress(ctx, level, src, (size_t)(unsigned)ulen, dst, fourmc_zstd_compress_bound((size_t)(unsigned)ulen));
+    if (r >= 0) {
+        (*env)->SetIntField(env, self, zc_uncompressedDirectBufLen, 0);        /* :96-97 */
+    } else {
+        char msg[EXC_LEN];
+        snprintf(msg, sizeof msg, "%s returned: %lu", "ZSTD_compress", (unsigned long)r);   /* :99-102 */
+        throw_ie(env, msg);
+    }
+    return (jint)r;
+}
+
+JNIEXPORT jint JNICALL PKG(ZstdCompressor, compressBytesDirect)(JNIEnv *env, jobject self) { return zstd_compress_common(env, self, 1); }     /* :72-105, level 1 */
+JNIEXPORT jint JNICALL PKG(ZstdCompressor, compressBytesDirectMC)(JNIEnv *env, jobject self) { return zstd_compress_common(env, self, 2); }   /* :107-138, level 3 */
+JNIEXPORT jint JNICALL PKG(ZstdCompressor, compressBytesDirectHC)(JNIEnv *env, jobject self, jint l) { return zstd_compress_common(env, self, l >= 12 ? 4 : 3); }   /* :140-172 */
 JNIEXPORT jint JNICALL PKG(ZstdCompressor, compressBound)(JNIEnv *env, jclass cls, jint n)
 { (void)env; (void)cls; return n + (n >> 8) + (n < (128 << 10) ? (((128 << 10) - n) >> 11) : 0); }   /* ZSTD_COMPRESSBOUND, zstd.h:204 */
 JNIEXPORT jint JNICALL PKG(ZstdCompressor, xxhash32)(JNIEnv *env, jclass cls, jbyteArray b, jint off, jint len, jint seed)

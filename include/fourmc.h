@@ -159,10 +159,12 @@ int fourmc_xxh32_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_items,
                               const void *d_base, const uint64_t *d_off, const uint32_t *d_len,
                               uint32_t seed, uint32_t *d_out);
 
-/* ---- 4mz (zstd blocks): decoding only in this build ------------------------------------------ */
+/* ---- 4mz (zstd blocks) ------------------------------------------------------------------------ */
 /* Same contracts as the 4mc calls above, for streams with the "4MZ\0" magic whose compressed blocks
- * are zstd frames: native/4mc.c:709-857 (decodeFourMZ), :810 ZSTD_decompress.  Writing 4mz
- * (native/4mc.c:389-553) is not implemented: the writers return FOURMC_E_UNSUPPORTED. */
+ * are zstd frames.  Readers: native/4mc.c:709-857 (decodeFourMZ), :810 ZSTD_decompress.  Writers:
+ * native/4mc.c:389-553 (fourMZcompressFilename), :467 ZSTD_compress with the stored fallback
+ * :469-485.  The frames are valid zstd (ZSTD_decompress restores the input) but not the reference's
+ * bytes; all four levels currently share the "Fast" encoder. */
 long long fourmc_4mz_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, void *out, size_t out_capacity);
 long long fourmc_4mz_decoded_size_host(const void *in, size_t n);
 int fourmc_4mz_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n,
@@ -171,6 +173,24 @@ int fourmc_4mz_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in
  * Returns the decoded size, or a negative value where ZSTD_isError() is true for the reference. */
 long long fourmc_zstd_decompress(fourmc_ctx *ctx, const void *src, size_t compressed_size,
                                  void *dst, size_t dst_capacity);
+
+/* ZSTD_compressBound: native/jniZstdCompressor.c compressBound, native/zstd/zstd.h:204. */
+size_t fourmc_zstd_compress_bound(size_t n);
+/* ZSTD_compress on one block (host pointers): native/4mc.c:467, native/jniZstdCompressor.c:93,125,158.
+ * Returns the frame size, or -70 (zstd's dstSize_tooSmall, for which ZSTD_isError() is true) when
+ * the frame does not fit in dst_capacity -- the caller then stores the block raw (native/4mc.c:469). */
+long long fourmc_zstd_compress(fourmc_ctx *ctx, int level, const void *src, size_t src_size,
+                               void *dst, size_t dst_capacity);
+/* fourmc_4mc_compress_host / _device / _span_device / fourmc_4mc_build_index_device for 4mz. */
+long long fourmc_4mz_compress_host(fourmc_ctx *ctx, int level, const void *in, size_t n,
+                                   void *out, size_t out_capacity);
+int fourmc_4mz_compress_device(fourmc_ctx *ctx, void *stream, int level, const void *d_in, size_t n,
+                               void *d_out, size_t out_capacity, uint64_t *d_out_size, uint32_t *d_block_lens);
+int fourmc_4mz_compress_span_device(fourmc_ctx *ctx, void *stream, int level, const void *d_in, size_t n,
+                                    void *d_span, size_t span_capacity, uint64_t *d_span_size,
+                                    uint32_t *d_block_lens);
+int fourmc_4mz_build_index_device(fourmc_ctx *ctx, void *stream, const uint32_t *d_block_lens,
+                                  uint32_t n_blocks, void *d_header, void *d_tail);
 
 /* ---- synthetic inputs, bit-identical on host and device ---------------------- */
 

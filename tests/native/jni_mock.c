@@ -54,6 +54,7 @@ int mock_open(const char *libpath)
     ((void (*)(JNIEnv *, jclass))sym("Java_com_fing_compression_fourmc_Lz4Compressor_initIDs"))(&g_env, NULL);
     ((void (*)(JNIEnv *, jclass))sym("Java_com_fing_compression_fourmc_Lz4Decompressor_initIDs"))(&g_env, NULL);
     ((void (*)(JNIEnv *, jclass))sym("Java_com_fing_compression_fourmc_ZstdDecompressor_initIDs"))(&g_env, NULL);
+    ((void (*)(JNIEnv *, jclass))sym("Java_com_fing_compression_fourmc_ZstdCompressor_initIDs"))(&g_env, NULL);
     return 0;
 }
 
@@ -107,11 +108,25 @@ int mock_zstd_decompress(unsigned char *in, int c, unsigned char *out, int cap, 
     return r;
 }
 
-int mock_zstd_throws(char *msg)
+int mock_zstd_compress(int which, int hc_level, unsigned char *in, int n, unsigned char *out, int *len_after, int *threw, char *msg)
 {
-    FakeObj o = {0, 0, 0, 0, 0};
+    FakeObj o = {in, n, out, 0, 4 << 20};
+    g_threw = 0; g_exc[0] = 0;
+    int r;
+    if (which == 0) r = ((jint (*)(JNIEnv *, jobject))sym("Java_com_fing_compression_fourmc_ZstdCompressor_compressBytesDirect"))(&g_env, &o);
+    else if (which == 1) r = ((jint (*)(JNIEnv *, jobject))sym("Java_com_fing_compression_fourmc_ZstdCompressor_compressBytesDirectMC"))(&g_env, &o);
+    else r = ((jint (*)(JNIEnv *, jobject, jint))sym("Java_com_fing_compression_fourmc_ZstdCompressor_compressBytesDirectHC"))(&g_env, &o, hc_level);
+    *len_after = o.uncompressedDirectBufLen; *threw = g_threw; strcpy(msg, g_exc);
+    return r;
+}
+
+int mock_zstd_bound(int n) { return ((jint (*)(JNIEnv *, jclass, jint))sym("Java_com_fing_compression_fourmc_ZstdCompressor_compressBound"))(&g_env, NULL, n); }
+
+/* the streaming zstd natives resolve (class initialisation) but throw when used */
+int mock_zstd_stream_throws(char *msg)
+{
     g_threw = 0;
-    ((jint (*)(JNIEnv *, jobject))sym("Java_com_fing_compression_fourmc_ZstdCompressor_compressBytesDirect"))(&g_env, &o);
+    ((jlong (*)(JNIEnv *, jclass))sym("Java_com_fing_compression_fourmc_zstd_ZstdStreamCompressor_createCStream"))(&g_env, NULL);
     strcpy(msg, g_exc);
     return g_threw;
 }

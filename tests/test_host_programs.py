@@ -127,5 +127,21 @@ def test_jni_shim_through_fake_jvm(ora, pkg):
     bad = comp[:len(comp) // 2]
     d = M.mock_zstd_decompress(C.create_string_buffer(bad, len(bad)), len(bad), out, 4 * 1024 * 1024, C.byref(la), C.byref(threw), msg)
     assert d < 0 and threw.value == 1 and msg.value == b"java/lang/InternalError: LZ4_decompress_safe returned: %d" % d
-    # the zstd compressor natives resolve but are not built
-    assert M.mock_zstd_throws(msg) == 1 and b"InternalError" in msg.value
+    # ZstdCompressor natives (native/jniZstdCompressor.c:72-172): frames the reference-shaped decoder restores
+    assert M.mock_zstd_bound(4 * 1024 * 1024) == 4 * 1024 * 1024 + 16384
+    for which, lvl in ((0, 0), (1, 0), (2, 6), (2, 12)):
+        src = C.create_string_buffer(data, len(data))
+        dst = C.create_string_buffer(4 * 1024 * 1024 + 16384)
+        r = M.mock_zstd_compress(which, lvl, src, len(data), dst, C.byref(la), C.byref(threw), msg)
+        assert 0 < r < len(data) // 2 and threw.value == 0 and la.value == 0
+        out = C.create_string_buffer(4 * 1024 * 1024)
+        d = M.mock_zstd_decompress(C.create_string_buffer(dst.raw[:r], r), r, out, 4 * 1024 * 1024, C.byref(la), C.byref(threw), msg)
+        assert d == len(data) and out.raw[:d] == data and threw.value == 0
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref4mc.so")):
+            R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref4mc.so"))
+            R.ZSTD_decompress.restype = C.c_size_t
+            R.ZSTD_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+            o2 = C.create_string_buffer(len(data))
+            assert R.ZSTD_decompress(o2, len(data), dst.raw[:r], r) == len(data) and o2.raw == data
+    # the streaming zstd natives resolve but are not built
+    assert M.mock_zstd_stream_throws(msg) == 1 and b"InternalError" in msg.value

@@ -161,8 +161,7 @@ def test_gpu_4mz_container_errors(ctx, pkg):
     assert ctx.decompress_4mz_rc(good[:len(good) // 2], n) == pkg.E_INPUT
     two = golden_bytes("A.4mz") + good                           # concatenated streams (native/4mc.c:908-912)
     assert ctx.decompress_4mz(two) == b"A" + golden_bytes("logtext_128k.bin")
-    with pytest.raises(pkg.FourMcError):
-        pkg.FourMzCodec(ctx).compress(b"abc")
+    assert pkg.FourMzCodec(ctx).decompress(pkg.FourMzCodec(ctx).compress(b"abc" * 1000)) == b"abc" * 1000
 
 
 def assemble_4mz(ora, blocks):
@@ -209,5 +208,3 @@ def test_cli_decodes_reference_4mz(pkg, tmp_path):
     out = tmp_path / "o.bin"
     subprocess.run([cli, "-f", "-q", "-z", "-d", src, str(out)], check=True)
     assert out.read_bytes() == gen_logtext(pkg, 1280 * 1024, first_page=64)
-    r = subprocess.run([cli, "-f", "-q", "-z", "-1", str(out), str(tmp_path / "o.4mz")])
-    assert r.returncode == 1                                     # 4mz writing is not built

@@ -16,4 +16,9 @@ for v in conftest.golden_json("lz4_decode.json")[::25]:
     ctx.lz4_decompress_safe(bytes.fromhex(v["hex"]), v["cap"])
 assert ctx.xxh32(data[:100001]) >= 0
 c = ctx.lz4_compress(data[:300000]); r, o = ctx.lz4_decompress_safe(c, 300000); assert o == data[:300000]
+z = ctx.compress_4mz(data)
+assert ctx.decompress_4mz(z) == data
+for n in (0, 1, 13, 4096, 65537, 300000):
+    z2 = ctx.compress_4mz(data[:n]); assert ctx.decompress_4mz(z2) == data[:n]
+f = ctx.zstd_compress(data[:200000]); r, o = ctx.zstd_decompress(f, 200000); assert o == data[:200000]
 print("sanitize workload ok")
