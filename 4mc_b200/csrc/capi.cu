@@ -375,8 +375,18 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
         if (codec == CODEC_ZSTD) {
             if ((r = ensure_ztables(ctx))) return r;
             if ((r = ensure(ctx, ws.zwork, (size_t)nb * sizeof(fmz::Work)))) return r;
+            static bool zd_attr = false;
+            if (!zd_attr) {
+                CK(cudaFuncSetAttribute(zstd_frames_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZD_SMEM));
+                zd_attr = true;
+            }
+            static int zd_serial = -1;                          // FOURMC_ZD_SERIAL=1: the serial decoder only (development aid)
+            if (zd_serial < 0) zd_serial = getenv("FOURMC_ZD_SERIAL") ? 1 : 0;
+            if (!zd_serial)
+                KL("zstd_frames_warp_kernel", st, zstd_frames_warp_kernel<<<(nb + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, ZD_SMEM, st>>>(
+                    desc, nb, (fmz::Work *)ws.zwork.p, (const fmz::Tables *)ctx->ztables.p, (int32_t *)ws.result.p));
             KL("zstd_frames_kernel", st, zstd_frames_kernel<<<(nb + 31) / 32, 32, 0, st>>>(desc, nb, (fmz::Work *)ws.zwork.p,
-                                                           (const fmz::Tables *)ctx->ztables.p, (int32_t *)ws.result.p));
+                                                           (const fmz::Tables *)ctx->ztables.p, (int32_t *)ws.result.p, zd_serial ? 0 : 1));
         } else
         KL("lz4_parse_kernel", st, lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, D1_SMEM, st>>>(desc, nb, (uint32_t *)ws.tokmap.p, (uint32_t *)ws.chunkop.p,
                                                        (int32_t *)ws.result.p));

@@ -34,7 +34,10 @@ constexpr int BLOCK_MAX = 128 * 1024;   // zstd.h:132-133
 struct HufEntry { uint8_t sym, nbits; };
 struct SeqEntry { uint32_t base; uint16_t next; uint8_t nbits, extra; };
 
+struct WtEntry { uint16_t next; uint8_t sym, nbits; };     // FSE table of the Huffman weights (log <= 6)
+
 struct Work {                            // per frame, lives in global memory on the GPU
+    static constexpr int HUF_MAX_LOG = 12;
     HufEntry huf[4096];
     SeqEntry ll[512], ml[512], of[256];
     int huf_log, ll_log, ml_log, of_log;
@@ -45,7 +48,7 @@ struct Work {                            // per frame, lives in global memory on
     uint16_t symnext[256];
     uint8_t weights[256];
     uint32_t rank[16];
-    struct { uint16_t next; uint8_t sym, nbits; } wt[64];   // FSE table of the Huffman weights (log <= 6)
+    WtEntry wt[64];
     uint8_t lit[BLOCK_MAX + 32];
 };
 
@@ -93,10 +96,24 @@ struct SeqBits {
     long long at;                        // byte offset the container was loaded from
     uint32_t used;                       // bits consumed from the top of the container
     uint64_t c;
-    FZ_HD void load() { uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)p[at + i] << (8 * i); c = v; }
+    long long len;                       // bytes of the stream
+    FZ_HD void load()
+    {
+#if defined(__CUDA_ARCH__)
+        if (at + 12 <= len) {            // three aligned words + funnel shifts (the extra bytes read stay inside the block)
+            const uintptr_t a = (uintptr_t)(p + at);
+            const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+            const uint32_t sh = (uint32_t)(a & 3) * 8;
+            const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+            c = (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+            return;
+        }
+#endif
+        uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)p[at + i] << (8 * i); c = v;
+    }
     FZ_HD bool init(const uint8_t *src, long long n)
     {
-        p = src;
+        p = src; len = n;
         if (n < 1 || src[n - 1] == 0) return false;
         used = 8 - highbit(src[n - 1]);
         if (n >= 8) { at = n - 8; load(); }
@@ -236,7 +253,8 @@ FZ_HD inline bool build_seq_table(SeqEntry *t, uint16_t *symnext, const short *n
 
 // HUF_readStats + HUF_readDTableX1 (entropy_common.c:244-312, huf_decompress.c:344-480).
 // Returns bytes consumed or <0.
-FZ_HD inline int read_huffman(Work &w, const uint8_t *src, long long n)
+template <class W>
+FZ_HD inline int read_huffman(W &w, const uint8_t *src, long long n)
 {
     if (n < 1) return ERR_SRCSIZE;
     int isz = src[0], osz;
@@ -287,6 +305,7 @@ FZ_HD inline int read_huffman(Work &w, const uint8_t *src, long long n)
     if (total == 0) return ERR_CORRUPT;
     const int log = highbit(total) + 1;
     if (log > 12) return ERR_CORRUPT;
+    if (log > W::HUF_MAX_LOG) return ERR_UNSUPPORTED;       // table does not fit this work area (the warp kernel's: retried serially)
     {
         const uint32_t rest = (1u << log) - total;
         if ((1u << highbit(rest)) != rest) return ERR_CORRUPT;
@@ -414,7 +433,8 @@ FZ_HD inline void make_tables(Tables &T)
 }
 
 // one of the three sequence tables (zstd_decompress_block.c:608-653)
-FZ_HD inline int build_mode(int mode, SeqEntry *t, int *log, int *ok, Work &w, const Tables &T, int which,
+template <class W>
+FZ_HD inline int build_mode(int mode, SeqEntry *t, int *log, int *ok, W &w, const Tables &T, int which,
                             const uint8_t *src, long long n)
 {
     const int max_sym = which == 0 ? 35 : which == 1 ? 31 : 52;         // LL, OF, ML

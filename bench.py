@@ -31,6 +31,7 @@ BLOCK = 4 * 1024 * 1024
 GIB = 1 << 30
 SEED = 0x4D43
 METRIC = "4mc_fast_lz4_compress_plus_decompress_uncompressed_GBps"
+METRIC_4MZ = "4mz_fast_zstd_compress_plus_decompress_uncompressed_GBps"
 
 
 def parse_args():
@@ -39,6 +40,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--codec", default="4mc", choices=["4mc", "4mz"],
+                    help="4mc = the headline LZ4 path (BASELINE.json configs[1]); 4mz = the zstd path (configs[2], on the log-text input)")
     ap.add_argument("--total-gib", type=float, default=64.0, help="resident synthetic input per GPU")
     ap.add_argument("--batch-gib", type=float, default=16.0, help="bytes per step per GPU")
     ap.add_argument("--e2e-gib", type=float, default=8.0, help="bytes per end-to-end step per GPU")
@@ -57,8 +60,28 @@ class CpuReference:
     :637-661 (XXH32 + LZ4_decompress_safe), spread over all host cores (the reference itself is
     single-threaded; Hadoop runs one task per core)."""
 
-    def __init__(self):
+    def __init__(self, codec="4mc"):
         ref = os.path.join(ROOT, "oracle", "_ref", "libref4mc.so")
+        self.codec = codec
+        if codec == "4mz":
+            # ZSTD_compress level 1 / ZSTD_decompress per block (native/4mc.c:467, :810); there is no
+            # zstd port in oracle/, so this arm needs the reference build
+            if not os.path.exists(ref):
+                raise SystemExit("the 4mz CPU arm needs oracle/_ref/libref4mc.so (make -C oracle ref)")
+            self.kind = "reference"
+            L = C.CDLL(ref)
+            L.ZSTD_compress.restype = C.c_size_t
+            L.ZSTD_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+            L.ZSTD_decompress.restype = C.c_size_t
+            L.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+            self.compress = lambda src, dst, n, cap: L.ZSTD_compress(dst, cap, src, n, 1)
+            self.decompress = lambda src, dst, c, cap: L.ZSTD_decompress(dst, cap, src, c)
+            self.xxh = L.XXH32
+            self.xxh.restype = C.c_uint32
+            self.xxh.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
+            self.cores = os.cpu_count() or 1
+            self.pool = ThreadPoolExecutor(self.cores)
+            return
         if os.path.exists(ref):
             self.kind = "reference"
             L = C.CDLL(ref)
@@ -123,8 +146,8 @@ class CpuReference:
         return t1 - t0, t2 - t1, sum(csz)
 
 
-def run_cpu(gib, steps, warmup):
-    ref = CpuReference()
+def run_cpu(gib, steps, warmup, codec="4mc"):
+    ref = CpuReference(codec)
     nbytes = int(gib * GIB) // BLOCK * BLOCK
     src = ref.make_input(nbytes)
     slot = BLOCK + BLOCK // 255 + 64
@@ -143,7 +166,8 @@ def run_cpu(gib, steps, warmup):
     return {
         "value": total / (tc + td) / 1e9, "unit": "GB/s", "cores": ref.cores, "kind": ref.kind,
         "sample": f"{nbytes / GIB:.2f} GiB log-text per step x {steps} steps, {ref.cores} threads, in memory "
-                  f"(LZ4_compress_default+XXH32 / XXH32+LZ4_decompress_safe per 4 MiB block)",
+                  + ("(ZSTD_compress level 1+XXH32 / XXH32+ZSTD_decompress per 4 MiB block)" if codec == "4mz" else
+                     "(LZ4_compress_default+XXH32 / XXH32+LZ4_decompress_safe per 4 MiB block)"),
         "compress_GBps": total / tc / 1e9, "decompress_GBps": total / td / 1e9, "ratio": nbytes / csum,
         "ms_per_step": (tc + td) / steps * 1e3,
     }
@@ -153,12 +177,12 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cpu = run_cpu(args.cpu_gib, args.steps, args.warmup)
+    cpu = run_cpu(args.cpu_gib, args.steps, args.warmup, args.codec)
     line = {
-        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "GB/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC_4MZ if args.codec == "4mz" else METRIC, "value": cpu["value"], "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "4mc Fast (LZ4) compress+decompress, synthetic log-text, 4 MiB blocks",
+        "config": {"workload": ("4mz Fast (ZSTD level 1)" if args.codec == "4mz" else "4mc Fast (LZ4)") + " compress+decompress, synthetic log-text, 4 MiB blocks",
                    "bytes_per_step": int(args.cpu_gib * GIB), "l2": "inputs larger than any cache"},
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "detail": {k: cpu[k] for k in ("compress_GBps", "decompress_GBps", "ratio")},
@@ -217,6 +241,13 @@ def main_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = pkg.Context(local)                      # raises (no CPU fallback) if the device is unusable
+    zst = args.codec == "4mz"
+    compress_device = ctx.compress_4mz_device if zst else ctx.compress_device
+    decompress_device = ctx.decompress_4mz_device if zst else ctx.decompress_device
+    build_index_device = ctx.build_index_4mz_device if zst else ctx.build_index_device
+    lib = pkg.lib()
+    compress_host = lib.fourmc_4mz_compress_host if zst else lib.fourmc_4mc_compress_host
+    decompress_host = lib.fourmc_4mz_decompress_host if zst else lib.fourmc_4mc_decompress_host
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     st = stream.cuda_stream
@@ -259,16 +290,16 @@ def main_ours(args):
         s_ptr = src.data_ptr() + b * batch
         if record:
             record[0].record(stream)
-        ctx.compress_device(s_ptr, batch, comp.data_ptr(), cap, size.data_ptr(), d_block_lens=lens.data_ptr(), stream=st)
+        compress_device(s_ptr, batch, comp.data_ptr(), cap, size.data_ptr(), d_block_lens=lens.data_ptr(), stream=st)
         if world > 1:
             # the only exchange of the sharded writer: block lengths -> footer index on rank 0
             dist.all_gather_into_tensor(all_lens, lens)
             if rank == 0:
-                ctx.build_index_device(all_lens.data_ptr(), nb * world, None, tail.data_ptr(), stream=st)
+                build_index_device(all_lens.data_ptr(), nb * world, None, tail.data_ptr(), stream=st)
         if record:
             record[1].record(stream)
         csz = int(size.item())                    # the stream length the reader needs (one 8-byte D2H)
-        ctx.decompress_device(comp.data_ptr(), csz, out.data_ptr(), batch, res.data_ptr(), stream=st)
+        decompress_device(comp.data_ptr(), csz, out.data_ptr(), batch, res.data_ptr(), stream=st)
         if record:
             record[2].record(stream)
         return b, csz
@@ -348,9 +379,9 @@ def main_ours(args):
 
         def e2e_step():
             t_a = time.perf_counter()
-            c = ctx.compress_host_ptr(h_in.data_ptr(), en, h_comp.data_ptr(), ecap)
+            c = ctx._check(compress_host(ctx.handle, 1, h_in.data_ptr(), en, h_comp.data_ptr(), ecap))
             t_b = time.perf_counter()
-            d = ctx.decompress_host_ptr(h_comp.data_ptr(), c, h_out.data_ptr(), en)
+            d = ctx._check(decompress_host(ctx.handle, h_comp.data_ptr(), c, h_out.data_ptr(), en))
             e2e_t[0] += t_b - t_a
             e2e_t[1] += time.perf_counter() - t_b
             assert d == en
@@ -373,17 +404,18 @@ def main_ours(args):
 
     cpu = None
     if not args.no_cpu and rank == 0 and world == 1:
-        c = run_cpu(args.cpu_gib, 2, 1)
+        c = run_cpu(args.cpu_gib, 2, 1, args.codec)
         cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
         cpu["compress_GBps"], cpu["decompress_GBps"] = c["compress_GBps"], c["decompress_GBps"]
     sampler.stop()
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC_4MZ if zst else METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: 4mc Fast (LZ4) compress+decompress 64 GiB synthetic log-text, 4 MiB blocks",
+            "config": {"workload": ("configs[2]: 4mz Fast (ZSTD) compress+decompress on the 64 GiB synthetic log-text input of configs[1], 4 MiB blocks"
+                                    if zst else "configs[1]: 4mc Fast (LZ4) compress+decompress 64 GiB synthetic log-text, 4 MiB blocks"),
                        "resident_input_gib_per_gpu": total / GIB, "batch_gib_per_step_per_gpu": batch / GIB,
                        "blocks_per_step_per_gpu": nb, "parallelism": f"block-sharded x{world}",
                        "l2": "inputs (GiBs per step) far larger than the 126 MB L2; no flush needed"},
