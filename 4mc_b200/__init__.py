@@ -20,7 +20,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib4mcgpu.so")
+LIB_PATH = os.environ.get("FOURMC_LIB") or os.path.join(_HERE, "lib4mcgpu.so")      # FOURMC_LIB: a development build to A/B against
 CSRC = os.path.join(_HERE, "csrc")
 
 BLOCKSIZE = 4 * 1024 * 1024

@@ -36,7 +36,7 @@ struct EncWs {
 };
 
 struct DecWs {
-    DevBuf desc, xxh, status, tokmap, chunkop, result, info, tables, outsize, final_, zwork;
+    DevBuf desc, xxh, status, tokmap, chunkop, result, info, tables, outsize, final_, zwork, zlane;
     // the checksum pass runs beside the parse on its own stream (both only read the payloads)
     cudaStream_t side = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
@@ -380,11 +380,36 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
                 CK(cudaFuncSetAttribute(zstd_frames_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZD_SMEM));
                 zd_attr = true;
             }
-            static int zd_serial = -1;                          // FOURMC_ZD_SERIAL=1: the serial decoder only (development aid)
-            if (zd_serial < 0) zd_serial = getenv("FOURMC_ZD_SERIAL") ? 1 : 0;
-            if (!zd_serial)
+            // FOURMC_ZD_MODE = lane (default) | warp | serial: which fast path runs before the exact serial decoder
+            static int zd_mode = -1;
+            if (zd_mode < 0) {
+                const char *e = getenv("FOURMC_ZD_MODE");
+                zd_mode = !e ? 2 : !strcmp(e, "serial") ? 0 : !strcmp(e, "warp") ? 1 : 2;
+            }
+            const int zd_serial = zd_mode == 0;
+            if (zd_mode == 1)
                 KL("zstd_frames_warp_kernel", st, zstd_frames_warp_kernel<<<(nb + ZD_WARPS - 1) / ZD_WARPS, ZD_WARPS * 32, ZD_SMEM, st>>>(
                     desc, nb, (fmz::Work *)ws.zwork.p, (const fmz::Tables *)ctx->ztables.p, (int32_t *)ws.result.p));
+            if (zd_mode == 2) {
+                // resident warps per SM: the fewest that give the smallest number of rounds over the
+                // frames (a frame's latency grows with the warps sharing an SM); FOURMC_ZL_PER_SM overrides
+                static int forced = -1;
+                if (forced < 0) { const char *e = getenv("FOURMC_ZL_PER_SM"); forced = e ? atoi(e) : 0; if (forced > 32) forced = 32; }
+                uint32_t per_sm = (uint32_t)forced;
+                if (!per_sm) {
+                    const uint32_t sm = (uint32_t)ctx->sm_count, most = 28;
+                    const uint32_t rounds = (nb + sm * most - 1) / (sm * most);
+                    per_sm = (nb + sm * rounds - 1) / (sm * rounds);
+                    if (per_sm < 1) per_sm = 1;
+                    if (per_sm > most) per_sm = most;
+                }
+                const uint32_t grid = std::min<uint32_t>(nb, (uint32_t)ctx->sm_count * per_sm);
+                if ((r = ensure(ctx, ws.zlane, (size_t)grid * sizeof(ZlScratch) + 64))) return r;
+                uint32_t *counter = (uint32_t *)((uint8_t *)ws.zlane.p + (size_t)grid * sizeof(ZlScratch));
+                CK(cudaMemsetAsync(counter, 0, 4, st));
+                KL("zstd_frames_lane_kernel", st, zstd_frames_lane_kernel<<<grid, 32, 0, st>>>(
+                    desc, nb, (ZlScratch *)ws.zlane.p, (const fmz::Tables *)ctx->ztables.p, (int32_t *)ws.result.p, counter));
+            }
             KL("zstd_frames_kernel", st, zstd_frames_kernel<<<(nb + 31) / 32, 32, 0, st>>>(desc, nb, (fmz::Work *)ws.zwork.p,
                                                            (const fmz::Tables *)ctx->ztables.p, (int32_t *)ws.result.p, zd_serial ? 0 : 1));
         } else
@@ -520,7 +545,7 @@ void fourmc_ctx_destroy(fourmc_ctx *ctx)
         release(e.scratch); release(e.meta); release(e.plan); release(e.lens); release(e.off); release(e.misc); release(e.zout); release(e.zrout);
         DecWs &d = ctx->dec[i];
         release(d.desc); release(d.xxh); release(d.status); release(d.tokmap); release(d.chunkop);
-        release(d.result); release(d.info); release(d.tables); release(d.outsize); release(d.final_); release(d.zwork);
+        release(d.result); release(d.info); release(d.tables); release(d.outsize); release(d.final_); release(d.zwork); release(d.zlane);
         if (d.side) cudaStreamDestroy(d.side);
         if (d.fork) cudaEventDestroy(d.fork);
         if (d.join) cudaEventDestroy(d.join);

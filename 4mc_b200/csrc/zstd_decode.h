@@ -52,7 +52,14 @@ struct Work {                            // per frame, lives in global memory on
     uint8_t lit[BLOCK_MAX + 32];
 };
 
-FZ_HD inline int highbit(uint32_t v) { int r = -1; while (v) { v >>= 1; r++; } return r; }
+FZ_HD inline int highbit(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)v);           // -1 for 0, like the loop below
+#else
+    int r = -1; while (v) { v >>= 1; r++; } return r;
+#endif
+}
 
 // ---- bit readers ----------------------------------------------------------------------------
 

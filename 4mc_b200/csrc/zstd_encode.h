@@ -33,7 +33,10 @@ namespace fmz {
 constexpr int ZE_REGION = 65536;               // input bytes per zstd block
 constexpr int ZE_THREADS = 128;                // threads of the entropy CTA
 constexpr int ZE_WARPS = ZE_THREADS / 32;
-constexpr int ZE_TILE = 2048;                  // sequences per pass of the sequence encoder
+#ifndef FOURMC_ZE_TILE
+#define FOURMC_ZE_TILE 1024
+#endif
+constexpr int ZE_TILE = FOURMC_ZE_TILE;        // sequences per pass of the sequence encoder
 constexpr int ZE_PER_THREAD = ZE_TILE / ZE_THREADS;
 constexpr int ZE_HUF_MAXBITS = 11;             // zstd_compress_literals.c: LitHufLog
 constexpr int ZE_MIN_HUF_LITS = 256;           // below: raw literals
@@ -401,6 +404,8 @@ struct ZShared {
     uint16_t fse[3][ZE_TILE];         // value | nbits << 10, in encoding order inside the tile
     uint32_t scan[ZE_THREADS];
     uint32_t scan_tmp[ZE_WARPS];
+    uint32_t ll_base[36], ml_base[53];        // copies of the format constants (the global ones cost a cache miss per use)
+    uint8_t ll_bits[36], ml_bits[53];
     uint32_t state[3];
     int32_t mode[3], log[3], max_code[3], ncount_len[3];
     int32_t nsym, max_sym, huf_log, hufdesc_len;
@@ -429,6 +434,8 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
         for (int i = tid; i < ZE_OUT_SLOT / 16; i += ZE_THREADS) z[i] = Z16{0, 0, 0, 0};
         for (int i = tid; i < 256; i += ZE_THREADS) { sh.hist[i] = 0; sh.nbits[i] = 0; }
         for (int i = tid; i < 3 * 64; i += ZE_THREADS) sh.chist[i / 64][i % 64] = 0;
+        if (tid < 36) { sh.ll_base[tid] = T.ll_base[tid]; sh.ll_bits[tid] = T.ll_bits[tid]; }
+        if (tid < 53) { sh.ml_base[tid] = T.ml_base[tid]; sh.ml_bits[tid] = T.ml_bits[tid]; }
         if (tid == 0) { sh.nsym = 0; sh.max_sym = 0; sh.fail = 0; sh.bitpos = 0; sh.max_code[0] = sh.max_code[1] = sh.max_code[2] = 0; }
     });
 
@@ -654,7 +661,7 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
             const uint32_t p0 = (uint32_t)tid * ZE_PER_THREAD, p1 = p0 + ZE_PER_THREAD < cnt ? p0 + ZE_PER_THREAD : cnt;
             for (uint32_t p = p0; p < p1; p++) {
                 const uint32_t lc = sh.code[0][p], oc = sh.code[1][p], mc = sh.code[2][p];
-                bits += (sh.fse[0][p] >> 10) + (sh.fse[1][p] >> 10) + (sh.fse[2][p] >> 10) + T.ll_bits[lc] + T.ml_bits[mc] + oc;
+                bits += (sh.fse[0][p] >> 10) + (sh.fse[1][p] >> 10) + (sh.fse[2][p] >> 10) + sh.ll_bits[lc] + sh.ml_bits[mc] + oc;
             }
             sh.scan[tid] = bits;
         });
@@ -674,8 +681,8 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
                 br.add(fo & 1023u, (int)(fo >> 10));
                 br.add(fm & 1023u, (int)(fm >> 10));
                 br.add(fl & 1023u, (int)(fl >> 10));
-                br.add((uint32_t)in.ll[i] - T.ll_base[lc], T.ll_bits[lc]);
-                br.add((uint32_t)in.ml[i] - T.ml_base[mc], T.ml_bits[mc]);
+                br.add((uint32_t)in.ll[i] - sh.ll_base[lc], sh.ll_bits[lc]);
+                br.add((uint32_t)in.ml[i] - sh.ml_base[mc], sh.ml_bits[mc]);
                 br.add(((uint32_t)in.off[i] + 3u) - (1u << oc), (int)oc);
             }
             br.finish();
