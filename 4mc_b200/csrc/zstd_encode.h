@@ -12,8 +12,9 @@
 //   * one zstd block per 64 KiB REGION of the 4 MiB 4mz block (64 per frame); the LZ sequences of
 //     a region come from the same shared-memory match finder as the LZ4 path (lz4_encode.cuh);
 //   * literals: raw, RLE, or Huffman with a fresh tree per block (direct 4-bit weights), 4 streams;
-//   * sequences: per table predefined / RLE / FSE-described, never "repeat"; offsets are always
-//     coded as real offsets (no repeat-offset codes), so blocks do not depend on each other;
+//   * sequences: per table predefined / RLE / FSE-described, never "repeat"; offsets are real
+//     offsets or "same offset as the previous sequence of this block" (the one repeat code that
+//     does not depend on earlier blocks), so blocks do not depend on each other;
 //   * single-segment frame header with a 4-byte content size, no checksum.
 // Everything that writes output bits works on a zeroed buffer with OR semantics, so any number
 // of threads can assemble one bitstream from prefix-summed bit positions.
@@ -381,6 +382,15 @@ struct ZRegionIn {
     uint32_t rlen;                    // region length in input bytes
 };
 
+// Offset as coded (zstd_compress_internal.h: offBase).  3 + offset for a real offset; 1 = "the
+// previous sequence's offset again" (repeat code 0, needs a non-empty literal run).  Only that one
+// repeat code is used: right after any sequence of the same block the decoder's newest history
+// entry IS that sequence's offset, whatever the earlier blocks did -- so blocks stay independent.
+FZ_HD inline uint32_t ze_off_base(const uint16_t *ll, const uint16_t *off, uint32_t i)
+{
+    return (i > 0 && ll[i] > 0 && off[i] == off[i - 1]) ? 1u : (uint32_t)off[i] + 3u;
+}
+
 struct ZRegionOut {
     uint32_t bytes;                   // body size of the compressed block (literals + sequences sections)
     uint32_t raw;                     // 1: emit the region as a raw block instead
@@ -444,7 +454,7 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
         for (uint32_t i = (uint32_t)tid; i < nlit; i += ZE_THREADS) ex.add32(&sh.hist[in.lits[i]], 1);
         for (uint32_t i = (uint32_t)tid; i < nseq; i += ZE_THREADS) {
             ex.add32(&sh.chist[0][ll_code(in.ll[i])], 1);
-            ex.add32(&sh.chist[1][(uint32_t)highbit((uint32_t)in.off[i] + 3u)], 1);
+            ex.add32(&sh.chist[1][(uint32_t)highbit(ze_off_base(in.ll, in.off, i))], 1);
             ex.add32(&sh.chist[2][ml_code((uint32_t)in.ml[i] - 3u)], 1);
         }
     });
@@ -627,7 +637,7 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
             for (uint32_t p = (uint32_t)tid; p < cnt; p += ZE_THREADS) {
                 const uint32_t i = hi - 1 - p;
                 sh.code[0][p] = (uint8_t)ll_code(in.ll[i]);
-                sh.code[1][p] = (uint8_t)highbit((uint32_t)in.off[i] + 3u);
+                sh.code[1][p] = (uint8_t)highbit(ze_off_base(in.ll, in.off, i));
                 sh.code[2][p] = (uint8_t)ml_code((uint32_t)in.ml[i] - 3u);
             }
         });
@@ -683,7 +693,7 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
                 br.add(fl & 1023u, (int)(fl >> 10));
                 br.add((uint32_t)in.ll[i] - sh.ll_base[lc], sh.ll_bits[lc]);
                 br.add((uint32_t)in.ml[i] - sh.ml_base[mc], sh.ml_bits[mc]);
-                br.add(((uint32_t)in.off[i] + 3u) - (1u << oc), (int)oc);
+                br.add(ze_off_base(in.ll, in.off, i) - (1u << oc), (int)oc);
             }
             br.finish();
         });

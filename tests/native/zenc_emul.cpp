@@ -28,26 +28,38 @@ struct EmuExec {
 
 inline uint32_t rd4(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 
-// greedy matcher over one region: most recent occurrence of a 4-byte hash, minimum match `mm`
-void find_sequences(const uint8_t *d, int n, int mm, std::vector<uint16_t> &ll, std::vector<uint16_t> &ml,
+// Greedy matchers over one region (test-only stand-ins for the region kernel):
+//   mode 0  most recent occurrence of a 4-byte hash
+//   mode 1  FIRST occurrence (what the GPU match finder indexes)
+//   mode 2  first occurrence, but the previous match's offset is tried first (repeat offset)
+void find_sequences(const uint8_t *d, int n, int mm, int mode, std::vector<uint16_t> &ll, std::vector<uint16_t> &ml,
                     std::vector<uint16_t> &off, std::vector<uint8_t> &lits)
 {
     std::vector<int> table(1 << 14, -1);
-    int p = 0, anchor = 0;
+    if (mode >= 1)
+        for (int q = n - 4; q >= 0; q--) table[(rd4(d + q) * 2654435761u) >> 18] = q;
+    int p = 0, anchor = 0, rep = 0;
     while (p + 4 <= n) {
         const uint32_t v = rd4(d + p);
         const uint32_t h = (v * 2654435761u) >> 18;
-        const int c = table[h];
-        table[h] = p;
-        if (c >= 0 && rd4(d + c) == v) {
+        int c = table[h];
+        if (mode == 0) table[h] = p;
+        int best = 0, bo = 0;
+        if (c >= 0 && c < p && rd4(d + c) == v) {
             int len = 4;
             while (p + len < n && d[p + len] == d[c + len]) len++;
-            if (len >= mm && len <= 65535 && p - anchor <= 65535) {
-                ll.push_back((uint16_t)(p - anchor)); ml.push_back((uint16_t)len); off.push_back((uint16_t)(p - c));
-                lits.insert(lits.end(), d + anchor, d + p);
-                p += len; anchor = p;
-                continue;
-            }
+            best = len; bo = p - c;
+        }
+        if (mode == 2 && rep > 0 && p - rep >= 0 && p > anchor && rd4(d + p - rep) == v) {
+            int len = 4;
+            while (p + len < n && d[p + len] == d[p - rep + len]) len++;
+            if (len + 3 >= best) { best = len; bo = rep; }
+        }
+        if (best >= (bo == rep && mode == 2 ? 4 : mm) && best <= 65535 && p - anchor <= 65535) {
+            ll.push_back((uint16_t)(p - anchor)); ml.push_back((uint16_t)best); off.push_back((uint16_t)bo);
+            lits.insert(lits.end(), d + anchor, d + p);
+            p += best; anchor = p; rep = bo;
+            continue;
         }
         p++;
     }
@@ -58,6 +70,7 @@ void find_sequences(const uint8_t *d, int n, int mm, std::vector<uint16_t> &ll, 
 
 // One zstd frame for src[0..n), n <= 4 MiB, assembled the way the GPU kernels assemble it.
 // Returns the frame size, or -1 when it does not fit.
+// min_match: low 4 bits = minimum match length, bits 4.. = matcher mode (see find_sequences)
 extern "C" long long zenc_emul_compress(uint8_t *dst, long long cap, const uint8_t *src, long long n, int min_match)
 {
     static fmz::Tables T;
@@ -73,7 +86,7 @@ extern "C" long long zenc_emul_compress(uint8_t *dst, long long cap, const uint8
         const int rlen = (int)std::min<long long>(fmz::ZE_REGION, n - o);
         std::vector<uint16_t> ll, ml, off;
         std::vector<uint8_t> lits;
-        find_sequences(src + o, rlen, min_match, ll, ml, off, lits);
+        find_sequences(src + o, rlen, min_match & 15, min_match >> 4, ll, ml, off, lits);
         lits.resize(lits.size() + 8);
         fmz::ZRegionIn in{ll.data(), ml.data(), off.data(), lits.data(), (uint32_t)ll.size(), (uint32_t)(lits.size() - 8), (uint32_t)rlen};
         fmz::ZRegionOut ro{0, 0};

@@ -83,7 +83,7 @@ def sample_inputs(pkg):
 def test_emulated_encoder_frames_decode(zenc, zdec, pkg):
     ref = ref_decoder()
     for name, data in sample_inputs(pkg).items():
-        for mm in (4, 5):
+        for mm in (4, 5, 4 | (1 << 4), 5 | (2 << 4)):           # bits 4..: the stand-in matcher (recent / first / first + repeat offset)
             cap = len(data) + len(data) // 64 + 1024
             out = C.create_string_buffer(cap)
             c = zenc.zenc_emul_compress(out, cap, data, len(data), mm)
