@@ -169,6 +169,18 @@ int slice_blocks()
     return v;
 }
 
+int zslice_blocks()
+{
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("FOURMC_ZSLICE_BLOCKS");
+        v = e ? atoi(e) : 384;
+        if (v < 1) v = 1;
+        if (v > 4096) v = 4096;
+    }
+    return v;
+}
+
 int pipe_depth()
 {
     static int v = 0;
@@ -1112,8 +1124,9 @@ static long long decompress_host_impl(fourmc_ctx *ctx, int codec, const void *in
     const int walk_err = walk_streams(src, n, blocks, &total, codec == CODEC_ZSTD ? FOURMC_MAGIC_4MZ : FOURMC_MAGIC_4MC,
                                       codec == CODEC_ZSTD ? 0x289A1C9Au : 0xA4B73443u);
     if (total > out_capacity) return fail(ctx, FOURMC_E_OUTPUT, "destination too small");
-    // slices of consecutive blocks; footers travel as hash-only items
-    const size_t sl_blocks = (size_t)slice_blocks();
+    // slices of consecutive blocks; footers travel as hash-only items.  A zstd frame takes tens of
+    // milliseconds however few are in flight (its entropy streams are serial), so 4mz slices are larger.
+    const size_t sl_blocks = codec == CODEC_ZSTD ? (size_t)zslice_blocks() : (size_t)slice_blocks();
     int r;
     struct Slice { size_t b0, b1; uint64_t s0, s1, d0, d1; };
     std::vector<Slice> slices;
@@ -1134,7 +1147,7 @@ static long long decompress_host_impl(fourmc_ctx *ctx, int codec, const void *in
     const size_t pin_need = 4096 + FM_PIPE_MAX * tb_host + blocks.size() * 5 + 64;
     if ((r = pinned_scratch(ctx, pin_need))) return r;
     uint8_t *pin = (uint8_t *)ctx->pinned + 4096;
-    const int np = pipe_depth();
+    const int np = codec == CODEC_ZSTD ? std::min(pipe_depth(), 3) : pipe_depth();
     uint8_t *h_tables[FM_PIPE_MAX];
     for (int i = 0; i < FM_PIPE_MAX; i++) h_tables[i] = pin + (size_t)i * tb_host;
     uint32_t *hashes = (uint32_t *)(pin + FM_PIPE_MAX * tb_host);

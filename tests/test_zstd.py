@@ -202,6 +202,27 @@ def test_gpu_4mz_device_call_many_blocks(ctx, pkg, ora):
 
 
 @pytest.mark.gpu
+def test_gpu_decodes_live_reference_frames(ctx, pkg, ora, ref):
+    """Full 4 MiB blocks compressed by the reference's ZSTD_compress here and now, at the four 4mz levels
+    (1 / 3 / 6 / 12: native/4mc.c:415-425): 32 sub-blocks per frame with treeless literals and repeat-mode
+    tables, decoded by the batch path and by the per-block call."""
+    ref.ZSTD_compress.restype = C.c_size_t
+    ref.ZSTD_compress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]
+    data = gen_logtext(pkg, 2 * 4 * MIB + 123457, first_page=999)
+    for lvl in (1, 3, 6, 12):
+        blocks = []
+        for o in range(0, len(data), 4 * MIB):
+            src = data[o:o + 4 * MIB]
+            cb = C.create_string_buffer(len(src))
+            c = ref.ZSTD_compress(cb, len(src) - 1, src, len(src), lvl)
+            assert 0 < c < len(src)
+            blocks.append((len(src), c, cb.raw[:c]))
+        assert ctx.decompress_4mz(assemble_4mz(ora, blocks)) == data, lvl
+        r, out = ctx.zstd_decompress(blocks[0][2], 4 * MIB)
+        assert r == 4 * MIB and out == data[:4 * MIB], lvl
+
+
+@pytest.mark.gpu
 def test_cli_decodes_reference_4mz(pkg, tmp_path):
     cli = os.path.join(ROOT, "4mc_b200", "host", "4mc")
     src = os.path.join(ROOT, "tests", "golden", "logtext_1280k.z2.4mz")
