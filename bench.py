@@ -351,14 +351,15 @@ def main_ours(args):
     roofline = None
     if dom:
         name, (cnt, ms) = dom
-        algo = batch + 12 * nb + mean_c          # compress: read u, write 12+c; decompress: read 12+c, write u
+        per_step = max(1, round(cnt / args.steps))   # launches of this kernel per step (the 4mz writer works in groups of blocks)
+        algo = (batch + 12 * nb + mean_c) / per_step   # compress: read u, write 12+c; decompress: read 12+c, write u
         ach = algo / (ms / cnt / 1e3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             t = json.load(open(tp)).get(name)
             if t:
-                traffic = t["dram_bytes_per_uncompressed_byte"] * batch
+                traffic = t["dram_bytes_per_uncompressed_byte"] * batch / per_step
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
                     "avg_launch_ms": ms / cnt}

@@ -13,13 +13,17 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
-for f in (f"{tag}_bench.json", f"{tag}_bench_reference.json", f"{tag}_launches.csv"):
+for f in (f"{tag}_bench.json", f"{tag}_bench_reference.json", f"{tag}_launches.csv",
+          f"{tag}_bench_4mz.json", f"{tag}_bench_4mz_reference.json", f"{tag}_launches_4mz.csv"):
     if os.path.exists(os.path.join(G, f)):
         shutil.copy(os.path.join(G, f), os.path.join(P, f))
 
-# ---- launch list -> per-kernel shares
-lp = os.path.join(G, f"{tag}_launches.csv")
-if os.path.exists(lp):
+# ---- launch lists -> per-kernel shares
+for suffix, cmd in (("", "python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu"),
+                    ("_4mz", "python bench.py --codec 4mz --steps 1 --warmup 1 --no-e2e --no-cpu")):
+    lp = os.path.join(G, f"{tag}_launches{suffix}.csv")
+    if not os.path.exists(lp):
+        continue
     rows = list(csv.reader(open(lp)))
     hdr = next(r for r in rows if "Kernel Name" in r)
     ki, mi, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -34,9 +38,8 @@ if os.path.exists(lp):
         a[0] += 1
         a[1] += v
     tot = sum(a[1] for a in agg.values()) or 1
-    with open(os.path.join(P, f"{tag}_launches_summary.md"), "w") as f:
-        f.write(f"# ncu launch list summary ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none "
-                f"python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu`\n\n")
+    with open(os.path.join(P, f"{tag}_launches{suffix}_summary.md"), "w") as f:
+        f.write(f"# ncu launch list summary ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none {cmd}`\n\n")
         f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES.\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {k} | {a[0]} | {a[1]:.3f} | {100 * a[1] / tot:.1f}% |\n")
@@ -50,6 +53,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+# uncompressed bytes one captured launch covers: the whole 16 GiB batch, except the zstd entropy
+# stage, which runs once per group of 512 blocks (capi.cu zgroup_blocks)
+LAUNCH_BYTES = {"zstd_entropy_kernel": 512 * 4 * 2 ** 20}
 traffic_path = os.path.join(P, "traffic.json")
 traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
 for rep in sorted(os.listdir(G)):
@@ -63,7 +69,8 @@ for rep in sorted(os.listdir(G)):
     hdr, units, vals = rows[0], rows[1], rows[2]
     got = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
     with open(os.path.join(P, f"{tag}_{kernel}_metrics.txt"), "w") as f:
-        f.write(f"# {kernel}: ncu --set full --clock-control none (one launch of `bench.py --steps 1 --total-gib 16`, 16 GiB batch)\n")
+        f.write(f"# {kernel}: ncu --set full --clock-control none (one launch of `bench.py --steps 1 --total-gib 16`, "
+                f"{LAUNCH_BYTES.get(kernel, 16 * 2 ** 30) / 2 ** 30:g} GiB per launch)\n")
         for w in WANT:
             if w in got:
                 f.write(f"{w:80s} {got[w][0]} {got[w][1]}\n")
@@ -71,7 +78,7 @@ for rep in sorted(os.listdir(G)):
         def num(k):
             v, u = got[k]
             return float(v.replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
-        traffic[kernel] = {"dram_bytes_per_uncompressed_byte": (num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) / (16 * 2 ** 30),
+        traffic[kernel] = {"dram_bytes_per_uncompressed_byte": (num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) / LAUNCH_BYTES.get(kernel, 16 * 2 ** 30),
                            "source": f"profiles/{tag}_{kernel}_metrics.txt"}
     except (KeyError, ValueError):
         pass
