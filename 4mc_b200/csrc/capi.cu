@@ -196,11 +196,19 @@ int pipe_depth()
 int level_min_match(int level)
 {
     // level 1 (Fast): minimum match 5 gives fewer, longer sequences at the same ratio on text
-    // (DESIGN.md); the other levels currently share the kernel.
+    // (DESIGN.md); the chain parse of levels 2..4 takes every match of 4 or more.
     const char *e = getenv("FOURMC_MIN_MATCH");
     if (e) { int v = atoi(e); if (v >= 4 && v <= 16) return v; }
-    (void)level;
-    return 5;
+    return level >= 2 ? 4 : 5;
+}
+
+// Levels as in native/4mc.c:243-253 (1 fast, 2 medium = LZ4 MC, 3 high = HC 4, 4 ultra = HC 8; the
+// 4mz twins :415-425): candidates tried per chain search; 0 selects the Fast parse.
+int level_chain_depth(int level)
+{
+    const char *e = getenv("FOURMC_CHAIN_DEPTH");
+    if (e) { int v = atoi(e); if (v >= 0 && v <= 4096) return v; }
+    return level <= 1 ? 0 : level == 2 ? 4 : level == 3 ? 16 : 64;
 }
 
 enum { CODEC_LZ4 = 0, CODEC_ZSTD = 1 };
@@ -239,8 +247,10 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     if ((r = ensure(ctx, ws.off, (size_t)nb * 8))) return r;
     if ((r = ensure(ctx, ws.misc, 64))) return r;
     if (!ctx->region_attr_set) {
-        CK(cudaFuncSetAttribute(lz4_region_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
-        CK(cudaFuncSetAttribute(lz4_region_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_CHAIN));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_CHAIN));
         ctx->region_attr_set = true;
     }
     CK(cudaMemsetAsync(ws.misc.p, 0, 64, st));
@@ -250,8 +260,14 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     P.work_counter = (uint32_t *)ws.misc.p;
     P.min_match = level_min_match(level);
     P.slot_bytes = ENC_SLOT;
-    const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
-    KL("lz4_region_kernel", st, lz4_region_kernel<false><<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
+    P.depth = level_chain_depth(level); P.lazy = P.depth > 0;
+    if (P.depth > 0) {
+        const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
+        KL("lz4_region_chain_kernel", st, lz4_region_kernel<false, true><<<grid, ENC_THREADS, ENC_SMEM_CHAIN, st>>>(P));
+    } else {
+        const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
+        KL("lz4_region_kernel", st, lz4_region_kernel<false, false><<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
+    }
     uint32_t *lens = d_block_lens_out ? d_block_lens_out : (uint32_t *)ws.lens.p;
     KL("lz4_block_size_kernel", st, lz4_block_size_kernel<<<(nb + 127) / 128, 128, 0, st>>>((const RegionMeta *)ws.meta.p, nb, n,
                                                            (BlockPlan *)ws.plan.p, lens, raw_limit));
@@ -300,8 +316,10 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
     if ((r = ensure(ctx, ws.lens, (size_t)nb * 4))) return r;
     if ((r = ensure(ctx, ws.off, (size_t)nb * 8))) return r;
     if (!ctx->region_attr_set) {
-        CK(cudaFuncSetAttribute(lz4_region_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
-        CK(cudaFuncSetAttribute(lz4_region_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_CHAIN));
+        CK(cudaFuncSetAttribute(lz4_region_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM_CHAIN));
         ctx->region_attr_set = true;
     }
     uint8_t *misc = (uint8_t *)ws.misc.p;
@@ -319,8 +337,14 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
         P.work_counter = (uint32_t *)misc;
         P.min_match = level_min_match(level);
         P.slot_bytes = fmz::ZE_IN_SLOT;
-        const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
-        KL("lz4_region_kernel", st, lz4_region_kernel<true><<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
+        P.depth = level_chain_depth(level); P.lazy = P.depth > 0;
+        if (P.depth > 0) {
+            const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
+            KL("lz4_region_chain_kernel", st, lz4_region_kernel<true, true><<<grid, ENC_THREADS, ENC_SMEM_CHAIN, st>>>(P));
+        } else {
+            const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
+            KL("lz4_region_kernel", st, lz4_region_kernel<true, false><<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
+        }
         ZEncParams Z;
         Z.meta = (const RegionMeta *)ws.meta.p; Z.scratch_in = (const uint8_t *)ws.scratch.p;
         Z.scratch_out = (uint8_t *)ws.zout.p; Z.rout = (fmz::ZRegionOut *)ws.zrout.p;

@@ -44,6 +44,9 @@ constexpr int ENC_MAXREC = ENC_SLICE / 4 + 1;    // inner records of one slice
 constexpr int ENC_PAD = 64;
 constexpr int ENC_STAGE = 48 * 1024;             // output staging: the (dead) hash table + 16 KiB
 constexpr size_t ENC_SMEM = ENC_REGION + ENC_PAD + ENC_STAGE;
+// chain parse (levels 2..4): u16 prev[65536] (previous position with the same hash) + u16 head[1 << 14]
+constexpr int ENC_STAGE_CHAIN = 2 * ENC_REGION + (2 << 14);
+constexpr size_t ENC_SMEM_CHAIN = ENC_REGION + ENC_PAD + ENC_STAGE_CHAIN;
 static_assert((sizeof(uint16_t) << ENC_HASH_BITS) <= ENC_STAGE, "the hash table lives inside the staging area");
 
 static_assert(ENC_THREADS * ENC_SLICE >= ENC_REGION, "slices must cover the region");
@@ -64,6 +67,8 @@ struct EncParams {
     uint32_t *work_counter;  // zeroed before launch
     int min_match;           // >= 4
     uint32_t slot_bytes;     // scratch bytes per region (ENC_SLOT; fmz::ZE_IN_SLOT for sequence output)
+    int depth;               // chain parse: candidates tried per search (levels 2..4); unused by the Fast parse
+    int lazy;                // chain parse: one-step lazy evaluation
 };
 
 __device__ __forceinline__ uint32_t enc_hash(uint32_t v) { return (v * 2654435761u) >> (32 - ENC_HASH_BITS); }
@@ -117,8 +122,17 @@ __device__ __forceinline__ uint32_t enc_pack(int st_rel, int len, int off)
 // (literal length, match length, offset) arrays plus the gathered literals for the zstd entropy
 // stage (zstd_encode.cuh): slot = u16 ll[n] | u16 ml[n] | u16 off[n] | literals, n rounded up to 8;
 // RegionMeta.body_bytes then holds the literal count (tail literals included).
-template <bool ZSEQ>
-__global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
+//
+// CHAIN = false: the Fast parse (level 1), first-occurrence table.  CHAIN = true: levels 2..4
+// (LZ4 MC and HC are hash-chain searches, native/lz4/lz4mc.c:518-579,
+// native/lz4/lz4hc.c:239-447).  Every position of the region is linked to the previous position
+// with the same 4-byte hash (u16 prev[], built in ascending order by warp 0, 32 positions per step,
+// __match_any_sync for the links inside a step); a search follows `depth` links and keeps the
+// longest match; with `lazy` a match is dropped when the next position has a longer one.  The
+// slices, the stitching and the emit stages are shared with the Fast parse.  One CTA per SM
+// (224 KiB of shared memory).
+template <bool ZSEQ, bool CHAIN>
+__global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(EncParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *data = smem;                                          // ENC_REGION + ENC_PAD
@@ -170,7 +184,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
         }
         for (int i = bulk + tid; i < rlen; i += ENC_THREADS) data[i] = gsrc[i];
         if (tid < ENC_PAD) data[rlen + tid] = 0;                   // reads past the end see zeros
-        for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += ENC_THREADS) ((uint32_t *)table)[i] = 0xffffffffu;
+        uint16_t *prev = table, *head = table + ENC_REGION;         // CHAIN only
+        if constexpr (CHAIN) { for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += ENC_THREADS) ((uint32_t *)head)[i] = 0xffffffffu; }
+        else { for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += ENC_THREADS) ((uint32_t *)table)[i] = 0xffffffffu; }
         if (bulk) {
             uint32_t done = 0;
             while (!done) {
@@ -186,7 +202,23 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
         // ---- index: first occurrence of every 4-byte hash.  Descending sweep, 4 consecutive
         // positions per thread (two word loads, three funnel shifts); within a thread and between
         // steps the lower position is stored last, within a step the order is left to the race.
-        {
+        if constexpr (CHAIN) {
+            const int last = rlen - 4;
+            if (tid < 32) {
+                for (int base = 0; base <= last; base += 32) {
+                    const int p = base + lane;
+                    const bool live = p <= last;
+                    const uint32_t h = live ? enc_hash(smem_read4(data32, p)) : 0x10000u + (uint32_t)lane;
+                    const unsigned same = __match_any_sync(FM_FULL, h);
+                    const unsigned lower = same & ((1u << lane) - 1u);
+                    if (live) prev[p] = lower ? (uint16_t)(base + 31 - __clz(lower)) : head[h];
+                    __syncwarp();
+                    if (live && (same >> lane) == 1u) head[h] = (uint16_t)p;   // the highest lane of a group
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+        } else {
             const int last = rlen - 4;                             // last position with 4 bytes
             constexpr int STEP = ENC_THREADS * 4;
             for (int base = ((rlen - 1) / STEP) * STEP; base >= 0; base -= STEP) {
@@ -208,7 +240,45 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
         int nrec = 0;
         int l_st = 0, l_len = 0, l_off = 0;                        // last sequence (l_len == 0: none)
         const int ss = tid * ENC_SLICE;
-        if (ss < rlen) {
+        if (CHAIN && ss < rlen) {
+            const int se = min(ss + ENC_SLICE, rlen);
+            int p = ss, anchor = ss;
+            int have_p = -1, have_len = 0, have_off = 0;           // a search result carried over by the lazy step
+            auto search = [&](int q, int &bo) -> int {
+                const uint32_t v = smem_read4(data32, q);
+                const int maxlen = match_limit - q;
+                int best = 0, c = (int)prev[q];
+                for (int k = 0; k < P.depth && c != 0xffff; k++, c = (int)prev[c]) {
+                    if (smem_read4(data32, c) != v) continue;
+                    if (best >= 4 && data[q + best] != data[c + best]) continue;      // cannot beat the best so far
+                    int len = 4;
+                    while (len < maxlen) {
+                        const uint32_t x = smem_read4(data32, q + len) ^ smem_read4(data32, c + len);
+                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                        len += 4;
+                    }
+                    len = min(len, maxlen);
+                    if (len > best) { best = len; bo = q - c; }
+                }
+                return best;
+            };
+            while (p < se && p <= mf_limit) {
+                int off = 0, len;
+                if (have_p == p) { len = have_len; off = have_off; } else len = search(p, off);
+                if (len < P.min_match) { p++; continue; }
+                if (P.lazy && p + 1 <= mf_limit) {
+                    int off2 = 0;
+                    const int len2 = search(p + 1, off2);
+                    if (len2 > len) { have_p = p + 1; have_len = len2; have_off = off2; p++; continue; }
+                }
+                int st = p, m = p - off;
+                while (st > anchor && m > 0 && data[st - 1] == data[m - 1]) { st--; m--; len++; }
+                if (l_len) rec[nrec++] = enc_pack(l_st - ss, l_len, l_off);
+                l_st = st; l_len = len; l_off = st - m;
+                p = st + len; anchor = p;
+            }
+        }
+        if (!CHAIN && ss < rlen) {
             const int se = min(ss + ENC_SLICE, rlen);
             // pass 1 -- every position of the slice, no skipping: does the table hold an earlier
             // position with the same four bytes?  One bit per position (uniform work for all lanes).
@@ -356,8 +426,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 2) lz4_region_kernel(EncParams P)
         // those are copied by the whole warp afterwards.
         uint8_t *stage = (uint8_t *)table;
         __syncthreads();                                            // every thread is done with the table
-        const bool staged = out_off + bytes <= ENC_STAGE;
-        if (tid == 0) s_flush = min(total_bytes, ENC_STAGE);
+        constexpr int STAGE_CAP = CHAIN ? ENC_STAGE_CHAIN : ENC_STAGE;
+        const bool staged = out_off + bytes <= STAGE_CAP;
+        if (tid == 0) s_flush = min(total_bytes, STAGE_CAP);
         __syncthreads();
         if (!staged && bytes > 0) atomicMin(&s_flush, out_off);     // the staged prefix ends at the first direct writer
         int long_n = 0, long_src = 0;

@@ -17,7 +17,11 @@ inline uint32_t hsh(uint32_t v) { return (v * 2654435761u) >> (32 - HB); }
 inline int ext(int v) { return v < 15 ? 0 : 1 + (v - 15) / 255; }
 inline uint8_t *emit_len(uint8_t *o, int v) { while (v >= 255) { *o++ = 255; v -= 255; } *o++ = (uint8_t)v; return o; }
 
-void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_off, int min_match, std::vector<uint8_t> &body, Meta &mt)
+// depth == 0: the Fast parse (first-occurrence table).  depth > 0: the chain parse of the higher
+// levels -- every position linked to the previous position with the same hash, `depth` candidates
+// per search, optional one-step lazy evaluation.
+void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_off, int min_match, std::vector<uint8_t> &body, Meta &mt,
+            int depth = 0, int lazy = 0)
 {
     const int rlen = (int)std::min<uint32_t>(REGION, blk_len - r_off);
     std::vector<uint8_t> data(REGION + PAD, 0);
@@ -32,11 +36,51 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_off, int min_match,
     std::vector<std::vector<Seq>> inner(THREADS);
     std::vector<Seq> last(THREADS, Seq{0, 0, 0});
     const uint8_t *d = data.data();
+    std::vector<uint16_t> prev;
+    if (depth > 0) {
+        // chain build, ascending (on the GPU: one warp, 32 positions per step, __match_any_sync for the
+        // links inside a step)
+        prev.assign(REGION, 0xffff);
+        std::vector<uint16_t> head(1 << HB, 0xffff);
+        for (int p = 0; p <= rlen - 4; p++) { const uint32_t h = hsh(rd4(d, p)); prev[p] = head[h]; head[h] = (uint16_t)p; }
+    }
+    auto search = [&](int p, int &bo) -> int {
+        const uint32_t v = rd4(d, p);
+        const int maxlen = match_limit - p;
+        int best = 0, c = prev[p];
+        for (int k = 0; k < depth && c != 0xffff; k++, c = prev[c]) {
+            if (rd4(d, c) != v) continue;
+            int len = 4;
+            while (len < maxlen && d[p + len] == d[c + len]) len++;
+            len = std::min(len, maxlen);
+            if (len > best) { best = len; bo = p - c; }
+        }
+        return best;
+    };
     for (int t = 0; t < THREADS; t++) {
         const int ss = t * SLICE;
         if (ss >= rlen) continue;
         const int se = std::min(ss + SLICE, rlen);
         int p = ss, anchor = ss;
+        if (depth > 0) {
+            int have_len = 0, have_off = 0, have_p = -1;          // a search result carried over by the lazy step
+            while (p < se && p <= mf_limit) {
+                int off = 0, len;
+                if (have_p == p) { len = have_len; off = have_off; } else len = search(p, off);
+                if (len < min_match) { p++; continue; }
+                if (lazy && p + 1 <= mf_limit) {
+                    int off2 = 0;
+                    const int len2 = search(p + 1, off2);
+                    if (len2 > len) { have_p = p + 1; have_len = len2; have_off = off2; p++; continue; }
+                }
+                int st = p, m = p - off;
+                while (st > anchor && m > 0 && d[st - 1] == d[m - 1]) { st--; m--; len++; }
+                if (last[t].len) inner[t].push_back(last[t]);
+                last[t] = Seq{st, len, st - m};
+                p = st + len; anchor = p;
+            }
+            continue;
+        }
         while (p < se && p <= mf_limit) {
             const uint32_t v = rd4(d, p);
             const int c = table[hsh(v)];
@@ -103,11 +147,18 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_off, int min_match,
 
 // Compresses one block (n <= 4 MiB) the way the kernels do.  Returns the LZ4 payload size written
 // to dst (capacity must be >= n + n/255 + 64), never "stored".
-extern "C" int enc_emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match)
+static int emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth, int lazy);
+extern "C" int enc_emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match) { return emul_block(src, n, dst, min_match, 0, 0); }
+// the chain parse of levels 2..4 (capi.cu level_chain_depth / level_lazy)
+extern "C" int enc_emul_block_chain(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth, int lazy)
+{
+    return emul_block(src, n, dst, min_match, depth, lazy);
+}
+static int emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth, int lazy)
 {
     std::vector<Meta> meta(RPB, Meta{0, 0, 0, 0});
     std::vector<std::vector<uint8_t>> bodies(RPB);
-    for (int r = 0; r < RPB; r++) if ((uint32_t)r * REGION < (uint32_t)n) region(src, (uint32_t)n, (uint32_t)r * REGION, min_match, bodies[r], meta[r]);
+    for (int r = 0; r < RPB; r++) if ((uint32_t)r * REGION < (uint32_t)n) region(src, (uint32_t)n, (uint32_t)r * REGION, min_match, bodies[r], meta[r], depth, lazy);
     uint8_t *o = dst; uint32_t carry = 0;
     for (int r = 0; r < RPB; r++) {
         const Meta &x = meta[r];

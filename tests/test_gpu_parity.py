@@ -10,6 +10,7 @@ import pytest
 from conftest import golden_bytes, golden_json, gen_logtext
 
 pytestmark = pytest.mark.gpu
+MIB = 1024 * 1024
 
 
 # ---------------------------------------------------------------- XXH32
@@ -241,3 +242,38 @@ def test_device_decode_detects_corruption(ctx, pkg):
         assert code == pkg.E_CONTENT and blk >= 0
         if expect_block is not None:
             assert blk == expect_block
+
+
+def test_levels_2_to_4_chain_parse(ctx, ora, pkg, ref_cli, tmp_path):
+    """Levels 2..4 (SURVEY rows a11 / a12, and the upper 4mz levels of a10): the hash-chain parse.  Valid
+    streams (oracle, reference CLI), ratio above the Fast level and growing with the level."""
+    import os
+    import subprocess
+    text = gen_logtext(pkg, 9 * MIB + 4321, first_page=5)
+    mixed = text[:3 * MIB] + bytes(300000) + os.urandom(MIB) + (b"abcdefg" * 200000)[:MIB] + text[:100]
+    sizes = {}
+    for level in (1, 2, 3, 4):
+        for name, data in (("text", text), ("mixed", mixed)):
+            s = ctx.compress_4mc(data, level)
+            assert ora.decompress_4mc(s, len(data)) == (len(data), data), (level, name)
+            assert ctx.decompress_4mc(s) == data
+            z = ctx.compress_4mz(data, level)
+            assert ctx.decompress_4mz(z) == data, (level, name)
+            if name == "text":
+                sizes[level] = (len(s), len(z))
+            if level == 3:
+                for blob, flag in ((s, []), (z, ["-z"])):
+                    src, out = tmp_path / "lv.bin", tmp_path / "lv.out"
+                    src.write_bytes(blob)
+                    subprocess.run([ref_cli, "-f", "-q", "-q"] + flag + ["-d", str(src), str(out)], check=True)
+                    assert out.read_bytes() == data
+    for k in (0, 1):
+        assert sizes[4][k] < sizes[3][k] < sizes[2][k] < sizes[1][k], sizes
+    assert len(text) / sizes[2][0] > 2.15 and len(text) / sizes[4][0] > 2.25, sizes
+    # per-block calls: LZ4_compressMC / LZ4_compressHC2 / ZSTD_compress(level) of the JNI natives
+    blk = text[:4 * MIB]
+    for level in (2, 3, 4):
+        c = ctx.lz4_compress(blk, level)
+        assert ora.lz4_decompress(c, len(blk)) == (len(blk), blk)
+        f = ctx.zstd_compress(blk, level)
+        assert ctx.zstd_decompress(f, len(blk)) == (len(blk), blk)

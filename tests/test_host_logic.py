@@ -62,6 +62,8 @@ def emul():
     L = build_native("enc_emul", ["tests/native/enc_emul.cpp"])
     L.enc_emul_block.restype = C.c_int
     L.enc_emul_block.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+    L.enc_emul_block_chain.restype = C.c_int
+    L.enc_emul_block_chain.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int]
     return L
 
 
@@ -73,6 +75,25 @@ def test_encode_algorithm_roundtrip(emul, ora, pkg, n):
         dst = C.create_string_buffer(n + n // 255 + 128)
         c = emul.enc_emul_block(src, n, dst, 5)
         assert ora.lz4_decompress(dst.raw[:c], n) == (n, src), (name, n)
+
+
+@pytest.mark.parametrize("n", [0, 13, 133, 65537, 200000, 4194304])
+def test_chain_parse_algorithm_roundtrip(emul, ora, pkg, n):
+    """Levels 2..4 (hash-chain search, lazy evaluation): sequential emulation of the
+    chain variant of lz4_region_kernel; the output decodes to the input and the ratio grows with the depth."""
+    text = gen_logtext(pkg, 4 * 1024 * 1024)
+    kinds = (("text", text[:n]), ("zeros", bytes(n)), ("period", (b"abcdefg" * (n // 7 + 1))[:n]))
+    for name, src in kinds[:1] if n > 200000 else kinds:       # the degenerate inputs are slow in the emulation at 4 MiB
+        sizes = []
+        for depth, lazy in ((4, 1), (16, 1), (64, 1), (4, 0)):
+            dst = C.create_string_buffer(n + n // 255 + 128)
+            c = emul.enc_emul_block_chain(src, n, dst, 4, depth, lazy)
+            assert ora.lz4_decompress(dst.raw[:c], n) == (n, src), (name, n, depth)
+            sizes.append(c)
+        if name == "text" and n == 4194304:
+            fast = emul.enc_emul_block(src, n, C.create_string_buffer(n + n // 255 + 128), 5)
+            assert sizes[2] < sizes[1] < sizes[0] < fast
+            assert n / sizes[0] > 2.2 and n / sizes[2] > 2.3       # reference: MC 2.255, HC 2.597 / 2.680 (BASELINE.md)
 
 
 def test_encode_algorithm_ratio(emul, pkg):
