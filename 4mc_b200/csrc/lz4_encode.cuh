@@ -126,8 +126,8 @@ __device__ __forceinline__ uint32_t enc_pack(int st_rel, int len, int off)
 // CHAIN = false: the Fast parse (level 1), first-occurrence table.  CHAIN = true: levels 2..4
 // (LZ4 MC and HC are hash-chain searches, native/lz4/lz4mc.c:518-579,
 // native/lz4/lz4hc.c:239-447).  Every position of the region is linked to the previous position
-// with the same 4-byte hash (u16 prev[], built in ascending order by warp 0, 32 positions per step,
-// __match_any_sync for the links inside a step); a search follows `depth` links and keeps the
+// with the same 4-byte hash (u16 prev[], built in ascending rounds of 128 positions by four warps);
+// a search follows `depth` links and keeps the
 // longest match; with `lazy` a match is dropped when the next position has a longer one.  The
 // slices, the stitching and the emit stages are shared with the Fast parse.  One CTA per SM
 // (224 KiB of shared memory).
@@ -203,18 +203,23 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
         // positions per thread (two word loads, three funnel shifts); within a thread and between
         // steps the lower position is stored last, within a step the order is left to the race.
         if constexpr (CHAIN) {
+            // Chain build.  All threads first store every position's hash in prev[]; then warps 0..3 walk
+            // the region in ascending rounds of 128 positions: a position is linked to the head of its
+            // bucket as of the previous round, then the round's positions become the heads (for equal
+            // hashes inside a round one of them wins, the others stay reachable only through their own
+            // links -- 0.2 % of ratio on text, tests/native/enc_emul.cpp EMUL_BUILD=128000).
             const int last = rlen - 4;
-            if (tid < 32) {
-                for (int base = 0; base <= last; base += 32) {
-                    const int p = base + lane;
+            for (int p = tid; p <= last; p += ENC_THREADS) prev[p] = (uint16_t)enc_hash(smem_read4(data32, p));
+            __syncthreads();
+            if (tid < 128) {
+                for (int base = 0; base <= last; base += 128) {
+                    const int p = base + tid;
                     const bool live = p <= last;
-                    const uint32_t h = live ? enc_hash(smem_read4(data32, p)) : 0x10000u + (uint32_t)lane;
-                    const unsigned same = __match_any_sync(FM_FULL, h);
-                    const unsigned lower = same & ((1u << lane) - 1u);
-                    if (live) prev[p] = lower ? (uint16_t)(base + 31 - __clz(lower)) : head[h];
-                    __syncwarp();
-                    if (live && (same >> lane) == 1u) head[h] = (uint16_t)p;   // the highest lane of a group
-                    __syncwarp();
+                    uint32_t h = 0;
+                    if (live) { h = prev[p]; prev[p] = head[h]; }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (live) head[h] = (uint16_t)p;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
             }
             __syncthreads();

@@ -73,7 +73,8 @@ int fourmc_lz4_compress_bound(int n);
  * LZ4_compress / LZ4_compressMC / LZ4_compressHC2 (native/jniCompressor.c:91,123,156).
  * Returns the compressed size (> 0), 0 when it does not fit in dst_capacity (the caller then
  * stores the block raw, native/4mc.c:318-329), or a negative FOURMC_E_*.
- * The bytes are a valid LZ4 block but not the reference's bytes.  level: 1 fast .. 4 ultra. */
+ * The bytes are a valid LZ4 block but not the reference's bytes.  level: 1 fast (first-occurrence
+ * table, greedy) .. 2 medium / 3 high / 4 ultra (hash chains, 4 / 16 / 64 candidates, lazy). */
 int fourmc_lz4_compress(fourmc_ctx *ctx, int level, const void *src, int src_size,
                         void *dst, int dst_capacity);
 
@@ -164,7 +165,7 @@ int fourmc_xxh32_batch_device(fourmc_ctx *ctx, void *stream, uint32_t n_items,
  * are zstd frames.  Readers: native/4mc.c:709-857 (decodeFourMZ), :810 ZSTD_decompress.  Writers:
  * native/4mc.c:389-553 (fourMZcompressFilename), :467 ZSTD_compress with the stored fallback
  * :469-485.  The frames are valid zstd (ZSTD_decompress restores the input) but not the reference's
- * bytes; all four levels currently share the "Fast" encoder. */
+ * bytes; levels 2..4 use the hash-chain match finder of the LZ4 levels 2..4. */
 long long fourmc_4mz_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, void *out, size_t out_capacity);
 long long fourmc_4mz_decoded_size_host(const void *in, size_t n);
 int fourmc_4mz_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n,

@@ -38,11 +38,29 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_off, int min_match,
     const uint8_t *d = data.data();
     std::vector<uint16_t> prev;
     if (depth > 0) {
-        // chain build, ascending (on the GPU: one warp, 32 positions per step, __match_any_sync for the
-        // links inside a step)
+        // chain build, ascending.  EMUL_BUILD=0 is the exact chain; R*1000+W emulates rounds of R positions
+        // with exact links only inside windows of W (the kernel: four warps, rounds of 128, W = 0)
         prev.assign(REGION, 0xffff);
         std::vector<uint16_t> head(1 << HB, 0xffff);
-        for (int p = 0; p <= rlen - 4; p++) { const uint32_t h = hsh(rd4(d, p)); prev[p] = head[h]; head[h] = (uint16_t)p; }
+        const char *bm = getenv("EMUL_BUILD");
+        const int mode = bm ? atoi(bm) : 128000;             // the kernel's build: rounds of 128, no links inside a round
+        if (mode == 0)
+            for (int p = 0; p <= rlen - 4; p++) { const uint32_t h = hsh(rd4(d, p)); prev[p] = head[h]; head[h] = (uint16_t)p; }
+        else {
+            // rounds of R positions: links go to the head as of the previous round; inside a round only
+            // positions within W of each other are linked exactly; the round's highest position wins the head
+            const int R = mode / 1000, W = mode % 1000;
+            for (int r0 = 0; r0 <= rlen - 4; r0 += R) {
+                const int r1 = std::min(r0 + R, rlen - 3);
+                for (int p = r0; p < r1; p++) {
+                    const uint32_t h = hsh(rd4(d, p));
+                    int pr = head[h];
+                    for (int q = p - 1; q >= std::max(r0, p - W) && q >= (p / 32) * 32; q--) if (hsh(rd4(d, q)) == h) { pr = q; break; }
+                    prev[p] = (uint16_t)pr;
+                }
+                for (int p = r0; p < r1; p++) head[hsh(rd4(d, p))] = (uint16_t)p;
+            }
+        }
     }
     auto search = [&](int p, int &bo) -> int {
         const uint32_t v = rd4(d, p);
