@@ -238,6 +238,11 @@ def main_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # stdout carries the one JSON line only: everything libraries print there (NCCL's version banner under
+    # NCCL_DEBUG, for one) goes to stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = pkg.Context(local)                      # raises (no CPU fallback) if the device is unusable
@@ -426,10 +431,12 @@ def main_ours(args):
             "detail": {"compress_GBps": world * batch * args.steps / (t_c / 1e3) / 1e9,
                        "decompress_GBps": world * batch * args.steps / (t_d / 1e3) / 1e9,
                        "ratio": batch / mean_c, "verified_round_trip": verified,
+                       "step_ms": [[round(e[0].elapsed_time(e[1]), 2), round(e[1].elapsed_time(e[2]), 2)] for e in evs],
                        "kernel_ms": {k: {"launches": v[0], "total_ms": round(v[1], 3)} for k, v in sorted(ktimes.items())}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
