@@ -89,6 +89,13 @@ def lib() -> C.CDLL:
         "fourmc_4mz_compress_device": (i32, [vp, vp, i32, vp, sz, vp, sz, vp, vp]),
         "fourmc_4mz_compress_span_device": (i32, [vp, vp, i32, vp, sz, vp, sz, vp, vp]),
         "fourmc_4mz_build_index_device": (i32, [vp, vp, vp, u32, vp, vp]),
+        "fourmc_read_index_host": (C.c_longlong, [vp, vp, sz, vp, sz]),
+        "fourmc_index_find_next_position": (C.c_int64, [vp, i32, C.c_int64]),
+        "fourmc_index_find_belonging_block": (C.c_int64, [vp, i32, C.c_int64]),
+        "fourmc_index_align_slice_start": (C.c_int64, [vp, i32, C.c_int64, C.c_int64]),
+        "fourmc_index_align_slice_end": (C.c_int64, [vp, i32, C.c_int64, C.c_int64]),
+        "fourmc_plan_splits": (i32, [vp, i32, C.c_int64, C.c_int64, vp, vp, i32]),
+        "fourmc_read_split_lines_host": (C.c_longlong, [vp, vp, sz, C.c_int64, C.c_int64, vp, sz]),
         "fourmc_gen_device": (i32, [vp, vp, i32, u64, u64, u64, vp]),
         "fourmc_gen_host": (i32, [i32, u64, u64, u64, vp]),
     }
@@ -264,6 +271,28 @@ class Context:
     def decompress_4mz_device(self, d_in: int, n: int, d_out: int, out_capacity: int, d_result: int, stream=None):
         self._check(lib().fourmc_4mz_decompress_device(self._h, stream, d_in, n, d_out, out_capacity, d_result))
 
+    # ---- block index, splits, line records (FourMcBlockIndex / FourMcInputFormat / FourMcLineRecordReader) ----
+    def read_index(self, stream_bytes) -> list[int]:
+        """Block offsets from the footer index of a whole .4mc / .4mz file (FourMcInputStream.readIndex)."""
+        b = _buf(stream_bytes)
+        n = self._check(int(lib().fourmc_read_index_host(self._h, b, len(b), None, 0)))
+        arr = (C.c_int64 * max(n, 1))()
+        self._check(int(lib().fourmc_read_index_host(self._h, b, len(b), arr, n)))
+        return list(arr[:n])
+
+    def read_split_lines(self, stream_bytes, start: int, length: int) -> bytes:
+        """The records FourMcLineRecordReader returns for the split [start, start + length), concatenated."""
+        b = _buf(stream_bytes)
+        cap = (length // 4 + 8 * 1024 * 1024) * 16
+        while True:
+            out = C.create_string_buffer(cap)
+            rc = int(lib().fourmc_read_split_lines_host(self._h, b, len(b), start, length, out, cap))
+            if rc == E_OUTPUT and cap < (1 << 36):
+                cap *= 4
+                continue
+            self._check(rc)
+            return out.raw[:rc]
+
     # ---- device-resident calls: raw device pointers (ints) and an optional CUDA stream handle ----
     def gen_device(self, d_out: int, n_pages: int, seed: int = 0x4D43, first_page: int = 0, kind: int = 0, stream=None):
         self._check(lib().fourmc_gen_device(self._h, stream, kind, seed, first_page, n_pages, d_out))
@@ -394,6 +423,36 @@ class FourMcCodec:
 
     def decompress(self, stream) -> bytes:
         return self.ctx.decompress_4mc(stream)
+
+
+class FourMcBlockIndex:
+    """Mirror of com.fing.compression.fourmc.FourMcBlockIndex (FourMcBlockIndex.java:92-173) over the C-ABI."""
+    NOT_FOUND = -1
+
+    def __init__(self, offsets):
+        self.offsets = list(offsets)
+        self._arr = (C.c_int64 * max(len(self.offsets), 1))(*self.offsets)
+
+    def find_next_position(self, pos: int) -> int:
+        return int(lib().fourmc_index_find_next_position(self._arr, len(self.offsets), pos))
+
+    def find_belonging_block_index(self, pos: int) -> int:
+        return int(lib().fourmc_index_find_belonging_block(self._arr, len(self.offsets), pos))
+
+    def align_slice_start_to_index(self, start: int, end: int) -> int:
+        return int(lib().fourmc_index_align_slice_start(self._arr, len(self.offsets), start, end))
+
+    def align_slice_end_to_index(self, end: int, file_size: int) -> int:
+        return int(lib().fourmc_index_align_slice_end(self._arr, len(self.offsets), end, file_size))
+
+    def plan_splits(self, file_size: int, split_size: int) -> list[tuple[int, int]]:
+        """FourMcInputFormat.getSplits for one file: [(start, length)] (FourMcInputFormat.java:126-173)."""
+        n = int(lib().fourmc_plan_splits(self._arr, len(self.offsets), file_size, split_size, None, None, 0))
+        if n < 0:
+            raise FourMcError(n, "fourmc_plan_splits")
+        st, ln = (C.c_int64 * max(n, 1))(), (C.c_int64 * max(n, 1))()
+        lib().fourmc_plan_splits(self._arr, len(self.offsets), file_size, split_size, st, ln, n)
+        return [(int(st[i]), int(ln[i])) for i in range(n)]
 
 
 # ---- block sharding across ranks (SURVEY.md 8e) ---------------------------------------------

@@ -1242,6 +1242,206 @@ long long fourmc_4mz_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
     return decompress_host_impl(ctx, CODEC_ZSTD, in, n, out, out_capacity);
 }
 
+// ---- block index and splits: the step either side of the path (BASELINE.json configs[4]) ------
+
+// FourMcBlockIndex.findNextPosition (FourMcBlockIndex.java:92-104): the first block offset >= pos.
+int64_t fourmc_index_find_next_position(const int64_t *offsets, int n, int64_t pos)
+{
+    if (!offsets || n <= 0) return FOURMC_NOT_FOUND;
+    const int64_t *it = std::lower_bound(offsets, offsets + n, pos);
+    return it == offsets + n ? FOURMC_NOT_FOUND : *it;
+}
+
+// FourMcBlockIndex.findBelongingBlockIndex (:111-124): the block whose offset is the last one <= pos.
+int64_t fourmc_index_find_belonging_block(const int64_t *offsets, int n, int64_t pos)
+{
+    if (!offsets || n <= 0) return FOURMC_NOT_FOUND;
+    const int64_t *it = std::upper_bound(offsets, offsets + n, pos);
+    return it == offsets ? FOURMC_NOT_FOUND : (int64_t)(it - offsets) - 1;
+}
+
+// FourMcBlockIndex.alignSliceStartToIndex (:142-153)
+int64_t fourmc_index_align_slice_start(const int64_t *offsets, int n, int64_t start, int64_t end)
+{
+    if (start == 0) return 0;
+    const int64_t s = fourmc_index_find_next_position(offsets, n, start);
+    return (s == FOURMC_NOT_FOUND || s >= end) ? FOURMC_NOT_FOUND : s;
+}
+
+// FourMcBlockIndex.alignSliceEndToIndex (:163-173)
+int64_t fourmc_index_align_slice_end(const int64_t *offsets, int n, int64_t end, int64_t file_size)
+{
+    const int64_t e = fourmc_index_find_next_position(offsets, n, end);
+    return e == FOURMC_NOT_FOUND ? file_size : e;
+}
+
+// FourMcInputFormat.getSplits for one file (FourMcInputFormat.java:126-173): Hadoop's default byte-range
+// splits (FileInputFormat: pieces of split_size, the last one up to 1.1 x split_size) nudged to block starts;
+// splits that contain no block start disappear.  Returns the number of splits (may exceed cap: call again).
+int fourmc_plan_splits(const int64_t *offsets, int n, int64_t file_size, int64_t split_size,
+                       int64_t *starts, int64_t *lengths, int cap)
+{
+    if (file_size < 0 || split_size <= 0 || (n > 0 && !offsets)) return FOURMC_E_ARG;
+    int count = 0;
+    auto emit = [&](int64_t s, int64_t len) {
+        int64_t a = s, b = s + len;
+        if (n > 0) {                                              // an empty index leaves the default split (:153-156)
+            a = fourmc_index_align_slice_start(offsets, n, s, s + len);
+            b = fourmc_index_align_slice_end(offsets, n, s + len, file_size);
+            if (a == FOURMC_NOT_FOUND || b == FOURMC_NOT_FOUND) return;
+        }
+        if (count < cap && starts && lengths) { starts[count] = a; lengths[count] = b - a; }
+        count++;
+    };
+    int64_t remaining = file_size, pos = 0;
+    while ((double)remaining / (double)split_size > 1.1) { emit(pos, split_size); pos += split_size; remaining -= split_size; }
+    if (remaining != 0) emit(pos, remaining);
+    return count;
+}
+
+// FourMcInputStream.readIndex (FourMcInputStream.java:163-239): block offsets from the footer of a whole
+// .4mc / .4mz file in host memory; the footer checksum is verified on the device.  Returns the number of
+// blocks (offsets[] receives min(count, cap) of them), 0 for a file too short to hold an index, or
+// FOURMC_E_CONTENT.
+long long fourmc_read_index_host(fourmc_ctx *ctx, const void *file, size_t file_size, int64_t *offsets, size_t cap)
+{
+    if (!ctx || (!file && file_size)) return FOURMC_E_ARG;
+    const uint8_t *f = (const uint8_t *)file;
+    if (file_size < 12 + 20) return 0;
+    const uint32_t fsize = be32(f + file_size - 12), magic = be32(f + file_size - 8), ck = be32(f + file_size - 4);
+    if (magic != FOURMC_MAGIC_4MC && magic != FOURMC_MAGIC_4MZ) return FOURMC_E_CONTENT;
+    if (fsize >= file_size - 12 || fsize < 20 || ((fsize - 20) & 3)) return FOURMC_E_CONTENT;
+    const uint8_t *foot = f + file_size - fsize;
+    if (be32(foot) != fsize || be32(foot + 4) != FOURMC_VERSION) return FOURMC_E_CONTENT;
+    int st = FOURMC_OK;
+    const uint32_t h = fourmc_xxh32(ctx, foot, fsize - 4, 0, &st);
+    if (st != FOURMC_OK) return st;
+    if (h != ck) return FOURMC_E_CONTENT;
+    const size_t nb = (fsize - 20) / 4;
+    int64_t cur = 0;
+    for (size_t i = 0; i < nb; i++) {
+        cur += be32(foot + 8 + 4 * i);
+        if (i < cap && offsets) offsets[i] = cur;
+    }
+    return (long long)nb;
+}
+
+namespace {
+__global__ void find_byte_kernel(const uint8_t *p, unsigned long long n, uint8_t v, unsigned long long *first)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (p[i] == v) { atomicMin(first, i); break; }
+}
+}  // namespace
+
+// FourMcLineRecordReader over one split (FourMcLineRecordReader.java:116-163): the bytes of all the records
+// (lines, with their terminators) the reader would return for the split [start, start + length) of a whole
+// .4mc / .4mz file in host memory -- when start != 0 the first (partial) line is skipped, and the line that is
+// being read when the position passes the split end is finished from the following block(s).  The split's
+// blocks are decoded on the device in one batch; the two line boundaries are found there too.
+long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t file_size, int64_t start, int64_t length,
+                                       void *out, size_t out_capacity)
+{
+    if (!ctx || !file || start < 0 || length < 0 || (!out && out_capacity)) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint8_t *f = (const uint8_t *)file;
+    if (file_size < 12) return FOURMC_E_CONTENT;
+    const uint32_t magic = be32(f);
+    if (magic != FOURMC_MAGIC_4MC && magic != FOURMC_MAGIC_4MZ) return FOURMC_E_CONTENT;
+    const int codec = magic == FOURMC_MAGIC_4MZ ? CODEC_ZSTD : CODEC_LZ4;
+    const long long nb_ll = fourmc_read_index_host(ctx, file, file_size, nullptr, 0);
+    if (nb_ll < 0) return nb_ll;
+    if (nb_ll == 0) return 0;
+    std::vector<int64_t> offs((size_t)nb_ll);
+    fourmc_read_index_host(ctx, file, file_size, offs.data(), offs.size());
+    const int n = (int)nb_ll;
+    const int64_t end = start + length;
+    // first block of the split: the reader seeks to `start`, which the planner put on a block start
+    int b0 = 0;
+    if (start != 0) {
+        const int64_t s = fourmc_index_find_next_position(offs.data(), n, start);
+        if (s == FOURMC_NOT_FOUND || s >= end) return 0;
+        b0 = (int)(std::lower_bound(offs.begin(), offs.end(), s) - offs.begin());
+    }
+    const int b1 = (int)(std::lower_bound(offs.begin(), offs.end(), end) - offs.begin());      // blocks [b0, b1) start before `end`
+    if (b0 >= b1) return 0;
+    // block headers (native/4mc.c:603-668 field order), the split's blocks plus the ones after it while a line is open
+    struct HB { uint64_t src; uint32_t c, u, x; };
+    auto header = [&](int b, HB &h) -> bool {
+        const uint64_t o = (uint64_t)offs[b];
+        if (o + 12 > file_size) return false;
+        h.u = be32(f + o); h.c = be32(f + o + 4); h.x = be32(f + o + 8); h.src = o + 12;
+        return h.c <= FOURMC_BLOCKSIZE && (h.u == h.c || h.u <= FOURMC_BLOCKSIZE) && h.src + h.c <= file_size && h.u != 0;
+    };
+    cudaStream_t st = ctx->stream;
+    DecWs &ws = ctx->dec[0];
+    int r;
+    if ((r = pinned_scratch(ctx, 4096))) return r;
+    int t1 = std::min(n, b1 + 1);                                  // decode through block t1 - 1
+    for (;;) {
+        const uint32_t cnt = (uint32_t)(t1 - b0);
+        std::vector<HB> hb(cnt);
+        uint64_t total_u = 0;
+        for (uint32_t i = 0; i < cnt; i++) { if (!header(b0 + (int)i, hb[i])) return FOURMC_E_CONTENT; total_u += hb[i].u; }
+        const uint64_t src0 = hb[0].src, src1 = hb[cnt - 1].src + hb[cnt - 1].c;
+        if ((r = ensure(ctx, ctx->stage_in[0], (size_t)(src1 - src0) + 64))) return r;
+        if ((r = ensure(ctx, ctx->stage_out[0], (size_t)total_u + 64))) return r;
+        const size_t tb = (size_t)cnt * 33 + 64 + 16;
+        if ((r = ensure(ctx, ws.tables, tb))) return r;
+        std::vector<uint8_t> ht((size_t)cnt * 28);
+        uint64_t *t_src = (uint64_t *)ht.data(), *t_dst = t_src + cnt;
+        uint32_t *t_c = (uint32_t *)(t_dst + cnt), *t_u = t_c + cnt, *t_x = t_u + cnt;
+        uint64_t dpos = 0, u_split = 0;
+        for (uint32_t i = 0; i < cnt; i++) {
+            t_src[i] = hb[i].src - src0; t_dst[i] = dpos; t_c[i] = hb[i].c; t_u[i] = hb[i].u; t_x[i] = hb[i].x;
+            dpos += hb[i].u;
+            if ((int)i < b1 - b0) u_split = dpos;                  // decoded bytes of the split's own blocks
+        }
+        uint8_t *d_tb = (uint8_t *)ws.tables.p;
+        CK(cudaMemcpyAsync(ctx->stage_in[0].p, f + src0, (size_t)(src1 - src0), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tb, ht.data(), ht.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                             // ht is pageable host memory
+        const uint64_t *d_so = (const uint64_t *)d_tb, *d_do = d_so + cnt;
+        const uint32_t *d_c = (const uint32_t *)(d_do + cnt), *d_u = d_c + cnt, *d_x = d_u + cnt;
+        int32_t *d_osz = (int32_t *)(d_x + cnt);
+        uint8_t *d_st = (uint8_t *)(d_osz + cnt);
+        unsigned long long *d_first = (unsigned long long *)(((uintptr_t)(d_st + cnt) + 15) & ~(uintptr_t)15);
+        if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[0].p, d_so, d_c, d_u, d_x, 1, ctx->stage_out[0].p, d_do, d_osz, d_st, codec)))
+            return r;
+        // first line terminator of the split (skipped line) and the first one at or after the split's end
+        CK(cudaMemsetAsync(d_first, 0xff, 16, st));
+        const uint8_t *d_out = (const uint8_t *)ctx->stage_out[0].p;
+        if (start != 0)
+            KL("find_byte_kernel", st, find_byte_kernel<<<1024, 256, 0, st>>>(d_out, u_split, (uint8_t)'\n', d_first));
+        if (total_u > u_split)
+            KL("find_byte_kernel", st, find_byte_kernel<<<256, 256, 0, st>>>(d_out + u_split, total_u - u_split, (uint8_t)'\n', d_first + 1));
+        uint8_t *hs = (uint8_t *)ctx->pinned;
+        std::vector<uint8_t> status(cnt);
+        CK(cudaMemcpyAsync(hs, d_first, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(status.data(), d_st, cnt, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < cnt; i++) if (status[i] != FOURMC_BLOCK_OK) return FOURMC_E_CONTENT;
+        const unsigned long long first_nl = ((unsigned long long *)hs)[0], tail_nl = ((unsigned long long *)hs)[1];
+        uint64_t from = 0, to;
+        if (start != 0) {
+            // the skipped line must end inside the split's own blocks, else the reader's position is past `end`
+            if (first_nl == ~0ull) return 0;
+            from = first_nl + 1;
+        }
+        if (tail_nl != ~0ull) to = u_split + tail_nl + 1;
+        else if (t1 < n) { t1 = std::min(n, t1 + 4); continue; }    // the open line runs through every block decoded so far
+        else to = total_u;                                         // end of the file: the last line has no terminator
+        if (to < from) to = from;
+        if (to - from > out_capacity) return fail(ctx, FOURMC_E_OUTPUT, "destination too small");
+        if (to > from) {
+            CK(cudaMemcpyAsync(out, d_out + from, (size_t)(to - from), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        return (long long)(to - from);
+    }
+}
+
 // ZSTD_decompress on one block (native/4mc.c:810, native/jniZstdDecompressor.c): decoded size, or a
 // negative value when ZSTD_isError() would be true for the reference.
 long long fourmc_zstd_decompress(fourmc_ctx *ctx, const void *src, size_t compressed_size, void *dst, size_t dst_capacity)

@@ -35,7 +35,7 @@ constexpr int ZE_REGION = 65536;               // input bytes per zstd block
 constexpr int ZE_THREADS = 128;                // threads of the entropy CTA
 constexpr int ZE_WARPS = ZE_THREADS / 32;
 #ifndef FOURMC_ZE_TILE
-#define FOURMC_ZE_TILE 1024
+#define FOURMC_ZE_TILE 512
 #endif
 constexpr int ZE_TILE = FOURMC_ZE_TILE;        // sequences per pass of the sequence encoder
 constexpr int ZE_PER_THREAD = ZE_TILE / ZE_THREADS;

@@ -193,6 +193,33 @@ int fourmc_4mz_compress_span_device(fourmc_ctx *ctx, void *stream, int level, co
 int fourmc_4mz_build_index_device(fourmc_ctx *ctx, void *stream, const uint32_t *d_block_lens,
                                   uint32_t n_blocks, void *d_header, void *d_tail);
 
+/* ---- block index, splits, line records: the callers either side of the path --------------------
+ * (BASELINE.json configs[4]: per-split decode of a .4mc read through the InputFormat) */
+#define FOURMC_NOT_FOUND (-1)                         /* FourMcBlockIndex.NOT_FOUND */
+
+/* FourMcInputStream.readIndex (FourMcInputStream.java:163-239): absolute offsets of the block headers
+ * from the footer of a whole .4mc / .4mz file in host memory (footer XXH32 verified on the device).
+ * Returns the block count (offsets[] receives min(count, cap)), 0 when the file cannot hold an
+ * index, FOURMC_E_CONTENT on a damaged footer. */
+long long fourmc_read_index_host(fourmc_ctx *ctx, const void *file, size_t file_size, int64_t *offsets, size_t cap);
+
+/* FourMcBlockIndex.java:92-104, :111-124, :142-153, :163-173 -- same results, FOURMC_NOT_FOUND included. */
+int64_t fourmc_index_find_next_position(const int64_t *offsets, int n, int64_t pos);
+int64_t fourmc_index_find_belonging_block(const int64_t *offsets, int n, int64_t pos);
+int64_t fourmc_index_align_slice_start(const int64_t *offsets, int n, int64_t start, int64_t end);
+int64_t fourmc_index_align_slice_end(const int64_t *offsets, int n, int64_t end, int64_t file_size);
+
+/* FourMcInputFormat.getSplits for one file (FourMcInputFormat.java:126-173) on top of Hadoop's default
+ * byte-range splits of split_size bytes.  Returns the number of splits. */
+int fourmc_plan_splits(const int64_t *offsets, int n, int64_t file_size, int64_t split_size,
+                       int64_t *starts, int64_t *lengths, int cap);
+
+/* FourMcLineRecordReader over one split (FourMcLineRecordReader.java:116-163): every record (line, with its
+ * terminator) the reader returns for [start, start + length), concatenated into out.  The split's blocks
+ * (and the block(s) that finish its last line) are decoded on the device.  Returns the byte count. */
+long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t file_size, int64_t start,
+                                       int64_t length, void *out, size_t out_capacity);
+
 /* ---- synthetic inputs, bit-identical on host and device ---------------------- */
 
 /* kind 0 = log-text.  Fills pages [first_page, first_page + n_pages) of 4096 bytes each. */

@@ -21,4 +21,6 @@ assert ctx.decompress_4mz(z) == data
 for n in (0, 1, 13, 4096, 65537, 300000):
     z2 = ctx.compress_4mz(data[:n]); assert ctx.decompress_4mz(z2) == data[:n]
 f = ctx.zstd_compress(data[:200000]); r, o = ctx.zstd_decompress(f, 200000); assert o == data[:200000]
+ix = pkg.FourMcBlockIndex(ctx.read_index(s))
+assert b"".join(ctx.read_split_lines(s, a, ln) for a, ln in ix.plan_splits(len(s), 1 << 20)) == data
 print("sanitize workload ok")
