@@ -513,8 +513,7 @@ __global__ void gen_kernel(int kind, uint64_t seed, uint64_t first_page, uint64_
     constexpr int ROW = FMG_PAGE + 16;
     const uint64_t p0 = (uint64_t)blockIdx.x * 32;
     const uint64_t mine = p0 + threadIdx.x;
-    (void)kind;
-    if (mine < n_pages) fmg_logtext_page(seed, first_page + mine, pages + (size_t)threadIdx.x * ROW);
+    if (mine < n_pages) fmg_page(kind, seed, first_page + mine, pages + (size_t)threadIdx.x * ROW);
     __syncwarp();
     for (int r = 0; r < 32 && p0 + r < n_pages; r++) {
         const uint4 *s = (const uint4 *)(pages + (size_t)r * ROW);
@@ -844,7 +843,7 @@ int fourmc_gen_device(fourmc_ctx *ctx, void *stream, int kind, uint64_t seed, ui
                       uint64_t n_pages, void *d_out)
 {
     if (!ctx || !d_out) return FOURMC_E_ARG;
-    if (kind != 0) return fail(ctx, FOURMC_E_UNSUPPORTED, "only kind 0 (log-text) is implemented");
+    if (kind < 0 || kind > 2) return fail(ctx, FOURMC_E_ARG, "kind: 0 log-text, 1 JSON, 2 silesia-like mix");
     if (n_pages == 0) return FOURMC_OK;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
@@ -862,8 +861,8 @@ int fourmc_gen_device(fourmc_ctx *ctx, void *stream, int kind, uint64_t seed, ui
 
 int fourmc_gen_host(int kind, uint64_t seed, uint64_t first_page, uint64_t n_pages, void *out)
 {
-    if (kind != 0 || !out) return FOURMC_E_ARG;
-    for (uint64_t p = 0; p < n_pages; p++) fmg_logtext_page(seed, first_page + p, (uint8_t *)out + p * FMG_PAGE);
+    if (kind < 0 || kind > 2 || !out) return FOURMC_E_ARG;
+    for (uint64_t p = 0; p < n_pages; p++) fmg_page(kind, seed, first_page + p, (uint8_t *)out + p * FMG_PAGE);
     return FOURMC_OK;
 }
 

@@ -29,7 +29,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 BLOCK = 4 * 1024 * 1024
 GIB = 1 << 30
-SEED = 0x4D43
+SEED = 0x4D43                  # log-text (configs[1]); the 4mz runs use the JSON generator, seed 0x4D5A (configs[2])
+SEED_JSON = 0x4D5A
 METRIC = "4mc_fast_lz4_compress_plus_decompress_uncompressed_GBps"
 METRIC_4MZ = "4mz_fast_zstd_compress_plus_decompress_uncompressed_GBps"
 
@@ -107,13 +108,14 @@ class CpuReference:
     def make_input(self, nbytes):
         pkg = importlib.import_module("4mc_b200")
         gen = pkg.lib().fourmc_gen_host
+        kind, seed = (1, SEED_JSON) if self.codec == "4mz" else (0, SEED)
         buf = (C.c_char * nbytes)()
         base = C.addressof(buf)
         pages = nbytes // 4096
         per = max(1, pages // (self.cores * 4))
 
         def work(p0):
-            gen(0, SEED, p0, min(per, pages - p0), base + p0 * 4096)
+            gen(kind, seed, p0, min(per, pages - p0), base + p0 * 4096)
         list(self.pool.map(work, range(0, pages, per)))
         return buf
 
@@ -165,7 +167,7 @@ def run_cpu(gib, steps, warmup, codec="4mc"):
     total = nbytes * steps
     return {
         "value": total / (tc + td) / 1e9, "unit": "GB/s", "cores": ref.cores, "kind": ref.kind,
-        "sample": f"{nbytes / GIB:.2f} GiB log-text per step x {steps} steps, {ref.cores} threads, in memory "
+        "sample": f"{nbytes / GIB:.2f} GiB {'JSON' if codec == '4mz' else 'log-text'} per step x {steps} steps, {ref.cores} threads, in memory "
                   + ("(ZSTD_compress level 1+XXH32 / XXH32+ZSTD_decompress per 4 MiB block)" if codec == "4mz" else
                      "(LZ4_compress_default+XXH32 / XXH32+LZ4_decompress_safe per 4 MiB block)"),
         "compress_GBps": total / tc / 1e9, "decompress_GBps": total / td / 1e9, "ratio": nbytes / csum,
@@ -182,7 +184,8 @@ def main_reference(args):
         "impl": "reference", "metric": METRIC_4MZ if args.codec == "4mz" else METRIC, "value": cpu["value"], "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": ("4mz Fast (ZSTD level 1)" if args.codec == "4mz" else "4mc Fast (LZ4)") + " compress+decompress, synthetic log-text, 4 MiB blocks",
+        "config": {"workload": ("4mz Fast (ZSTD level 1) compress+decompress, synthetic JSON" if args.codec == "4mz" else
+                                "4mc Fast (LZ4) compress+decompress, synthetic log-text") + ", 4 MiB blocks",
                    "bytes_per_step": int(args.cpu_gib * GIB), "l2": "inputs larger than any cache"},
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "detail": {k: cpu[k] for k in ("compress_GBps", "decompress_GBps", "ratio")},
@@ -285,7 +288,8 @@ def main_ours(args):
     all_lens = torch.zeros(nb * world, dtype=torch.int32, device="cuda")
     tail = torch.zeros(12 + 20 + 4 * nb * world + 64, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
-    ctx.gen_device(src.data_ptr(), total // 4096, seed=SEED, first_page=rank * (total // 4096), stream=st)
+    ctx.gen_device(src.data_ptr(), total // 4096, seed=SEED_JSON if zst else SEED, first_page=rank * (total // 4096),
+                   kind=1 if zst else 0, stream=st)
     torch.cuda.synchronize()
 
     csizes = []
@@ -425,7 +429,7 @@ def main_ours(args):
             "metric": METRIC_4MZ if zst else METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": ("configs[2]: 4mz Fast (ZSTD) compress+decompress on the 64 GiB synthetic log-text input of configs[1], 4 MiB blocks"
+            "config": {"workload": ("configs[2]: 4mz Fast (ZSTD) compress+decompress 64 GiB synthetic JSON, 4 MiB blocks"
                                     if zst else "configs[1]: 4mc Fast (LZ4) compress+decompress 64 GiB synthetic log-text, 4 MiB blocks"),
                        "resident_input_gib_per_gpu": total / GIB, "batch_gib_per_step_per_gpu": batch / GIB,
                        "blocks_per_step_per_gpu": nb, "parallelism": f"block-sharded x{world}",

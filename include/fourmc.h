@@ -222,7 +222,9 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
 
 /* ---- synthetic inputs, bit-identical on host and device ---------------------- */
 
-/* kind 0 = log-text.  Fills pages [first_page, first_page + n_pages) of 4096 bytes each. */
+/* kind 0 = log-text (configs[0], [1]), 1 = JSON lines (configs[2]), 2 = silesia-like mix of block types
+ * incl. incompressible blocks (configs[3]).  Fills pages [first_page, first_page + n_pages) of 4096
+ * bytes each; a page is a pure function of (kind, seed, page index). */
 int fourmc_gen_device(fourmc_ctx *ctx, void *stream, int kind, uint64_t seed,
                       uint64_t first_page, uint64_t n_pages, void *d_out);
 int fourmc_gen_host(int kind, uint64_t seed, uint64_t first_page, uint64_t n_pages, void *out);

@@ -277,3 +277,32 @@ def test_levels_2_to_4_chain_parse(ctx, ora, pkg, ref_cli, tmp_path):
         assert ora.lz4_decompress(c, len(blk)) == (len(blk), blk)
         f = ctx.zstd_compress(blk, level)
         assert ctx.zstd_decompress(f, len(blk)) == (len(blk), blk)
+
+
+def test_generators_host_equals_device_and_round_trip(ctx, ora, pkg, ref_cli, tmp_path):
+    """The JSON (configs[2]) and silesia-like mix (configs[3]) inputs: the device generator is bit-identical to
+    the host one, and both containers restore them -- the mix holds incompressible blocks (stored path)."""
+    import torch
+    for kind, seed, pages in ((1, 0x4D5A, 3 * 1024 + 7), (2, 0x5148, 9 * 1024)):
+        n = pages * 4096
+        host = C.create_string_buffer(n)
+        assert pkg.lib().fourmc_gen_host(kind, seed, 5, pages, host) == 0
+        dev = torch.empty(n, dtype=torch.uint8, device="cuda")
+        ctx.gen_device(dev.data_ptr(), pages, seed=seed, first_page=5, kind=kind)
+        ctx.sync()
+        data = host.raw
+        assert bytes(dev.cpu().numpy()) == data, kind
+        s = ctx.compress_4mc(data)
+        assert ora.decompress_4mc(s, n) == (n, data) and ctx.decompress_4mc(s) == data
+        z = ctx.compress_4mz(data)
+        assert ctx.decompress_4mz(z) == data
+        src, out = tmp_path / "g.4mz", tmp_path / "g.out"
+        src.write_bytes(z)
+        subprocess.run([ref_cli, "-f", "-q", "-q", "-z", "-d", str(src), str(out)], check=True)
+        assert out.read_bytes() == data
+        if kind == 1:
+            assert n / len(z) > 2.5 and n / len(s) > 1.9           # reference: ZSTD 1 3.35, LZ4 2.12 on this input
+        else:
+            stored = [int.from_bytes(s[o + 4:o + 8], "big") == int.from_bytes(s[o:o + 4], "big") for o in ctx.read_index(s)]
+            assert any(stored) and not all(stored)
+    assert pkg.lib().fourmc_gen_host(3, 1, 0, 1, C.create_string_buffer(4096)) != 0
