@@ -59,7 +59,7 @@ struct fourmc_ctx {
     DevBuf stage_in[FM_PIPE_MAX], stage_out[FM_PIPE_MAX];    // device staging for the host-pointer entry points
     void *pinned = nullptr;              // small pinned scratch for scalars
     size_t pinned_cap = 0;
-    bool region_attr_set = false;
+    bool region_attr_set = false, d1_attr_set = false, zd_attr_set = false, gen_attr_set = false;   // per context = per device
     DevBuf ztables;                      // fmz::Tables (constant decode tables), uploaded once
     // optional per-kernel timing (fourmc_timing_enable): CUDA event pairs around every launch
     bool timing = false;
@@ -238,9 +238,14 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
         CK(cudaMemsetAsync(ws.misc.p, 0, 64, st));
         return FOURMC_OK;
     }
-    const uint32_t nreg = nb * ENC_REGIONS_PER_BLOCK;
+    // geometry: 64 regions of 64 KiB (Fast parse) or 128 regions of 32 KiB behind 32 KiB of look-back (chain parse)
+    const int depth = level_chain_depth(level);
+    const uint32_t region_bytes = depth > 0 ? ENC_CHAIN_REGION : ENC_REGION;
+    const uint32_t rpb = FOURMC_BLOCKSIZE / region_bytes;
+    const uint32_t slot_bytes = depth > 0 ? ENC_CHAIN_SLOT : ENC_SLOT;
+    const uint32_t nreg = nb * rpb;
     int r;
-    if ((r = ensure(ctx, ws.scratch, (size_t)nreg * ENC_SLOT))) return r;
+    if ((r = ensure(ctx, ws.scratch, (size_t)nreg * slot_bytes))) return r;
     if ((r = ensure(ctx, ws.meta, (size_t)nreg * sizeof(RegionMeta)))) return r;
     if ((r = ensure(ctx, ws.plan, (size_t)nb * sizeof(BlockPlan)))) return r;
     if ((r = ensure(ctx, ws.lens, (size_t)nb * 4))) return r;
@@ -270,12 +275,13 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     }
     uint32_t *lens = d_block_lens_out ? d_block_lens_out : (uint32_t *)ws.lens.p;
     KL("lz4_block_size_kernel", st, lz4_block_size_kernel<<<(nb + 127) / 128, 128, 0, st>>>((const RegionMeta *)ws.meta.p, nb, n,
-                                                           (BlockPlan *)ws.plan.p, lens, raw_limit));
+                                                           (BlockPlan *)ws.plan.p, lens, raw_limit, rpb));
     KL("scan_lens_kernel", st, scan_lens_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, base, (uint64_t *)ws.off.p,
                                                  (uint64_t *)((uint8_t *)ws.misc.p + 8)));
     KL("lz4_block_write_kernel", st, lz4_block_write_kernel<<<nb, ENC_WRITE_THREADS, 0, st>>>(d_in, (const uint8_t *)ws.scratch.p,
                                                              (const RegionMeta *)ws.meta.p, (const BlockPlan *)ws.plan.p,
-                                                             (const uint64_t *)ws.off.p, d_out_base, raw_limit >= 0 ? 1 : 0));
+                                                             (const uint64_t *)ws.off.p, d_out_base, raw_limit >= 0 ? 1 : 0,
+                                                             rpb, region_bytes, slot_bytes));
     return FOURMC_OK;
 }
 
@@ -306,10 +312,13 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
     if ((r = ensure(ctx, ws.misc, 64))) return r;
     if (nb == 0) { CK(cudaMemsetAsync(ws.misc.p, 0, 64, st)); return FOURMC_OK; }
     if ((r = ensure_ztables(ctx))) return r;
+    const int depth = level_chain_depth(level);
+    const uint32_t region_bytes = depth > 0 ? ENC_CHAIN_REGION : ENC_REGION;      // = bytes per zstd block
+    const uint32_t rpb = FOURMC_BLOCKSIZE / region_bytes;
     const uint32_t G = std::min<uint32_t>(nb, (uint32_t)zgroup_blocks());
-    const uint32_t greg = G * ENC_REGIONS_PER_BLOCK;
-    if ((r = ensure(ctx, ws.scratch, (size_t)greg * fmz::ZE_IN_SLOT))) return r;
-    if ((r = ensure(ctx, ws.zout, (size_t)greg * fmz::ZE_OUT_SLOT))) return r;
+    const uint32_t greg = G * rpb;
+    if ((r = ensure(ctx, ws.scratch, (size_t)greg * fmz::ze_in_slot(region_bytes)))) return r;
+    if ((r = ensure(ctx, ws.zout, (size_t)greg * fmz::ze_out_slot(region_bytes)))) return r;
     if ((r = ensure(ctx, ws.zrout, (size_t)greg * sizeof(fmz::ZRegionOut)))) return r;
     if ((r = ensure(ctx, ws.meta, (size_t)greg * sizeof(RegionMeta)))) return r;
     if ((r = ensure(ctx, ws.plan, (size_t)nb * sizeof(BlockPlan)))) return r;
@@ -329,15 +338,16 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
         const uint32_t gb = std::min<uint32_t>(G, nb - g0);
         const size_t goff = (size_t)g0 * FOURMC_BLOCKSIZE;
         const size_t gn = std::min<size_t>(n - goff, (size_t)gb * FOURMC_BLOCKSIZE);
-        const uint32_t nreg = gb * ENC_REGIONS_PER_BLOCK;
+        const uint32_t nreg = gb * rpb;
         if (g0) CK(cudaMemsetAsync(misc, 0, 4, st));
         EncParams P;
         P.in = d_in + goff; P.n = gn; P.n_regions = nreg;
         P.scratch = (uint8_t *)ws.scratch.p; P.meta = (RegionMeta *)ws.meta.p;
         P.work_counter = (uint32_t *)misc;
         P.min_match = level_min_match(level);
-        P.slot_bytes = fmz::ZE_IN_SLOT;
-        P.depth = level_chain_depth(level); P.lazy = P.depth > 0;
+        P.slot_bytes = fmz::ze_in_slot(region_bytes);
+        P.depth = depth; P.lazy = depth > 0;
+        P.region_bytes = region_bytes; P.regions_per_block = rpb;
         if (P.depth > 0) {
             const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
             KL("lz4_region_chain_kernel", st, lz4_region_kernel<true, true><<<grid, ENC_THREADS, ENC_SMEM_CHAIN, st>>>(P));
@@ -349,14 +359,15 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
         Z.meta = (const RegionMeta *)ws.meta.p; Z.scratch_in = (const uint8_t *)ws.scratch.p;
         Z.scratch_out = (uint8_t *)ws.zout.p; Z.rout = (fmz::ZRegionOut *)ws.zrout.p;
         Z.tables = (const fmz::Tables *)ctx->ztables.p; Z.n = gn; Z.n_regions = nreg;
+        Z.region_bytes = region_bytes; Z.regions_per_block = rpb;
         KL("zstd_entropy_kernel", st, zstd_entropy_kernel<<<nreg, fmz::ZE_THREADS, 0, st>>>(Z));
         KL("zstd_block_size_kernel", st, zstd_block_size_kernel<<<(gb + 127) / 128, 128, 0, st>>>(
-            (const fmz::ZRegionOut *)ws.zrout.p, gb, gn, (BlockPlan *)ws.plan.p + g0, lens + g0, raw_limit));
+            (const fmz::ZRegionOut *)ws.zrout.p, gb, gn, (BlockPlan *)ws.plan.p + g0, lens + g0, raw_limit, region_bytes, rpb));
         KL("scan_lens_carry_kernel", st, scan_lens_carry_kernel<<<1, SCAN_THREADS, 0, st>>>(
             lens + g0, gb, (uint64_t *)(misc + 24), (uint64_t *)ws.off.p + g0, (uint64_t *)(misc + 8)));
         KL("zstd_block_write_kernel", st, zstd_block_write_kernel<<<gb, ENC_WRITE_THREADS, 0, st>>>(
             d_in + goff, (const uint8_t *)ws.zout.p, (const fmz::ZRegionOut *)ws.zrout.p, (const BlockPlan *)ws.plan.p + g0,
-            (const uint64_t *)ws.off.p + g0, d_out_base, raw_limit >= 0 ? 1 : 0));
+            (const uint64_t *)ws.off.p + g0, d_out_base, raw_limit >= 0 ? 1 : 0, region_bytes, rpb));
     }
     return FOURMC_OK;
 }
@@ -403,18 +414,16 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
                 desc, (const uint32_t *)ws.xxh.p, nb, status));
             CK(cudaEventRecord(ws.join, ws.side));
         }
-        static bool d1_attr = false;
-        if (!d1_attr) {
+        if (!ctx->d1_attr_set) {
             CK(cudaFuncSetAttribute(lz4_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D1_SMEM));
-            d1_attr = true;
+            ctx->d1_attr_set = true;
         }
         if (codec == CODEC_ZSTD) {
             if ((r = ensure_ztables(ctx))) return r;
             if ((r = ensure(ctx, ws.zwork, (size_t)nb * sizeof(fmz::Work)))) return r;
-            static bool zd_attr = false;
-            if (!zd_attr) {
+            if (!ctx->zd_attr_set) {
                 CK(cudaFuncSetAttribute(zstd_frames_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZD_SMEM));
-                zd_attr = true;
+                ctx->zd_attr_set = true;
             }
             // FOURMC_ZD_MODE = lane (default) | warp | serial: which fast path runs before the exact serial decoder
             static int zd_mode = -1;
@@ -848,8 +857,7 @@ int fourmc_gen_device(fourmc_ctx *ctx, void *stream, int kind, uint64_t seed, ui
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
     const size_t smem = 32 * (FMG_PAGE + 16);
-    static bool attr = false;
-    if (!attr) { CK(cudaFuncSetAttribute(gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    if (!ctx->gen_attr_set) { CK(cudaFuncSetAttribute(gen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ctx->gen_attr_set = true; }
     const uint64_t max_grid = 1u << 30;
     for (uint64_t p0 = 0; p0 < n_pages; p0 += max_grid * 32) {
         const uint64_t cnt = std::min<uint64_t>(n_pages - p0, max_grid * 32);
@@ -946,7 +954,7 @@ long long fourmc_zstd_compress(fourmc_ctx *ctx, int level, const void *src, size
         fmz::ze_write_block_header((uint8_t *)dst + fmz::ZE_FRAME_HDR, true, 0, 0);
         return fmz::ZE_FRAME_HDR + 3;
     }
-    const size_t bound = src_size + 3 * ENC_REGIONS_PER_BLOCK + fmz::ZE_FRAME_HDR + 64;
+    const size_t bound = src_size + 3 * ENC_MAX_REGIONS_PER_BLOCK + fmz::ZE_FRAME_HDR + 64;
     if ((r = ensure(ctx, ctx->stage_in[0], src_size + 64))) return r;
     if ((r = ensure(ctx, ctx->stage_out[0], bound + 64))) return r;
     if ((r = pinned_scratch(ctx, 4096))) return r;

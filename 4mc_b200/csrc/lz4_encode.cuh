@@ -46,6 +46,15 @@ constexpr int ENC_STAGE = 48 * 1024;             // output staging: the (dead) h
 constexpr size_t ENC_SMEM = ENC_REGION + ENC_PAD + ENC_STAGE;
 // chain parse (levels 2..4): u16 prev[65536] (previous position with the same hash) + u16 head[1 << 14]
 constexpr int ENC_STAGE_CHAIN = 2 * ENC_REGION + (2 << 14);
+// Chain parse geometry: the 64 KiB shared-memory window holds 32 KiB of LOOK-BACK (the block's previous
+// bytes, searchable but not parsed) + a 32 KiB region of new bytes, so every position sees at least 32 KiB
+// of history (log text, depth 16: ratio 2.29 without the look-back, 2.49 with it).  128 regions per block.
+constexpr int ENC_CHAIN_REGION = 32768;
+constexpr int ENC_CHAIN_LOOKBACK = ENC_REGION - ENC_CHAIN_REGION;
+constexpr int ENC_CHAIN_SLICE = 68;              // 512 slices of 17 words cover the region
+constexpr int ENC_CHAIN_SLOT = ENC_CHAIN_REGION + 512;
+constexpr int ENC_MAX_REGIONS_PER_BLOCK = FOURMC_BLOCKSIZE / ENC_CHAIN_REGION;   // 128
+static_assert(ENC_THREADS * ENC_CHAIN_SLICE >= ENC_CHAIN_REGION, "chain slices must cover the region");
 constexpr size_t ENC_SMEM_CHAIN = ENC_REGION + ENC_PAD + ENC_STAGE_CHAIN;
 static_assert((sizeof(uint16_t) << ENC_HASH_BITS) <= ENC_STAGE, "the hash table lives inside the staging area");
 
@@ -69,6 +78,8 @@ struct EncParams {
     uint32_t slot_bytes;     // scratch bytes per region (ENC_SLOT; fmz::ZE_IN_SLOT for sequence output)
     int depth;               // chain parse: candidates tried per search (levels 2..4); unused by the Fast parse
     int lazy;                // chain parse: one-step lazy evaluation
+    uint32_t region_bytes;   // new bytes per region: ENC_REGION (Fast) or ENC_CHAIN_REGION (chain)
+    uint32_t regions_per_block;
 };
 
 __device__ __forceinline__ uint32_t enc_hash(uint32_t v) { return (v * 2654435761u) >> (32 - ENC_HASH_BITS); }
@@ -159,16 +170,20 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
         if (rg >= P.n_regions) break;
 
         // ---- locate the region
-        const uint32_t blk = rg / ENC_REGIONS_PER_BLOCK, rib = rg % ENC_REGIONS_PER_BLOCK;
+        const uint32_t blk = rg / P.regions_per_block, rib = rg % P.regions_per_block;
         const uint64_t blk_off = (uint64_t)blk * FOURMC_BLOCKSIZE;
         const uint32_t blk_len = (uint32_t)min((uint64_t)FOURMC_BLOCKSIZE, P.n - blk_off);
-        const uint32_t r_off = rib * ENC_REGION;                   // within the block
-        if (r_off >= blk_len) {                                    // region beyond a short last block
+        const uint32_t r_new = rib * P.region_bytes;               // first new byte, within the block
+        if (r_new >= blk_len) {                                    // region beyond a short last block
             if (tid == 0) P.meta[rg] = RegionMeta{0, 0, 0, 0};
             __syncthreads();
             continue;
         }
-        const int rlen = (int)min((uint32_t)ENC_REGION, blk_len - r_off);
+        // the window starts `lb` bytes earlier (chain parse: look-back into the block's previous bytes);
+        // positions below are relative to the window, new bytes are [lb, rlen)
+        const int lb = CHAIN ? (int)min((uint32_t)ENC_CHAIN_LOOKBACK, r_new) : 0;
+        const uint32_t r_off = r_new - (uint32_t)lb;
+        const int rlen = lb + (int)min(P.region_bytes, blk_len - r_new);
         const uint8_t *gsrc = P.in + blk_off + r_off;
         // LZ4 end-of-block rules, relative to the region (native/lz4/lz4.c:243-247): the last
         // match starts at least 12 bytes before the block end and ends at least 5 before it.
@@ -244,9 +259,9 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
         uint32_t rec[ENC_MAXREC];
         int nrec = 0;
         int l_st = 0, l_len = 0, l_off = 0;                        // last sequence (l_len == 0: none)
-        const int ss = tid * ENC_SLICE;
+        const int ss = CHAIN ? lb + tid * ENC_CHAIN_SLICE : tid * ENC_SLICE;
         if (CHAIN && ss < rlen) {
-            const int se = min(ss + ENC_SLICE, rlen);
+            const int se = min(ss + ENC_CHAIN_SLICE, rlen);
             int p = ss, anchor = ss;
             int have_p = -1, have_len = 0, have_off = 0;           // a search result carried over by the lazy step
             auto search = [&](int q, int &bo) -> int {
@@ -361,7 +376,9 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
         }
         // ---- stitch 2: where does my first literal run start; encoded size of my sequences
         int total_anchor;
-        const int anchor0 = cta_excl_scan<true>(surv_end, s_scan, &total_anchor);
+        int anchor0 = cta_excl_scan<true>(surv_end, s_scan, &total_anchor);
+        anchor0 = max(anchor0, lb);                                 // the first literal run starts at the first NEW byte
+        total_anchor = max(total_anchor, lb);
         int bytes = 0;
         {
             int a = anchor0;
@@ -395,7 +412,7 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
             int long_n = 0, long_src = 0;
             uint8_t *long_dst = nullptr;
             {
-                int a = anchor0, lp = anchor0 - matched_before, idx = seq_before;
+                int a = anchor0, lp = anchor0 - lb - matched_before, idx = seq_before;
                 for (int k = 0; k <= nrec; k++) {
                     int st, len, off;
                     if (k < nrec) {
@@ -420,10 +437,10 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
                 for (int i = lane; i < n; i += 32) dp[i] = data[sp + i];
             }
             {   // literals after the region's last match
-                uint8_t *dp = zlit + (total_anchor - total_matched);
+                uint8_t *dp = zlit + (total_anchor - lb - total_matched);
                 for (int i = total_anchor + tid; i < rlen; i += ENC_THREADS) dp[i - total_anchor] = data[i];
             }
-            total_bytes = rlen - total_matched;
+            total_bytes = rlen - lb - total_matched;
         } else {
         // ---- emit into the staging area (the hash table is dead now), flushed below with 128-bit
         // stores; sequences beyond its capacity (poorly compressible regions) go straight to HBM.
@@ -502,15 +519,15 @@ struct BlockPlan {              // produced by E2, consumed by the index scan an
 // raw_limit >= 0: bare LZ4 block for the per-block API; "stored" then means "does not fit in
 // raw_limit bytes" (LZ4_compress_default returns 0, native/lz4/lz4.c:1290-1300).
 __global__ void lz4_block_size_kernel(const RegionMeta *meta, uint32_t n_blocks, uint64_t n,
-                                      BlockPlan *plan, uint32_t *block_lens, int64_t raw_limit)
+                                      BlockPlan *plan, uint32_t *block_lens, int64_t raw_limit, uint32_t regions_per_block)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
     const uint64_t blk_off = (uint64_t)b * FOURMC_BLOCKSIZE;
     const uint32_t u = (uint32_t)min((uint64_t)FOURMC_BLOCKSIZE, n - blk_off);
-    const RegionMeta *m = meta + (size_t)b * ENC_REGIONS_PER_BLOCK;
+    const RegionMeta *m = meta + (size_t)b * regions_per_block;
     uint32_t carry = 0, c = 0;
-    for (int r = 0; r < ENC_REGIONS_PER_BLOCK; r++) {
+    for (uint32_t r = 0; r < regions_per_block; r++) {
         const RegionMeta x = m[r];
         if (x.nseq == 0) { carry += x.tail_lits; continue; }
         const int old_hdr = 1 + enc_ext_bytes((int)x.lead);
@@ -558,11 +575,12 @@ constexpr int ENC_WRITE_THREADS = 256;
 // out_base + block_off[b] is where block b's 12-byte header goes.
 __global__ void __launch_bounds__(ENC_WRITE_THREADS)
 lz4_block_write_kernel(const uint8_t *in, const uint8_t *scratch, const RegionMeta *meta,
-                       const BlockPlan *plan, const uint64_t *block_off, uint8_t *out_base, int raw_mode)
+                       const BlockPlan *plan, const uint64_t *block_off, uint8_t *out_base, int raw_mode,
+                       uint32_t regions_per_block, uint32_t region_bytes, uint32_t slot_bytes)
 {
     __shared__ __align__(16) uint32_t s_stage[XXH_WARP_SMEM_WORDS];
-    __shared__ uint32_t s_dst[ENC_REGIONS_PER_BLOCK + 1];   // payload offset of each region's piece
-    __shared__ uint32_t s_carry[ENC_REGIONS_PER_BLOCK + 1]; // literals carried INTO the region
+    __shared__ uint32_t s_dst[ENC_MAX_REGIONS_PER_BLOCK + 1];   // payload offset of each region's piece
+    __shared__ uint32_t s_carry[ENC_MAX_REGIONS_PER_BLOCK + 1]; // literals carried INTO the region
 
     const uint32_t b = blockIdx.x;
     const BlockPlan p = plan[b];
@@ -570,7 +588,8 @@ lz4_block_write_kernel(const uint8_t *in, const uint8_t *scratch, const RegionMe
     const uint8_t *src = in + blk_off;
     uint8_t *rec = out_base + block_off[b];
     uint8_t *pay = rec + 12;
-    const RegionMeta *m = meta + (size_t)b * ENC_REGIONS_PER_BLOCK;
+    const RegionMeta *m = meta + (size_t)b * regions_per_block;
+    const int RPB = (int)regions_per_block;
 
     if (p.stored) {
         if (raw_mode) return;               // nothing to write: the caller reports 0
@@ -578,7 +597,7 @@ lz4_block_write_kernel(const uint8_t *in, const uint8_t *scratch, const RegionMe
     } else {
         if (threadIdx.x == 0) {
             uint32_t carry = 0, c = 0;
-            for (int r = 0; r < ENC_REGIONS_PER_BLOCK; r++) {
+            for (int r = 0; r < RPB; r++) {
                 const RegionMeta x = m[r];
                 s_dst[r] = c; s_carry[r] = carry;
                 if (x.nseq == 0) { carry += x.tail_lits; continue; }
@@ -587,14 +606,14 @@ lz4_block_write_kernel(const uint8_t *in, const uint8_t *scratch, const RegionMe
                 c += (uint32_t)new_hdr + carry + (x.body_bytes - (uint32_t)old_hdr);
                 carry = x.tail_lits;
             }
-            s_dst[ENC_REGIONS_PER_BLOCK] = c; s_carry[ENC_REGIONS_PER_BLOCK] = carry;
+            s_dst[RPB] = c; s_carry[RPB] = carry;
         }
         __syncthreads();
-        for (int r = 0; r < ENC_REGIONS_PER_BLOCK; r++) {
+        for (int r = 0; r < RPB; r++) {
             const RegionMeta x = m[r];
             if (x.nseq == 0) continue;
             const uint32_t carry = s_carry[r];
-            const uint8_t *slot = scratch + ((size_t)b * ENC_REGIONS_PER_BLOCK + r) * ENC_SLOT;
+            const uint8_t *slot = scratch + ((size_t)b * RPB + r) * slot_bytes;
             uint8_t *o = pay + s_dst[r];
             const int old_hdr = 1 + enc_ext_bytes((int)x.lead);
             const int lit = (int)(x.lead + carry);
@@ -605,12 +624,12 @@ lz4_block_write_kernel(const uint8_t *in, const uint8_t *scratch, const RegionMe
                 if (lit >= 15) emit_len(q, lit - 15);
             }
             // carried literals are input bytes just before the region
-            cta_copy(o + new_hdr, src + (size_t)r * ENC_REGION - carry, carry);
+            cta_copy(o + new_hdr, src + (size_t)r * region_bytes - carry, carry);
             cta_copy(o + new_hdr + carry, slot + old_hdr, x.body_bytes - (uint32_t)old_hdr);
         }
         {   // closing sequence: literals only
-            const uint32_t carry = s_carry[ENC_REGIONS_PER_BLOCK];
-            uint8_t *o = pay + s_dst[ENC_REGIONS_PER_BLOCK];
+            const uint32_t carry = s_carry[RPB];
+            uint8_t *o = pay + s_dst[RPB];
             const int hdr = 1 + enc_ext_bytes((int)carry);
             if (threadIdx.x == 0) {
                 uint8_t *q = o;

@@ -53,44 +53,47 @@ struct ZEncParams {
     const fmz::Tables *tables;
     uint64_t n;                    // input bytes of the batch
     uint32_t n_regions;
+    uint32_t region_bytes, regions_per_block;      // 65536 x 64 (Fast parse) or 32768 x 128 (chain parse)
 };
 
 __global__ void __launch_bounds__(fmz::ZE_THREADS) zstd_entropy_kernel(ZEncParams P)
 {
     __shared__ fmz::ZShared sh;
     const uint32_t rg = blockIdx.x;
-    const uint32_t blk = rg / ENC_REGIONS_PER_BLOCK, rib = rg % ENC_REGIONS_PER_BLOCK;
+    const uint32_t blk = rg / P.regions_per_block, rib = rg % P.regions_per_block;
     const uint64_t blk_off = (uint64_t)blk * FOURMC_BLOCKSIZE;
     const uint32_t blk_len = (uint32_t)min((uint64_t)FOURMC_BLOCKSIZE, P.n - blk_off);
-    const uint32_t r_off = rib * ENC_REGION;
+    const uint32_t r_off = rib * P.region_bytes;
     if (r_off >= blk_len) return;                                  // region beyond a short last block
     const RegionMeta m = P.meta[rg];
     fmz::ZRegionIn in;
-    const uint8_t *slot_in = P.scratch_in + (size_t)rg * fmz::ZE_IN_SLOT;
+    const uint8_t *slot_in = P.scratch_in + (size_t)rg * fmz::ze_in_slot(P.region_bytes);
     const uint32_t stride = fmz::ze_seq_stride(m.nseq);
     in.ll = (const uint16_t *)slot_in; in.ml = in.ll + stride; in.off = in.ml + stride;
     in.lits = (const uint8_t *)(in.off + stride);
     in.nseq = m.nseq; in.nlit = m.body_bytes;
-    in.rlen = min((uint32_t)ENC_REGION, blk_len - r_off);
+    in.rlen = min(P.region_bytes, blk_len - r_off);
+    in.cap = P.region_bytes;
     CtaExec ex;
-    fmz::zenc_region(ex, sh, in, (uint32_t *)(P.scratch_out + (size_t)rg * fmz::ZE_OUT_SLOT), &P.rout[rg], *P.tables);
+    fmz::zenc_region(ex, sh, in, (uint32_t *)(P.scratch_out + (size_t)rg * fmz::ze_out_slot(P.region_bytes)), &P.rout[rg], *P.tables);
 }
 
 // raw_limit < 0: container mode, a block is stored when its frame reaches its raw size
 // (native/4mc.c:469-485: ZSTD_compress is offered u-1 bytes).  raw_limit >= 0: bare frame for the
 // per-block API; "stored" then means "does not fit in raw_limit bytes".
 __global__ void zstd_block_size_kernel(const fmz::ZRegionOut *rout, uint32_t n_blocks, uint64_t n,
-                                       BlockPlan *plan, uint32_t *block_lens, int64_t raw_limit)
+                                       BlockPlan *plan, uint32_t *block_lens, int64_t raw_limit,
+                                       uint32_t region_bytes, uint32_t regions_per_block)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
     const uint64_t blk_off = (uint64_t)b * FOURMC_BLOCKSIZE;
     const uint32_t u = (uint32_t)min((uint64_t)FOURMC_BLOCKSIZE, n - blk_off);
-    const fmz::ZRegionOut *r = rout + (size_t)b * ENC_REGIONS_PER_BLOCK;
+    const fmz::ZRegionOut *r = rout + (size_t)b * regions_per_block;
     uint32_t c = fmz::ZE_FRAME_HDR;
-    const uint32_t nreg = (u + ENC_REGION - 1) / ENC_REGION;
+    const uint32_t nreg = (u + region_bytes - 1) / region_bytes;
     for (uint32_t k = 0; k < nreg; k++) {
-        const uint32_t rlen = min((uint32_t)ENC_REGION, u - k * ENC_REGION);
+        const uint32_t rlen = min(region_bytes, u - k * region_bytes);
         c += 3u + (r[k].raw ? rlen : r[k].bytes);
     }
     if (nreg == 0) c += 3u;                                         // empty input: one empty raw block
@@ -110,10 +113,11 @@ __global__ void zstd_block_size_kernel(const fmz::ZRegionOut *rout, uint32_t n_b
 
 __global__ void __launch_bounds__(ENC_WRITE_THREADS)
 zstd_block_write_kernel(const uint8_t *in, const uint8_t *scratch_out, const fmz::ZRegionOut *rout,
-                        const BlockPlan *plan, const uint64_t *block_off, uint8_t *out_base, int raw_mode)
+                        const BlockPlan *plan, const uint64_t *block_off, uint8_t *out_base, int raw_mode,
+                        uint32_t region_bytes, uint32_t regions_per_block)
 {
     __shared__ __align__(16) uint32_t s_stage[XXH_WARP_SMEM_WORDS];
-    __shared__ uint32_t s_dst[ENC_REGIONS_PER_BLOCK + 1];
+    __shared__ uint32_t s_dst[ENC_MAX_REGIONS_PER_BLOCK + 1];
 
     const uint32_t b = blockIdx.x;
     const BlockPlan p = plan[b];
@@ -121,8 +125,8 @@ zstd_block_write_kernel(const uint8_t *in, const uint8_t *scratch_out, const fmz
     const uint8_t *src = in + blk_off;
     uint8_t *rec = out_base + block_off[b];
     uint8_t *pay = rec + 12;
-    const fmz::ZRegionOut *r = rout + (size_t)b * ENC_REGIONS_PER_BLOCK;
-    const uint32_t nreg = (p.usize + ENC_REGION - 1) / ENC_REGION;
+    const fmz::ZRegionOut *r = rout + (size_t)b * regions_per_block;
+    const uint32_t nreg = (p.usize + region_bytes - 1) / region_bytes;
 
     if (p.stored) {
         if (raw_mode) return;
@@ -132,7 +136,7 @@ zstd_block_write_kernel(const uint8_t *in, const uint8_t *scratch_out, const fmz
             uint32_t c = fmz::ZE_FRAME_HDR;
             for (uint32_t k = 0; k < nreg; k++) {
                 s_dst[k] = c;
-                const uint32_t rlen = min((uint32_t)ENC_REGION, p.usize - k * ENC_REGION);
+                const uint32_t rlen = min(region_bytes, p.usize - k * region_bytes);
                 c += 3u + (r[k].raw ? rlen : r[k].bytes);
             }
             fmz::ze_write_frame_header(pay, p.usize);
@@ -140,13 +144,13 @@ zstd_block_write_kernel(const uint8_t *in, const uint8_t *scratch_out, const fmz
         }
         __syncthreads();
         for (uint32_t k = 0; k < nreg; k++) {
-            const uint32_t rlen = min((uint32_t)ENC_REGION, p.usize - k * ENC_REGION);
+            const uint32_t rlen = min(region_bytes, p.usize - k * region_bytes);
             const fmz::ZRegionOut x = r[k];
             uint8_t *o = pay + s_dst[k];
             const bool last = k + 1 == nreg;
             if (threadIdx.x == 0) fmz::ze_write_block_header(o, last, x.raw ? 0 : 2, x.raw ? rlen : x.bytes);
-            if (x.raw) cta_copy(o + 3, src + (size_t)k * ENC_REGION, rlen);
-            else cta_copy(o + 3, scratch_out + ((size_t)b * ENC_REGIONS_PER_BLOCK + k) * fmz::ZE_OUT_SLOT, x.bytes);
+            if (x.raw) cta_copy(o + 3, src + (size_t)k * region_bytes, rlen);
+            else cta_copy(o + 3, scratch_out + ((size_t)b * regions_per_block + k) * fmz::ze_out_slot(region_bytes), x.bytes);
         }
     }
     __threadfence_block();

@@ -31,7 +31,7 @@
 
 namespace fmz {
 
-constexpr int ZE_REGION = 65536;               // input bytes per zstd block
+constexpr int ZE_REGION = 65536;               // input bytes per zstd block (32768 under the chain parse of levels 2..4)
 constexpr int ZE_THREADS = 128;                // threads of the entropy CTA
 constexpr int ZE_WARPS = ZE_THREADS / 32;
 #ifndef FOURMC_ZE_TILE
@@ -46,6 +46,8 @@ constexpr int ZE_MIN_FSE_SEQ = 64;             // below: predefined tables
 // n rounded up to 8.  6 n + literals <= 65536 + 2 n <= 98304 (each sequence covers >= 4 bytes).
 constexpr int ZE_IN_SLOT = 98304 + 64;
 constexpr int ZE_OUT_SLOT = ZE_REGION + 64;    // a block body that does not fit is emitted raw
+FZ_HD inline uint32_t ze_in_slot(uint32_t region) { return region + region / 2 + 64; }
+FZ_HD inline uint32_t ze_out_slot(uint32_t region) { return region + 64; }
 
 FZ_HD inline uint32_t ze_seq_stride(uint32_t nseq) { return (nseq + 7u) & ~7u; }
 
@@ -380,6 +382,7 @@ struct ZRegionIn {
     const uint8_t *lits;              // nlit bytes: literals of all sequences, then the tail literals
     uint32_t nseq, nlit;
     uint32_t rlen;                    // region length in input bytes
+    uint32_t cap;                     // capacity of the output slot's body area (the region size: a larger body is useless)
 };
 
 // Offset as coded (zstd_compress_internal.h: offBase).  3 + offset for a real offset; 1 = "the
@@ -436,12 +439,12 @@ template <class Exec>
 FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32_t *slot, ZRegionOut *out, const Tables &T)
 {
     const uint32_t nseq = in.nseq, nlit = in.nlit;
-    const uint32_t cap_bits = (uint32_t)ZE_REGION * 8;          // a body beyond the region size is useless anyway
+    const uint32_t cap_bits = in.cap * 8;                       // a body beyond the region size is useless anyway
 
     // ---- P0: zero the slot and the histograms
     ex.phase([&](int tid) {
         Z16 *z = (Z16 *)slot;
-        for (int i = tid; i < ZE_OUT_SLOT / 16; i += ZE_THREADS) z[i] = Z16{0, 0, 0, 0};
+        for (int i = tid; i < (int)((in.cap + 64) / 16); i += ZE_THREADS) z[i] = Z16{0, 0, 0, 0};
         for (int i = tid; i < 256; i += ZE_THREADS) { sh.hist[i] = 0; sh.nbits[i] = 0; }
         for (int i = tid; i < 3 * 64; i += ZE_THREADS) sh.chist[i / 64][i % 64] = 0;
         if (tid < 36) { sh.ll_base[tid] = T.ll_base[tid]; sh.ll_bits[tid] = T.ll_bits[tid]; }

@@ -200,15 +200,48 @@ def main_reference(args):
 # ------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """SM clock and throttle reasons while the timed region runs (B200_PROFILING.md), sampled every 200 ms
+    through NVML in a thread (an `nvidia-smi -lms 100` child was seen to stall a step by ~50 ms now and then);
+    falls back to the nvidia-smi loop when the NVML binding is missing."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
+        self.rows = []                      # (time, sm_mhz, sm_max_mhz, [reason names])
+        self.p = None
+        self._stop = threading.Event()
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            masks = [(getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                     (getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                     (getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                     (getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        r = get_reasons(h)
+                        self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(mx),
+                                          [n for m, n in masks if r & m]))
+                    except Exception:      # noqa: BLE001 -- a failed sample is just missing
+                        pass
+                    self._stop.wait(0.2)
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:                   # noqa: BLE001 -- no NVML binding: the nvidia-smi loop below
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        self.rows = []
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                       "-lms", "500"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -216,18 +249,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((time.perf_counter(), float(r[0]), float(r[1]),
+                                  [self.NAMES[i] for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")]))
+            except (ValueError, IndexError):
+                pass
 
     def window(self, t0, t1):
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
-        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        sm = [r[1] for r in rows]
+        mx = [r[2] for r in rows]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(rows)}
+                "reasons": sorted({n for r in rows for n in r[3]}), "samples": len(rows)}
 
     def stop(self):
+        self._stop.set()
         if self.p:
             self.p.terminate()
 

@@ -9,7 +9,7 @@
 #include <vector>
 
 namespace {
-constexpr int BLOCK = 4 << 20, REGION = 65536, RPB = BLOCK / REGION, THREADS = 512, SLICE = 132, HB = 14, PAD = 64;
+constexpr int BLOCK = 4 << 20, REGION = 65536, THREADS = 512, SLICE = 132, HB = 14, PAD = 64;
 struct Meta { uint32_t body_bytes, tail_lits, lead, nseq; };
 struct Seq { int st, len, off; };
 inline uint32_t rd4(const uint8_t *d, int p) { uint32_t v; memcpy(&v, d + p, 4); return v; }
@@ -20,10 +20,15 @@ inline uint8_t *emit_len(uint8_t *o, int v) { while (v >= 255) { *o++ = 255; v -
 // depth == 0: the Fast parse (first-occurrence table).  depth > 0: the chain parse of the higher
 // levels -- every position linked to the previous position with the same hash, `depth` candidates
 // per search, optional one-step lazy evaluation.
-void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_off, int min_match, std::vector<uint8_t> &body, Meta &mt,
+// In the chain parse the 64 KiB window is 32 KiB of look-back (earlier bytes of the block: searched, not
+// parsed) + a 32 KiB region of new bytes; positions are relative to the window, new bytes are [lb, rlen).
+constexpr int CHAIN_REGION = 32768, CHAIN_LOOKBACK = REGION - CHAIN_REGION, CHAIN_SLICE = 68;
+void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_new, int min_match, std::vector<uint8_t> &body, Meta &mt,
             int depth = 0, int lazy = 0)
 {
-    const int rlen = (int)std::min<uint32_t>(REGION, blk_len - r_off);
+    const int lb = depth > 0 ? (int)std::min<uint32_t>(CHAIN_LOOKBACK, r_new) : 0;
+    const uint32_t r_off = r_new - (uint32_t)lb;
+    const int rlen = lb + (int)std::min<uint32_t>(depth > 0 ? CHAIN_REGION : REGION, blk_len - r_new);
     std::vector<uint8_t> data(REGION + PAD, 0);
     memcpy(data.data(), blk + r_off, rlen);
     const int mf_limit = std::min(rlen - 1, (int)blk_len - 12 - (int)r_off);
@@ -76,9 +81,9 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_off, int min_match,
         return best;
     };
     for (int t = 0; t < THREADS; t++) {
-        const int ss = t * SLICE;
+        const int ss = depth > 0 ? lb + t * CHAIN_SLICE : t * SLICE;
         if (ss >= rlen) continue;
-        const int se = std::min(ss + SLICE, rlen);
+        const int se = std::min(ss + (depth > 0 ? CHAIN_SLICE : SLICE), rlen);
         int p = ss, anchor = ss;
         if (depth > 0) {
             int have_len = 0, have_off = 0, have_p = -1;          // a search result carried over by the lazy step
@@ -139,7 +144,7 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_off, int min_match,
     }
     // stitch 2 + emit
     body.clear();
-    int anchor = 0; uint32_t nseq = 0; mt.lead = 0;
+    int anchor = lb; uint32_t nseq = 0; mt.lead = 0;
     for (int t = 0; t < THREADS; t++) {
         std::vector<Seq> all = inner[t];
         if (last[t].len) all.push_back(last[t]);
@@ -174,9 +179,10 @@ extern "C" int enc_emul_block_chain(const uint8_t *src, int n, uint8_t *dst, int
 }
 static int emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth, int lazy)
 {
+    const int REG = depth > 0 ? CHAIN_REGION : REGION, RPB = BLOCK / REG;
     std::vector<Meta> meta(RPB, Meta{0, 0, 0, 0});
     std::vector<std::vector<uint8_t>> bodies(RPB);
-    for (int r = 0; r < RPB; r++) if ((uint32_t)r * REGION < (uint32_t)n) region(src, (uint32_t)n, (uint32_t)r * REGION, min_match, bodies[r], meta[r], depth, lazy);
+    for (int r = 0; r < RPB; r++) if ((uint32_t)r * REG < (uint32_t)n) region(src, (uint32_t)n, (uint32_t)r * REG, min_match, bodies[r], meta[r], depth, lazy);
     uint8_t *o = dst; uint32_t carry = 0;
     for (int r = 0; r < RPB; r++) {
         const Meta &x = meta[r];
@@ -184,7 +190,7 @@ static int emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match, in
         const int old_hdr = 1 + ext((int)x.lead), lit = (int)(x.lead + carry);
         *o++ = (uint8_t)((std::min(lit, 15) << 4) | (bodies[r][0] & 15));
         if (lit >= 15) o = emit_len(o, lit - 15);
-        memcpy(o, src + (size_t)r * REGION - carry, carry); o += carry;
+        memcpy(o, src + (size_t)r * REG - carry, carry); o += carry;
         memcpy(o, bodies[r].data() + old_hdr, x.body_bytes - old_hdr); o += x.body_bytes - old_hdr;
         carry = x.tail_lits;
     }

@@ -88,7 +88,7 @@ extern "C" long long zenc_emul_compress(uint8_t *dst, long long cap, const uint8
         std::vector<uint8_t> lits;
         find_sequences(src + o, rlen, min_match & 15, min_match >> 4, ll, ml, off, lits);
         lits.resize(lits.size() + 8);
-        fmz::ZRegionIn in{ll.data(), ml.data(), off.data(), lits.data(), (uint32_t)ll.size(), (uint32_t)(lits.size() - 8), (uint32_t)rlen};
+        fmz::ZRegionIn in{ll.data(), ml.data(), off.data(), lits.data(), (uint32_t)ll.size(), (uint32_t)(lits.size() - 8), (uint32_t)rlen, (uint32_t)fmz::ZE_REGION};
         fmz::ZRegionOut ro{0, 0};
         EmuExec ex;
         memset(sh, 0xA5, sizeof(*sh));                               // nothing may rely on zeroed shared memory

@@ -269,7 +269,7 @@ def test_levels_2_to_4_chain_parse(ctx, ora, pkg, ref_cli, tmp_path):
                     assert out.read_bytes() == data
     for k in (0, 1):
         assert sizes[4][k] < sizes[3][k] < sizes[2][k] < sizes[1][k], sizes
-    assert len(text) / sizes[2][0] > 2.15 and len(text) / sizes[4][0] > 2.25, sizes
+    assert len(text) / sizes[2][0] > 2.3 and len(text) / sizes[4][0] > 2.4, sizes
     # per-block calls: LZ4_compressMC / LZ4_compressHC2 / ZSTD_compress(level) of the JNI natives
     blk = text[:4 * MIB]
     for level in (2, 3, 4):
@@ -306,3 +306,32 @@ def test_generators_host_equals_device_and_round_trip(ctx, ora, pkg, ref_cli, tm
             stored = [int.from_bytes(s[o + 4:o + 8], "big") == int.from_bytes(s[o:o + 4], "big") for o in ctx.read_index(s)]
             assert any(stored) and not all(stored)
     assert pkg.lib().fourmc_gen_host(3, 1, 0, 1, C.create_string_buffer(4096)) != 0
+
+
+def test_distinct_contexts_are_thread_safe(pkg, ora):
+    """include/fourmc.h: a context is single-threaded, distinct contexts are independent (the Java objects
+    call the natives from many task threads at once)."""
+    import threading
+    datas = [gen_logtext(pkg, 6 * MIB + 1000 * i, first_page=100 * i) for i in range(4)]
+    errors = []
+
+    def work(i):
+        try:
+            c = pkg.Context(0)
+            for _ in range(3):
+                s = c.compress_4mc(datas[i])
+                assert c.decompress_4mc(s) == datas[i]
+                z = c.compress_4mz(datas[i], 1 + i % 2)
+                assert c.decompress_4mz(z) == datas[i]
+                blk = datas[i][:300000]
+                assert ora.lz4_decompress(c.lz4_compress(blk), len(blk)) == (len(blk), blk)
+            c.close()
+        except Exception as e:      # noqa: BLE001 -- reported below
+            errors.append((i, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
