@@ -169,6 +169,20 @@ int slice_blocks()
     return v;
 }
 
+// The 4mc host writer is bound by the upload (PCIe): smaller slices shorten the pipeline's fill and
+// drain (B200: 50.3 GB/s at 32 blocks, 47.8 at 128); the reader's kernels want the larger slices.
+int cslice_blocks()
+{
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("FOURMC_CSLICE_BLOCKS");
+        v = e ? atoi(e) : 32;
+        if (v < 1) v = 1;
+        if (v > 4096) v = 4096;
+    }
+    return v;
+}
+
 int zslice_blocks()
 {
     static int v = 0;
@@ -259,13 +273,14 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
         ctx->region_attr_set = true;
     }
     CK(cudaMemsetAsync(ws.misc.p, 0, 64, st));
-    EncParams P;
+    EncParams P = {};
     P.in = d_in; P.n = n; P.n_regions = nreg;
     P.scratch = (uint8_t *)ws.scratch.p; P.meta = (RegionMeta *)ws.meta.p;
     P.work_counter = (uint32_t *)ws.misc.p;
     P.min_match = level_min_match(level);
-    P.slot_bytes = ENC_SLOT;
-    P.depth = level_chain_depth(level); P.lazy = P.depth > 0;
+    P.slot_bytes = slot_bytes;
+    P.depth = depth; P.lazy = depth > 0;
+    P.region_bytes = region_bytes; P.regions_per_block = rpb;
     if (P.depth > 0) {
         const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
         KL("lz4_region_chain_kernel", st, lz4_region_kernel<false, true><<<grid, ENC_THREADS, ENC_SMEM_CHAIN, st>>>(P));
@@ -340,7 +355,7 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
         const size_t gn = std::min<size_t>(n - goff, (size_t)gb * FOURMC_BLOCKSIZE);
         const uint32_t nreg = gb * rpb;
         if (g0) CK(cudaMemsetAsync(misc, 0, 4, st));
-        EncParams P;
+        EncParams P = {};
         P.in = d_in + goff; P.n = gn; P.n_regions = nreg;
         P.scratch = (uint8_t *)ws.scratch.p; P.meta = (RegionMeta *)ws.meta.p;
         P.work_counter = (uint32_t *)misc;
@@ -355,7 +370,7 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
             const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
             KL("lz4_region_kernel", st, lz4_region_kernel<true, false><<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
         }
-        ZEncParams Z;
+        ZEncParams Z = {};
         Z.meta = (const RegionMeta *)ws.meta.p; Z.scratch_in = (const uint8_t *)ws.scratch.p;
         Z.scratch_out = (uint8_t *)ws.zout.p; Z.rout = (fmz::ZRegionOut *)ws.zrout.p;
         Z.tables = (const fmz::Tables *)ctx->ztables.p; Z.n = gn; Z.n_regions = nreg;
@@ -1022,7 +1037,7 @@ static long long compress_host_impl(fourmc_ctx *ctx, int codec, int level, const
     if (out_capacity < fourmc_4mc_bound(n)) return fail(ctx, FOURMC_E_OUTPUT, "output capacity below fourmc_4mc_bound(n)");
     CK(cudaSetDevice(ctx->device));
     const uint32_t nb = blocks_of(n);
-    const size_t sl_blocks = (size_t)slice_blocks();
+    const size_t sl_blocks = codec == CODEC_LZ4 && level <= 1 && !getenv("FOURMC_SLICE_BLOCKS") ? (size_t)cslice_blocks() : (size_t)slice_blocks();
     const size_t sl_bytes = sl_blocks * FOURMC_BLOCKSIZE;
     const size_t nslices = (n + sl_bytes - 1) / sl_bytes;
     int r;
