@@ -145,3 +145,21 @@ def test_jni_shim_through_fake_jvm(ora, pkg):
             assert R.ZSTD_decompress(o2, len(data), dst.raw[:r], r) == len(data) and o2.raw == data
     # the streaming zstd natives resolve but are not built
     assert M.mock_zstd_stream_throws(msg) == 1 and b"InternalError" in msg.value
+
+
+@pytest.mark.gpu
+def test_cli_levels_like_the_reference(ref_cli, pkg, tmp_path):
+    """-1 .. -4 and -z (native/4mccli.c:170-361, native/4mc.c:243-253 / :415-425): every level's output is read
+    by the reference CLI, and the higher levels are smaller."""
+    data = gen_logtext(pkg, 6 * 1024 * 1024 + 77, first_page=31)
+    src = tmp_path / "d.bin"
+    src.write_bytes(data)
+    for z in ([], ["-z"]):
+        sizes = []
+        for lv in ("-1", "-2", "-3", "-4"):
+            out, back = tmp_path / "o.bin", tmp_path / "b.bin"
+            assert subprocess.run([CLI, "-f", "-q"] + z + [lv, str(src), str(out)]).returncode == 0
+            subprocess.run([ref_cli, "-f", "-q", "-q"] + z + ["-d", str(out), str(back)], check=True)
+            assert back.read_bytes() == data
+            sizes.append(out.stat().st_size)
+        assert sizes[3] < sizes[2] < sizes[1] < sizes[0], sizes

@@ -220,6 +220,22 @@ def test_gpu_decodes_live_reference_frames(ctx, pkg, ora, ref):
         assert ctx.decompress_4mz(assemble_4mz(ora, blocks)) == data, lvl
         r, out = ctx.zstd_decompress(blocks[0][2], 4 * MIB)
         assert r == 4 * MIB and out == data[:4 * MIB], lvl
+    # a frame of more than 32 blocks through the per-block call: the tables in force ("repeat" modes, treeless
+    # literals) are carried from one chunk of 32 blocks to the next inside the lane-parallel kernel
+    big = gen_logtext(pkg, 7 * MIB + 99, first_page=4242)
+    for lvl in (1, 3):
+        cb = C.create_string_buffer(len(big))
+        c = ref.ZSTD_compress(cb, len(big), big, len(big), lvl)
+        assert 0 < c < 8 * MIB
+        assert ctx.zstd_decompress(cb.raw[:c], len(big)) == (len(big), big), lvl
+    # more sequences in one block than the fast path holds (two-symbol noise: ~6 bytes per sequence): the
+    # frame is handed to the serial decoder, same bytes
+    rng = random.Random(12)
+    dense = bytes(rng.choice(b"ab") for _ in range(2 * MIB))
+    cb = C.create_string_buffer(len(dense))
+    c = ref.ZSTD_compress(cb, len(dense), dense, len(dense), 1)
+    assert ctx.zstd_decompress(cb.raw[:c], len(dense)) == (len(dense), dense)
+    assert ctx.decompress_4mz(assemble_4mz(ora, [(len(dense), c, cb.raw[:c])])) == dense
 
 
 @pytest.mark.gpu

@@ -1,0 +1,11 @@
+#!/bin/bash
+run() { python bench.py --total-gib 16 --batch-gib 16 --steps 3 --warmup 3 --no-cpu 2>/dev/null | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        j = json.loads(l); e=j['e2e']; print('e2e', round(e['value'],2), 'c', round(e['compress_GBps'],1), 'd', round(e['decompress_GBps'],1))
+"; }
+echo "== default"; run
+echo "== CSLICE=128"; FOURMC_CSLICE_BLOCKS=128 run
+echo "== CSLICE=64"; FOURMC_CSLICE_BLOCKS=64 run
+echo "== default again"; run
