@@ -335,3 +335,60 @@ def test_distinct_contexts_are_thread_safe(pkg, ora):
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+def test_randomized_round_trips_all_levels_both_containers(ctx, ora, pkg):
+    """Seeded sweep over sizes, inputs and levels: whatever the GPU writes, the oracle (4mc) and the reference's
+    ZSTD_decompress (4mz, where oracle/_ref is present) restore it, and so does the GPU reader."""
+    import os
+    rng = random.Random(20261017)
+    R = None
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref4mc.so")
+    if os.path.exists(p):
+        R = C.CDLL(p)
+        R.ZSTD_decompress.restype = C.c_size_t
+        R.ZSTD_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+
+    def make(kind, n):
+        if kind == "zeros":
+            return bytes(n)
+        if kind == "random":
+            return rng.randbytes(n)
+        if kind == "period":
+            unit = rng.randbytes(rng.randint(1, 300))
+            return (unit * (n // len(unit) + 1))[:n]
+        if kind == "twosym":
+            return bytes(rng.choice(b"ab") for _ in range(min(n, 300000))) * (n // 300000 + 1)
+        k = {"text": 0, "json": 1, "mix": 2}[kind]
+        pages = (n + 4095) // 4096
+        buf = C.create_string_buffer(max(pages, 1) * 4096)
+        assert pkg.lib().fourmc_gen_host(k, rng.getrandbits(32), rng.randrange(1 << 20), pages, buf) == 0
+        return buf.raw[:n]
+
+    for case in range(28):
+        kind = rng.choice(["text", "text", "json", "mix", "mix", "zeros", "random", "period", "twosym"])
+        n = rng.choice([0, 1, rng.randrange(2, 70000), rng.randrange(70000, 5 * MIB), rng.randrange(5 * MIB, 13 * MIB), 4 * MIB, 8 * MIB + 1])
+        if kind == "twosym":
+            n = min(n, 2 * MIB)
+        data = make(kind, n)[:n]
+        level = rng.randint(1, 4)
+        s = ctx.compress_4mc(data, level)
+        assert ora.decompress_4mc(s, len(data)) == (len(data), data), (case, kind, n, level)
+        assert ctx.decompress_4mc(s) == data, (case, kind, n, level)
+        z = ctx.compress_4mz(data, level)
+        assert ctx.decompress_4mz(z) == data, (case, kind, n, level)
+        if R is not None:
+            pos, got = 12, b""
+            while True:
+                u, c = int.from_bytes(z[pos:pos + 4], "big"), int.from_bytes(z[pos + 4:pos + 8], "big")
+                if u == 0:
+                    break
+                payload = z[pos + 12:pos + 12 + c]
+                if c == u:
+                    got += payload
+                else:
+                    back = C.create_string_buffer(u)
+                    assert R.ZSTD_decompress(back, u, payload, c) == u, (case, kind, n, level)
+                    got += back.raw
+                pos += 12 + c
+            assert got == data, (case, kind, n, level)
