@@ -403,18 +403,24 @@ struct ZShared {
     uint32_t hist[256];               // literal histogram, then Huffman codes (value | nbits << 16)
     uint16_t sorted[256];
     uint8_t nbits[256];
-    HufBuild hb;
     uint32_t chist[3][64];            // LL, OF, ML code histograms
     short norm[3][64];
     FseCTable ct[3];
-    uint8_t cells[3][512];
-    uint8_t ncount[3][128];
-    uint8_t hufdesc[160];
-    uint8_t wts[256];                 // Huffman weights of symbols 0 .. max_sym-1
-    FseCTable wct;                    // FSE table of the weights (tree description)
-    uint8_t wcells[64];
-    uint8_t code[3][ZE_TILE];
-    uint16_t fse[3][ZE_TILE];         // value | nbits << 10, in encoding order inside the tile
+    union {                           // two working sets that never live at the same time
+        struct {                      // P3..P5: building the Huffman code and the FSE tables, their descriptions
+            HufBuild hb;
+            uint8_t cells[3][512];
+            uint8_t ncount[3][128];
+            uint8_t hufdesc[160];
+            uint8_t wts[256];         // Huffman weights of symbols 0 .. max_sym-1
+            FseCTable wct;            // FSE table of the weights (tree description)
+            uint8_t wcells[64];
+        } b;
+        struct {                      // the sequence tiles
+            uint8_t code[2][3][ZE_TILE];      // double-buffered: the next tile's codes are made while this one is packed
+            uint16_t fse[3][ZE_TILE];         // value | nbits << 10, in encoding order inside the tile
+        } t;
+    } u;
     uint32_t scan[ZE_THREADS];
     uint32_t scan_tmp[ZE_WARPS];
     uint32_t ll_base[36], ml_base[53];        // copies of the format constants (the global ones cost a cache miss per use)
@@ -429,6 +435,7 @@ struct ZShared {
     uint32_t bitpos;                  // bits of the sequence stream written so far
     uint32_t scan_total;
     int32_t fail;
+    int32_t pending;                  // the last packed tile's bits are not yet added to bitpos
 };
 
 // Executors: the GPU one (zstd_encode.cuh) runs a phase on every thread and ends it with a CTA
@@ -485,14 +492,14 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
             sh.lit_mode = 0;
             if (nlit > 0 && sh.nsym == 1) sh.lit_mode = 1;
             else if (nlit >= (uint32_t)ZE_MIN_HUF_LITS && sh.nsym >= 2) {
-                const int log = huf_build_lengths(sh.hb, sh.hist, sh.sorted, sh.nsym, sh.nbits);
+                const int log = huf_build_lengths(sh.u.b.hb, sh.hist, sh.sorted, sh.nsym, sh.nbits);
                 // the tree description: FSE-compressed weights when that is smaller or the only form
                 const int ms = sh.max_sym;
-                for (int s = 0; s < ms; s++) sh.wts[s] = sh.nbits[s] ? (uint8_t)(log + 1 - sh.nbits[s]) : 0;
+                for (int s = 0; s < ms; s++) sh.u.b.wts[s] = sh.nbits[s] ? (uint8_t)(log + 1 - sh.nbits[s]) : 0;
                 int dl = 0;
-                if (ms > 16) dl = huf_write_fse(sh.hufdesc, sh.wts, ms, sh.wct, sh.wcells);
+                if (ms > 16) dl = huf_write_fse(sh.u.b.hufdesc, sh.u.b.wts, ms, sh.u.b.wct, sh.u.b.wcells);
                 const int direct = ms <= 128 ? 1 + (ms + 1) / 2 : 0;
-                if (dl == 0 || (direct && direct <= dl)) dl = direct ? huf_write_direct(sh.hufdesc, sh.nbits, ms, log) : 0;
+                if (dl == 0 || (direct && direct <= dl)) dl = direct ? huf_write_direct(sh.u.b.hufdesc, sh.nbits, ms, log) : 0;
                 if (dl > 0) {
                     uint64_t bits = 0;
                     for (int s = 0; s <= ms; s++) bits += (uint64_t)sh.hist[s] * sh.nbits[s];
@@ -513,11 +520,11 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
             sh.max_code[k] = maxc;
             if (used == 1) {                                        // RLE: one symbol, no state bits
                 sh.mode[k] = 1; sh.ct[k].log = 0; sh.log[k] = 0; sh.ncount_len[k] = 1;
-                sh.ncount[k][0] = (uint8_t)maxc;
+                sh.u.b.ncount[k][0] = (uint8_t)maxc;
             } else if (nseq < (uint32_t)ZE_MIN_FSE_SEQ) {           // predefined distribution
                 const short *dn = k == 0 ? T.ll_norm : k == 1 ? T.of_norm : T.ml_norm;
                 const int dl = k == 1 ? 5 : 6, dmax = k == 0 ? 35 : k == 1 ? 28 : 52;
-                fse_build_ctable(sh.ct[k], dn, dmax, dl, sh.cells[k]);
+                fse_build_ctable(sh.ct[k], dn, dmax, dl, sh.u.b.cells[k]);
                 sh.mode[k] = 0; sh.log[k] = dl; sh.ncount_len[k] = 0;
             } else {
                 int log = max_log;
@@ -526,8 +533,8 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
                 if (log < 5) log = 5;
                 if (log > max_log) log = max_log;
                 fse_normalize(sh.norm[k], log, sh.chist[k], nseq, maxc);
-                sh.ncount_len[k] = fse_write_ncount(sh.ncount[k], sh.norm[k], maxc, log);
-                fse_build_ctable(sh.ct[k], sh.norm[k], maxc, log, sh.cells[k]);
+                sh.ncount_len[k] = fse_write_ncount(sh.u.b.ncount[k], sh.norm[k], maxc, log);
+                fse_build_ctable(sh.ct[k], sh.norm[k], maxc, log, sh.u.b.cells[k]);
                 sh.mode[k] = 2; sh.log[k] = log;
             }
         }
@@ -568,7 +575,7 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
                 else if (lh == 4) { const uint32_t v = 2u | (2u << 2) | (nlit << 4) | (comp << 18); put_bits(slot, 0, v, 32); }
                 else { const uint32_t v = 2u | (3u << 2) | (nlit << 4) | (comp << 22); put_bits(slot, 0, v, 32); put_byte(slot, 4, comp >> 10); }
                 pos = lh;
-                for (int i = 0; i < sh.hufdesc_len; i++) put_byte(slot, pos + i, sh.hufdesc[i]);
+                for (int i = 0; i < sh.hufdesc_len; i++) put_byte(slot, pos + i, sh.u.b.hufdesc[i]);
                 pos += (uint32_t)sh.hufdesc_len;
                 uint32_t so = pos + 6;
                 for (int w = 0; w < 4; w++) {
@@ -598,7 +605,7 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
         if (nseq > 0) {
             put_byte(slot, pos++, ((uint32_t)sh.mode[0] << 6) | ((uint32_t)sh.mode[1] << 4) | ((uint32_t)sh.mode[2] << 2));
             for (int k = 0; k < 3; k++)
-                if (sh.mode[k]) { for (int i = 0; i < sh.ncount_len[k]; i++) put_byte(slot, pos + i, sh.ncount[k][i]); pos += (uint32_t)sh.ncount_len[k]; }
+                if (sh.mode[k]) { for (int i = 0; i < sh.ncount_len[k]; i++) put_byte(slot, pos + i, sh.u.b.ncount[k][i]); pos += (uint32_t)sh.ncount_len[k]; }
         }
         sh.bits_base = pos;
         if (pos >= in.rlen) sh.fail = 1;                            // already no smaller than a raw block
@@ -631,40 +638,69 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
         }
     });
 
-    // ---- sequences: tiles of ZE_TILE from the LAST sequence backwards (zstd_compress_sequences.c:290-383)
+    // ---- sequences: tiles of ZE_TILE from the LAST sequence backwards (zstd_compress_sequences.c:290-383).
+    // Per tile: the three state chains (T2), per-thread bit totals (T3), scan, pack (T4).  The codes of the
+    // next tile are made in the same phase as the pack of this one (double-buffered), and the running bit
+    // position is brought up to date by thread 0 at the start of the next T2 / of the close phase.
     const uint32_t ntiles = (nseq + ZE_TILE - 1) / ZE_TILE;
+    auto make_codes = [&](int tid, uint32_t tile) {
+        const uint32_t hi = nseq - tile * ZE_TILE, cnt = hi < (uint32_t)ZE_TILE ? hi : (uint32_t)ZE_TILE;
+        uint8_t(*code)[ZE_TILE] = sh.u.t.code[tile & 1];
+        for (uint32_t p = (uint32_t)tid; p < cnt; p += ZE_THREADS) {                // position p of the tile <-> sequence hi - 1 - p
+            const uint32_t i = hi - 1 - p;
+            code[0][p] = (uint8_t)ll_code(in.ll[i]);
+            code[1][p] = (uint8_t)highbit(ze_off_base(in.ll, in.off, i));
+            code[2][p] = (uint8_t)ml_code((uint32_t)in.ml[i] - 3u);
+        }
+    };
+    auto settle = [&]() {                                                           // thread 0 only
+        if (!sh.pending) return;
+        sh.pending = 0;
+        if ((uint64_t)sh.bits_base * 8 + sh.bitpos + sh.scan_total + 64 > cap_bits) sh.fail = 1;
+        else sh.bitpos += sh.scan_total;
+    };
+    ex.phase([&](int tid) {
+        if (tid == 0) sh.pending = 0;
+        if (ntiles > 0) make_codes(tid, 0);
+    });
     for (uint32_t tile = 0; tile < ntiles; tile++) {
         const uint32_t hi = nseq - tile * ZE_TILE, cnt = hi < (uint32_t)ZE_TILE ? hi : (uint32_t)ZE_TILE;
-        // T1: codes, position p of the tile <-> sequence hi - 1 - p
-        ex.phase([&](int tid) {
-            for (uint32_t p = (uint32_t)tid; p < cnt; p += ZE_THREADS) {
-                const uint32_t i = hi - 1 - p;
-                sh.code[0][p] = (uint8_t)ll_code(in.ll[i]);
-                sh.code[1][p] = (uint8_t)highbit(ze_off_base(in.ll, in.off, i));
-                sh.code[2][p] = (uint8_t)ml_code((uint32_t)in.ml[i] - 3u);
-            }
-        });
+        uint8_t(*code)[ZE_TILE] = sh.u.t.code[tile & 1];
         // T2: the three state chains, one thread each (lanes 0..2 of warp 0 run in lockstep)
         ex.phase([&](int tid) {
+            if (tid == 0) settle();
             if (tid >= 3) return;
             const int k = tid;
             const FseCTable &ct = sh.ct[k];
             uint32_t p = 0;
-            if (ct.log == 0) { for (; p < cnt; p++) sh.fse[k][p] = 0; return; }
+            if (ct.log == 0) { for (; p < cnt; p++) sh.u.t.fse[k][p] = 0; return; }
             uint32_t st = sh.state[k];
             if (tile == 0) {                                         // FSE_initCState2 on the last sequence
-                const int sym = sh.code[k][0];
+                const int sym = code[k][0];
                 const uint32_t nbout = (uint32_t)(ct.dnb[sym] + (1 << 15)) >> 16;
                 st = (nbout << 16) - (uint32_t)ct.dnb[sym];
                 st = ct.state[(st >> nbout) + ct.dfs[sym]];
-                sh.fse[k][0] = 0;
+                sh.u.t.fse[k][0] = 0;
                 p = 1;
             }
-            for (; p < cnt; p++) {
-                const int sym = sh.code[k][p];
-                const uint32_t nbout = (st + (uint32_t)ct.dnb[sym]) >> 16;
-                sh.fse[k][p] = (uint16_t)((st & ((1u << nbout) - 1)) | (nbout << 10));
-                st = ct.state[(st >> nbout) + ct.dfs[sym]];
+            // The only loop-carried value is the state: the symbol two steps ahead and the per-symbol
+            // constants one step ahead are fetched before they are needed, so a step costs one dependent
+            // shared-memory load (the next state) instead of three.
+            if (p < cnt) {
+                const uint8_t *cd = code[k];
+                int sym_next = p + 1 < cnt ? cd[p + 1] : 0;
+                uint32_t dnb = (uint32_t)ct.dnb[cd[p]];
+                int dfs = ct.dfs[cd[p]];
+                for (; p < cnt; p++) {
+                    const int sym_after = p + 2 < cnt ? cd[p + 2] : 0;
+                    const uint32_t dnb_next = (uint32_t)ct.dnb[sym_next];
+                    const int dfs_next = ct.dfs[sym_next];
+                    const uint32_t nbout = (st + dnb) >> 16;
+                    const uint32_t outv = (st & ((1u << nbout) - 1)) | (nbout << 10);
+                    st = ct.state[(st >> nbout) + dfs];
+                    sh.u.t.fse[k][p] = (uint16_t)outv;
+                    dnb = dnb_next; dfs = dfs_next; sym_next = sym_after;
+                }
             }
             sh.state[k] = st;
         });
@@ -673,24 +709,26 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
             uint32_t bits = 0;
             const uint32_t p0 = (uint32_t)tid * ZE_PER_THREAD, p1 = p0 + ZE_PER_THREAD < cnt ? p0 + ZE_PER_THREAD : cnt;
             for (uint32_t p = p0; p < p1; p++) {
-                const uint32_t lc = sh.code[0][p], oc = sh.code[1][p], mc = sh.code[2][p];
-                bits += (sh.fse[0][p] >> 10) + (sh.fse[1][p] >> 10) + (sh.fse[2][p] >> 10) + sh.ll_bits[lc] + sh.ml_bits[mc] + oc;
+                const uint32_t lc = code[0][p], oc = code[1][p], mc = code[2][p];
+                bits += (sh.u.t.fse[0][p] >> 10) + (sh.u.t.fse[1][p] >> 10) + (sh.u.t.fse[2][p] >> 10) + sh.ll_bits[lc] + sh.ml_bits[mc] + oc;
             }
             sh.scan[tid] = bits;
         });
         ex.excl_scan(sh.scan, sh.scan_tmp, &sh.scan_total);
-        // T4: pack
+        // T4: pack this tile; make the next tile's codes
         ex.phase([&](int tid) {
+            if (tile + 1 < ntiles) make_codes(tid, tile + 1);
+            if (tid == 0) sh.pending = 1;
             if (sh.fail) return;
-            if ((uint64_t)sh.bits_base * 8 + sh.bitpos + sh.scan_total + 64 > cap_bits) return;      // checked again below
+            if ((uint64_t)sh.bits_base * 8 + sh.bitpos + sh.scan_total + 64 > cap_bits) return;      // settle() marks the failure
             const uint32_t p0 = (uint32_t)tid * ZE_PER_THREAD, p1 = p0 + ZE_PER_THREAD < cnt ? p0 + ZE_PER_THREAD : cnt;
             if (p0 >= p1) return;
             BitRun br;
             br.start(slot, (uint64_t)sh.bits_base * 8 + sh.bitpos + sh.scan[tid]);
             for (uint32_t p = p0; p < p1; p++) {
                 const uint32_t i = hi - 1 - p;
-                const uint32_t lc = sh.code[0][p], oc = sh.code[1][p], mc = sh.code[2][p];
-                const uint32_t fo = sh.fse[1][p], fm = sh.fse[2][p], fl = sh.fse[0][p];
+                const uint32_t lc = code[0][p], oc = code[1][p], mc = code[2][p];
+                const uint32_t fo = sh.u.t.fse[1][p], fm = sh.u.t.fse[2][p], fl = sh.u.t.fse[0][p];
                 br.add(fo & 1023u, (int)(fo >> 10));
                 br.add(fm & 1023u, (int)(fm >> 10));
                 br.add(fl & 1023u, (int)(fl >> 10));
@@ -700,16 +738,12 @@ FZ_HD inline void zenc_region(Exec &ex, ZShared &sh, const ZRegionIn &in, uint32
             }
             br.finish();
         });
-        ex.phase([&](int tid) {
-            if (tid != 0 || sh.fail) return;
-            if ((uint64_t)sh.bits_base * 8 + sh.bitpos + sh.scan_total + 64 > cap_bits) sh.fail = 1;
-            else sh.bitpos += sh.scan_total;
-        });
     }
 
     // ---- close: final states (ML, OF, LL), end mark, sizes
     ex.phase([&](int tid) {
         if (tid != 0) return;
+        settle();
         uint32_t total = sh.bits_base;
         if (!sh.fail && nseq > 0) {
             uint64_t g = (uint64_t)sh.bits_base * 8 + sh.bitpos;
