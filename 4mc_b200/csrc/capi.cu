@@ -140,7 +140,10 @@ int ensure(fourmc_ctx *ctx, DevBuf &b, size_t need)
 {
     if (b.cap >= need && b.p) return FOURMC_OK;
     if (b.p) { CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
-    size_t cap = (need + 255) & ~(size_t)255;
+    // 6 % of headroom: several workspaces are sized from compressed sizes, which differ a little from call to
+    // call (and from run to run: the encoder's index is filled by racing stores); without it a batch that is a
+    // few bytes larger than every earlier one costs a cudaFree + cudaMalloc of gigabytes in the middle of a call
+    size_t cap = (need + need / 16 + 255) & ~(size_t)255;
     if (cap < 256) cap = 256;
     CK(cudaMalloc(&b.p, cap));
     b.cap = cap;
@@ -550,6 +553,7 @@ int pinned_scratch(fourmc_ctx *ctx, size_t need)
 {
     if (ctx->pinned_cap >= need) return FOURMC_OK;
     if (ctx->pinned) { cudaFreeHost(ctx->pinned); ctx->pinned = nullptr; ctx->pinned_cap = 0; }
+    need += need / 8;                                 // headroom, as in ensure()
     CK(cudaMallocHost(&ctx->pinned, need));
     ctx->pinned_cap = need;
     return FOURMC_OK;
