@@ -286,7 +286,7 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     P.region_bytes = region_bytes; P.regions_per_block = rpb;
     if (P.depth > 0) {
         const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
-        KL("lz4_region_chain_kernel", st, lz4_region_kernel<false, true><<<grid, ENC_THREADS, ENC_SMEM_CHAIN, st>>>(P));
+        KL("lz4_region_chain_kernel", st, lz4_region_kernel<false, true><<<grid, ENC_CHAIN_THREADS, ENC_SMEM_CHAIN, st>>>(P));
     } else {
         const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
         KL("lz4_region_kernel", st, lz4_region_kernel<false, false><<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
@@ -368,7 +368,7 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
         P.region_bytes = region_bytes; P.regions_per_block = rpb;
         if (P.depth > 0) {
             const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
-            KL("lz4_region_chain_kernel", st, lz4_region_kernel<true, true><<<grid, ENC_THREADS, ENC_SMEM_CHAIN, st>>>(P));
+            KL("lz4_region_chain_kernel", st, lz4_region_kernel<true, true><<<grid, ENC_CHAIN_THREADS, ENC_SMEM_CHAIN, st>>>(P));
         } else {
             const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
             KL("lz4_region_kernel", st, lz4_region_kernel<true, false><<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));

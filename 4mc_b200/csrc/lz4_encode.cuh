@@ -51,10 +51,11 @@ constexpr int ENC_STAGE_CHAIN = 2 * ENC_REGION + (2 << 14);
 // of history (log text, depth 16: ratio 2.29 without the look-back, 2.49 with it).  128 regions per block.
 constexpr int ENC_CHAIN_REGION = 32768;
 constexpr int ENC_CHAIN_LOOKBACK = ENC_REGION - ENC_CHAIN_REGION;
-constexpr int ENC_CHAIN_SLICE = 68;              // 512 slices of 17 words cover the region
+constexpr int ENC_CHAIN_THREADS = 1024;          // the chain parse is latency bound per thread: twice the threads, half the slice
+constexpr int ENC_CHAIN_SLICE = 36;              // 1024 slices of 9 words cover the region
 constexpr int ENC_CHAIN_SLOT = ENC_CHAIN_REGION + 512;
 constexpr int ENC_MAX_REGIONS_PER_BLOCK = FOURMC_BLOCKSIZE / ENC_CHAIN_REGION;   // 128
-static_assert(ENC_THREADS * ENC_CHAIN_SLICE >= ENC_CHAIN_REGION, "chain slices must cover the region");
+static_assert(ENC_CHAIN_THREADS * ENC_CHAIN_SLICE >= ENC_CHAIN_REGION, "chain slices must cover the region");
 constexpr size_t ENC_SMEM_CHAIN = ENC_REGION + ENC_PAD + ENC_STAGE_CHAIN;
 static_assert((sizeof(uint16_t) << ENC_HASH_BITS) <= ENC_STAGE, "the hash table lives inside the staging area");
 
@@ -97,14 +98,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 
 // CTA-wide exclusive scan over ENC_THREADS values (max or add); `tmp` holds ENC_WARPS ints.
 // Identity is 0 for both (all values are >= 0).  *total (optional) = reduction over the CTA.
-template <bool IS_MAX>
+template <bool IS_MAX, int NWARPS = ENC_WARPS>
 __device__ __forceinline__ int cta_excl_scan(int v, int *tmp, int *total)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int incl = IS_MAX ? warp_incl_scan_max(v) : warp_incl_scan_add(v);
     if (lane == 31) tmp[warp] = incl;
     __syncthreads();
-    const int wv = lane < ENC_WARPS ? tmp[lane] : 0;
+    const int wv = lane < NWARPS ? tmp[lane] : 0;
     const int wincl = IS_MAX ? warp_incl_scan_max(wv) : warp_incl_scan_add(wv);
     int wexcl = __shfl_up_sync(FM_FULL, wincl, 1);
     if (lane == 0) wexcl = 0;
@@ -143,13 +144,14 @@ __device__ __forceinline__ uint32_t enc_pack(int st_rel, int len, int off)
 // slices, the stitching and the emit stages are shared with the Fast parse.  One CTA per SM
 // (224 KiB of shared memory).
 template <bool ZSEQ, bool CHAIN>
-__global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(EncParams P)
+__global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(EncParams P)
 {
+    constexpr int NT = CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, NW = NT / 32;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *data = smem;                                          // ENC_REGION + ENC_PAD
     uint32_t *data32 = (uint32_t *)smem;
     uint16_t *table = (uint16_t *)(smem + ENC_REGION + ENC_PAD);
-    __shared__ int s_scan[ENC_WARPS];
+    __shared__ int s_scan[NW];
     __shared__ uint32_t s_work;
     __shared__ int s_flush;
     __shared__ __align__(8) uint64_t s_bar;
@@ -197,11 +199,11 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smem_u32(data)), "l"(gsrc), "r"(bulk), "r"(smem_u32(&s_bar)) : "memory");
         }
-        for (int i = bulk + tid; i < rlen; i += ENC_THREADS) data[i] = gsrc[i];
+        for (int i = bulk + tid; i < rlen; i += NT) data[i] = gsrc[i];
         if (tid < ENC_PAD) data[rlen + tid] = 0;                   // reads past the end see zeros
         uint16_t *prev = table, *head = table + ENC_REGION;         // CHAIN only
-        if constexpr (CHAIN) { for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += ENC_THREADS) ((uint32_t *)head)[i] = 0xffffffffu; }
-        else { for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += ENC_THREADS) ((uint32_t *)table)[i] = 0xffffffffu; }
+        if constexpr (CHAIN) { for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += NT) ((uint32_t *)head)[i] = 0xffffffffu; }
+        else { for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += NT) ((uint32_t *)table)[i] = 0xffffffffu; }
         if (bulk) {
             uint32_t done = 0;
             while (!done) {
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
             // hashes inside a round one of them wins, the others stay reachable only through their own
             // links -- 0.2 % of ratio on text, tests/native/enc_emul.cpp EMUL_BUILD=128000).
             const int last = rlen - 4;
-            for (int p = tid; p <= last; p += ENC_THREADS) prev[p] = (uint16_t)enc_hash(smem_read4(data32, p));
+            for (int p = tid; p <= last; p += NT) prev[p] = (uint16_t)enc_hash(smem_read4(data32, p));
             __syncthreads();
             if (tid < 128) {
                 for (int base = 0; base <= last; base += 128) {
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
             __syncthreads();
         } else {
             const int last = rlen - 4;                             // last position with 4 bytes
-            constexpr int STEP = ENC_THREADS * 4;
+            constexpr int STEP = NT * 4;
             for (int base = ((rlen - 1) / STEP) * STEP; base >= 0; base -= STEP) {
                 const int p = base + 4 * tid;
                 if (p <= last) {
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
         }
 
         // ---- stitch 1: trim against everything earlier slices cover
-        const int cov = cta_excl_scan<true>(l_len ? l_st + l_len : 0, s_scan, nullptr);
+        const int cov = cta_excl_scan<true, NW>(l_len ? l_st + l_len : 0, s_scan, nullptr);
         int surv_end = 0;                                           // end of my last surviving sequence
         {
             int w = 0;
@@ -376,7 +378,7 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
         }
         // ---- stitch 2: where does my first literal run start; encoded size of my sequences
         int total_anchor;
-        int anchor0 = cta_excl_scan<true>(surv_end, s_scan, &total_anchor);
+        int anchor0 = cta_excl_scan<true, NW>(surv_end, s_scan, &total_anchor);
         anchor0 = max(anchor0, lb);                                 // the first literal run starts at the first NEW byte
         total_anchor = max(total_anchor, lb);
         int bytes = 0;
@@ -396,8 +398,8 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
         }
         const int myseq = nrec + (l_len ? 1 : 0);
         int total_bytes, total_seq;
-        const int out_off = cta_excl_scan<false>(bytes, s_scan, &total_bytes);
-        const int seq_before = cta_excl_scan<false>(myseq, s_scan, &total_seq);
+        const int out_off = cta_excl_scan<false, NW>(bytes, s_scan, &total_bytes);
+        const int seq_before = cta_excl_scan<false, NW>(myseq, s_scan, &total_seq);
 
         uint8_t *slot = P.scratch + (size_t)rg * P.slot_bytes;
         if constexpr (ZSEQ) {
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
             int mbytes = l_len;
             for (int k = 0; k < nrec; k++) mbytes += (int)((rec[k] >> 16) & 255);
             int total_matched;
-            const int matched_before = cta_excl_scan<false>(mbytes, s_scan, &total_matched);
+            const int matched_before = cta_excl_scan<false, NW>(mbytes, s_scan, &total_matched);
             const uint32_t stride = ((uint32_t)total_seq + 7u) & ~7u;
             uint16_t *zll = (uint16_t *)slot, *zml = zll + stride, *zoff = zml + stride;
             uint8_t *zlit = (uint8_t *)(zoff + stride);
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
             }
             {   // literals after the region's last match
                 uint8_t *dp = zlit + (total_anchor - lb - total_matched);
-                for (int i = total_anchor + tid; i < rlen; i += ENC_THREADS) dp[i - total_anchor] = data[i];
+                for (int i = total_anchor + tid; i < rlen; i += NT) dp[i - total_anchor] = data[i];
             }
             total_bytes = rlen - lb - total_matched;
         } else {
@@ -491,8 +493,8 @@ __global__ void __launch_bounds__(ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(
             const int nflush = s_flush;
             const uint4 *sv = (const uint4 *)stage;
             uint4 *dv = (uint4 *)slot;
-            for (int i = tid; i < (nflush >> 4); i += ENC_THREADS) dv[i] = sv[i];
-            for (int i = (nflush & ~15) + tid; i < nflush; i += ENC_THREADS) slot[i] = stage[i];
+            for (int i = tid; i < (nflush >> 4); i += NT) dv[i] = sv[i];
+            for (int i = (nflush & ~15) + tid; i < nflush; i += NT) slot[i] = stage[i];
         }
         }
         if (tid == 0) {

@@ -22,7 +22,7 @@ inline uint8_t *emit_len(uint8_t *o, int v) { while (v >= 255) { *o++ = 255; v -
 // per search, optional one-step lazy evaluation.
 // In the chain parse the 64 KiB window is 32 KiB of look-back (earlier bytes of the block: searched, not
 // parsed) + a 32 KiB region of new bytes; positions are relative to the window, new bytes are [lb, rlen).
-constexpr int CHAIN_REGION = 32768, CHAIN_LOOKBACK = REGION - CHAIN_REGION, CHAIN_SLICE = 68;
+constexpr int CHAIN_REGION = 32768, CHAIN_LOOKBACK = REGION - CHAIN_REGION, CHAIN_SLICE = 36, CHAIN_THREADS = 1024;
 void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_new, int min_match, std::vector<uint8_t> &body, Meta &mt,
             int depth = 0, int lazy = 0)
 {
@@ -38,8 +38,9 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_new, int min_match,
     // the GPU -- emulate "highest thread wins" (any order is legal)
     for (int base = ((rlen - 1) / THREADS) * THREADS; base >= 0; base -= THREADS)
         for (int t = THREADS - 1; t >= 0; t--) { int p = base + t; if (p <= rlen - 4 && (p & 1) == 0) table[hsh(rd4(data.data(), p))] = (uint16_t)p; }   // even positions only
-    std::vector<std::vector<Seq>> inner(THREADS);
-    std::vector<Seq> last(THREADS, Seq{0, 0, 0});
+    const int NTH = depth > 0 ? CHAIN_THREADS : THREADS;
+    std::vector<std::vector<Seq>> inner(NTH);
+    std::vector<Seq> last(NTH, Seq{0, 0, 0});
     const uint8_t *d = data.data();
     std::vector<uint16_t> prev;
     if (depth > 0) {
@@ -80,7 +81,7 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_new, int min_match,
         }
         return best;
     };
-    for (int t = 0; t < THREADS; t++) {
+    for (int t = 0; t < NTH; t++) {
         const int ss = depth > 0 ? lb + t * CHAIN_SLICE : t * SLICE;
         if (ss >= rlen) continue;
         const int se = std::min(ss + (depth > 0 ? CHAIN_SLICE : SLICE), rlen);
@@ -123,9 +124,9 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_new, int min_match,
         }
     }
     // stitch 1
-    std::vector<int> surv_end(THREADS, 0);
+    std::vector<int> surv_end(NTH, 0);
     int cov = 0;
-    for (int t = 0; t < THREADS; t++) {
+    for (int t = 0; t < NTH; t++) {
         const int my_end = last[t].len ? last[t].st + last[t].len : 0;
         std::vector<Seq> keep;
         for (auto s : inner[t]) {
@@ -145,7 +146,7 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_new, int min_match,
     // stitch 2 + emit
     body.clear();
     int anchor = lb; uint32_t nseq = 0; mt.lead = 0;
-    for (int t = 0; t < THREADS; t++) {
+    for (int t = 0; t < NTH; t++) {
         std::vector<Seq> all = inner[t];
         if (last[t].len) all.push_back(last[t]);
         int a = anchor;
