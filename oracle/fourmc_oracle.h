@@ -60,6 +60,11 @@ long long fmo_4mc_compress(const uint8_t *in, size_t n, uint8_t *out, size_t out
  * or one of FMO_ERR_*. */
 long long fmo_4mc_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap);
 
+/* zstd_oracle.c: a strict Zstandard frame decoder (ZSTD_decompress for valid frames: native/4mc.c:810) and the
+ * 4mz reader (native/4mc.c:709-857).  fmo_zstd_decompress returns the decoded size or -1. */
+long long fmo_zstd_decompress(uint8_t *dst, long long cap, const uint8_t *src, long long n);
+long long fmo_4mz_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap);
+
 /* Footer/index reader restating FourMcInputStream.readIndex
  * (java/hadoop-4mc/src/main/java/com/fing/compression/fourmc/FourMcInputStream.java:163-239).
  * Returns number of blocks (0 when the file is too small to hold an index), writes up to

@@ -1,0 +1,94 @@
+"""The Zstandard oracle (oracle/zstd_oracle.c: a strict frame decoder and the 4mz reader) pinned to the
+reference: the .4mz files the reference CLI wrote (tests/golden, harvested by make_golden.py), the reference's
+own ZSTD_decompress verdicts on 1767 valid and mutated frames (tests/golden/zstd_decode.json) and, where
+oracle/_ref exists, frames compressed live by the reference at the four 4mz levels."""
+import ctypes as C
+import random
+
+import pytest
+
+from conftest import golden_bytes, golden_json, gen_logtext
+
+MIB = 1 << 20
+
+
+@pytest.fixture(scope="module")
+def zora(oracle):
+    oracle.fmo_zstd_decompress.restype = C.c_longlong
+    oracle.fmo_zstd_decompress.argtypes = [C.c_char_p, C.c_longlong, C.c_char_p, C.c_longlong]
+    oracle.fmo_4mz_decompress.restype = C.c_longlong
+    oracle.fmo_4mz_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+
+    class Z:
+        @staticmethod
+        def frame(src, cap):
+            out = C.create_string_buffer(max(cap, 1) + 64)
+            r = oracle.fmo_zstd_decompress(out, cap, bytes(src), len(src))
+            return r, out.raw[:max(r, 0)]
+
+        @staticmethod
+        def stream(data, cap):
+            out = C.create_string_buffer(max(cap, 1))
+            r = oracle.fmo_4mz_decompress(bytes(data), len(data), out, cap)
+            return r, out.raw[:max(r, 0)]
+    return Z
+
+
+def test_reference_4mz_files(zora, pkg):
+    text = golden_bytes("logtext_128k.bin")
+    for lvl in (1, 2, 3, 4):
+        assert zora.stream(golden_bytes(f"logtext_128k.z{lvl}.4mz"), len(text)) == (len(text), text)
+    big = gen_logtext(pkg, 1280 * 1024, first_page=64)
+    for lvl in (1, 2):
+        assert zora.stream(golden_bytes(f"logtext_1280k.z{lvl}.4mz"), len(big)) == (len(big), big)
+    assert zora.stream(golden_bytes("empty.4mz"), 0)[0] == 0
+    assert zora.stream(golden_bytes("A.4mz"), 1) == (1, b"A")
+    n = 4 * MIB + 1
+    assert zora.stream(golden_bytes("zeros_4m1.4mz"), n) == (n, bytes(n))
+    rnd = golden_bytes("random_70000.bin")
+    assert zora.stream(golden_bytes("random_70000.4mz"), len(rnd)) == (len(rnd), rnd)
+
+
+def test_4mz_stream_errors(zora):
+    good = golden_bytes("logtext_128k.z1.4mz")
+    n = 128 * 1024
+    for at in (9, 100, len(good) - 1):              # header checksum, block payload, footer checksum
+        bad = bytearray(good); bad[at] ^= 1
+        assert zora.stream(bad, n)[0] < 0, at
+    assert zora.stream(good[:20], n)[0] < 0         # cut inside a block header
+    assert zora.stream(good.replace(b"4MZ\0", b"4MC\0", 1), n)[0] < 0
+    assert zora.stream(good, n - 1)[0] < 0          # output too small
+
+
+def test_reference_decode_verdicts(zora, ora):
+    """Every frame the reference decodes is decoded to the same bytes, or (for the handful of malformed frames the
+    reference tolerates) rejected; nothing the reference rejects is accepted."""
+    same = strict = 0
+    for z in golden_json("zstd_decode.json"):
+        src = bytes.fromhex(z["hex"])
+        for cap, ret, xxh in z["runs"]:
+            r, out = zora.frame(src, cap)
+            if ret < 0:
+                assert r < 0, (z["hex"][:64], cap, ret, r)
+            elif r >= 0:
+                assert r == ret and ora.xxh32(out) == xxh, (z["hex"][:64], cap, ret, r)
+                same += 1
+            else:
+                strict += 1
+    assert same > 500 and strict <= 4
+
+
+def test_live_reference_frames(zora, ref, pkg):
+    ref.ZSTD_compress.restype = C.c_size_t
+    ref.ZSTD_compress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]
+    rng = random.Random(0x4D5A)
+    text = gen_logtext(pkg, 2 * MIB)
+    cases = [b"", b"x", bytes(300000), text, text[:70001], bytes(rng.randrange(256) for _ in range(5000)),
+             bytes(rng.choice(b"ab") for _ in range(200000)), (text[:1000] * 900)]
+    for data in cases:
+        for lvl in (1, 3, 6, 12):
+            cap = len(data) + len(data) // 128 + 1024
+            out = C.create_string_buffer(cap)
+            c = ref.ZSTD_compress(out, cap, data, len(data), lvl)
+            assert c < cap
+            assert zora.frame(out.raw[:c], len(data)) == (len(data), data), (len(data), lvl)
