@@ -9,7 +9,9 @@ compressed to a complete .4mc stream (LZ4 encode, XXH32, block headers, footer i
 stream is decompressed again (index parse, XXH32 verify, LZ4 decode), everything resident in HBM.
 `value` = uncompressed bytes of the batch / (compress time + decompress time), summed over GPUs.
 `e2e` is the same round trip through the host-buffer C-ABI calls (fourmc_4mc_compress_host /
-fourmc_4mc_decompress_host) with pinned host buffers, PCIe copies inside the timed region.
+fourmc_4mc_decompress_host) with pinned host buffers, PCIe copies inside the timed region, measured twice:
+call after call, and with the writer call of step i+1 running beside the reader call of step i (two contexts,
+two host threads: both PCIe directions busy); `e2e.value` is the better of the two, both are in the line.
 One process per GPU (torchrun); ranks own disjoint page ranges of the input and exchange only the
 block-length index (one NCCL all-gather per step) -- weak scaling.
 """
@@ -449,10 +451,73 @@ def main_ours(args):
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         assert bool(torch.equal(h_out[:1 << 20], h_in[:1 << 20])) and bool(torch.equal(h_out[-(1 << 20):], h_in[-(1 << 20):]))
-        e2e = {"value": world * en * args.steps / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": en + ec,
-               "d2h_bytes_per_step": ec + en, "bytes_per_step": en, "ms_per_step": dt / args.steps * 1e3,
+        seq = {"value": world * en * args.steps / dt / 1e9, "ms_per_step": dt / args.steps * 1e3,
                "compress_GBps": world * en * args.steps / e2e_t[0] / 1e9, "decompress_GBps": world * en * args.steps / e2e_t[1] / 1e9}
-        del h_in, h_comp, h_out
+
+        # The same K round trips as a two-stage pipeline: the writer's call for step i+1 runs (second context, second
+        # host thread) while the reader's call for step i does, so both PCIe directions carry payload at once
+        # (a writer moves u in / c out, a reader c in / u out).  Every step still copies its input from pinned host
+        # memory and its result back; nothing is skipped, the K calls of each kind only overlap.
+        perr, dt2_local, h_comp2, ctx2 = None, float("inf"), None, None
+
+        def piped(k):
+            csz, err = [0] * k, []
+
+            def wr(i):
+                try:
+                    csz[i] = ctx2._check(compress_host(ctx2.handle, 1, h_in.data_ptr(), en, comps[i & 1].data_ptr(), ecap))
+                except Exception as e:          # noqa: BLE001 -- re-raised on the main thread
+                    err.append(e)
+            wr(0)
+            for i in range(k):
+                t = threading.Thread(target=wr, args=(i + 1,)) if i + 1 < k else None
+                if t:
+                    t.start()
+                try:
+                    if err:
+                        raise err[0]
+                    d = ctx._check(decompress_host(ctx.handle, comps[i & 1].data_ptr(), csz[i], h_out.data_ptr(), en))
+                    assert d == en
+                finally:
+                    if t:
+                        t.join()
+            if err:
+                raise err[0]
+
+        # a failure here is reported in the line and the sequential figure stands; the collectives stay outside
+        # the try blocks so that ranks never part ways
+        try:
+            ctx2 = pkg.Context(local)
+            h_comp2 = torch.empty(ecap, dtype=torch.uint8, pin_memory=True)
+            comps = (h_comp, h_comp2)
+            h_out.zero_()
+            piped(max(2, args.warmup))
+        except Exception as e:          # noqa: BLE001
+            perr = repr(e)[:200]
+        barrier()
+        if perr is None:
+            try:
+                t0 = time.perf_counter()
+                piped(args.steps)
+                torch.cuda.synchronize()
+                dt2_local = time.perf_counter() - t0
+                assert bool(torch.equal(h_out[:1 << 20], h_in[:1 << 20])) and bool(torch.equal(h_out[-(1 << 20):], h_in[-(1 << 20):]))
+            except Exception as e:      # noqa: BLE001
+                perr, dt2_local = repr(e)[:200], float("inf")
+        dt2 = max_over_ranks(dt2_local)
+        if ctx2 is not None:
+            ctx2.close()
+        pip = {"value": world * en * args.steps / dt2 / 1e9, "ms_per_step": dt2 / args.steps * 1e3}
+        if perr is not None or dt2 == float("inf"):
+            pip = {"value": 0.0, "ms_per_step": None, "error": perr or "failed on another rank"}
+        best = pip if pip["value"] > seq["value"] else seq
+        e2e = {"value": best["value"], "unit": "GB/s", "h2d_bytes_per_step": en + ec,
+               "d2h_bytes_per_step": ec + en, "bytes_per_step": en, "ms_per_step": best["ms_per_step"],
+               "mode": "pipelined: writer call of step i+1 beside the reader call of step i (two contexts)" if best is pip
+                       else "sequential: writer call, then reader call",
+               "sequential": seq, "pipelined": pip,
+               "compress_GBps": seq["compress_GBps"], "decompress_GBps": seq["decompress_GBps"]}
+        del h_in, h_comp, h_comp2, h_out
 
     cpu = None
     if not args.no_cpu and rank == 0 and world == 1:

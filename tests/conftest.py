@@ -41,6 +41,10 @@ def oracle():
     O.fmo_4mc_compress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
     O.fmo_4mc_decompress.restype = C.c_longlong
     O.fmo_4mc_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    O.fmo_zstd_decompress.restype = C.c_longlong
+    O.fmo_zstd_decompress.argtypes = [C.c_char_p, C.c_longlong, C.c_char_p, C.c_longlong]
+    O.fmo_4mz_decompress.restype = C.c_longlong
+    O.fmo_4mz_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
     O.fmo_4mc_read_index.restype = C.c_longlong
     O.fmo_4mc_read_index.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_int64), C.c_size_t]
     for f in ("fmo_index_find_next_position", "fmo_index_find_belonging_block"):
@@ -82,6 +86,17 @@ class OracleApi:
     def decompress_4mc(self, stream, cap):
         out = C.create_string_buffer(max(cap, 1))
         r = self.O.fmo_4mc_decompress(bytes(stream), len(stream), out, cap)
+        return r, out.raw[:max(r, 0)]
+
+    def zstd_decompress(self, frame, cap):
+        """oracle/zstd_oracle.c: strict Zstandard frame decoder"""
+        out = C.create_string_buffer(max(cap, 1) + 64)
+        r = self.O.fmo_zstd_decompress(out, cap, bytes(frame), len(frame))
+        return r, out.raw[:max(r, 0)]
+
+    def decompress_4mz(self, stream, cap):
+        out = C.create_string_buffer(max(cap, 1))
+        r = self.O.fmo_4mz_decompress(bytes(stream), len(stream), out, cap)
         return r, out.raw[:max(r, 0)]
 
 

@@ -13,24 +13,10 @@ MIB = 1 << 20
 
 
 @pytest.fixture(scope="module")
-def zora(oracle):
-    oracle.fmo_zstd_decompress.restype = C.c_longlong
-    oracle.fmo_zstd_decompress.argtypes = [C.c_char_p, C.c_longlong, C.c_char_p, C.c_longlong]
-    oracle.fmo_4mz_decompress.restype = C.c_longlong
-    oracle.fmo_4mz_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
-
+def zora(ora):
     class Z:
-        @staticmethod
-        def frame(src, cap):
-            out = C.create_string_buffer(max(cap, 1) + 64)
-            r = oracle.fmo_zstd_decompress(out, cap, bytes(src), len(src))
-            return r, out.raw[:max(r, 0)]
-
-        @staticmethod
-        def stream(data, cap):
-            out = C.create_string_buffer(max(cap, 1))
-            r = oracle.fmo_4mz_decompress(bytes(data), len(data), out, cap)
-            return r, out.raw[:max(r, 0)]
+        frame = staticmethod(ora.zstd_decompress)
+        stream = staticmethod(ora.decompress_4mz)
     return Z
 
 

@@ -80,7 +80,7 @@ def sample_inputs(pkg):
     }
 
 
-def test_emulated_encoder_frames_decode(zenc, zdec, pkg):
+def test_emulated_encoder_frames_decode(zenc, zdec, pkg, ora):
     ref = ref_decoder()
     for name, data in sample_inputs(pkg).items():
         for mm in (4, 5, 4 | (1 << 4), 5 | (2 << 4)):           # bits 4..: the stand-in matcher (recent / first / first + repeat offset)
@@ -91,6 +91,7 @@ def test_emulated_encoder_frames_decode(zenc, zdec, pkg):
             frame = out.raw[:c]
             assert c <= len(data) + 12 + 3 * ((len(data) + 65535) // 65536), name     # never worse than raw blocks
             assert zdec(frame, len(data)) == (len(data), data), name
+            assert ora.zstd_decompress(frame, len(data)) == (len(data), data), name      # the strict oracle
             if ref:
                 assert ref(frame, len(data)) == (len(data), data), name
     # the encoder must actually compress: log text well under half, zeros to almost nothing
@@ -183,6 +184,7 @@ def test_gpu_4mz_streams_decode_everywhere(ctx, pkg, ora, zdec, ref_cli, tmp_pat
                 got += out
         assert got == data, name
         assert ctx.decompress_4mz(stream) == data, name
+        assert ora.decompress_4mz(stream, len(data)) == (len(data), data), name          # the strict oracle
         src, out = tmp_path / "s.4mz", tmp_path / "s.out"
         src.write_bytes(stream)
         subprocess.run([ref_cli, "-f", "-q", "-q", "-z", "-d", str(src), str(out)], check=True)
