@@ -10,8 +10,9 @@ stream is decompressed again (index parse, XXH32 verify, LZ4 decode), everything
 `value` = uncompressed bytes of the batch / (compress time + decompress time), summed over GPUs.
 `e2e` is the same round trip through the host-buffer C-ABI calls (fourmc_4mc_compress_host /
 fourmc_4mc_decompress_host) with pinned host buffers, PCIe copies inside the timed region, measured twice:
-call after call, and with the writer call of step i+1 running beside the reader call of step i (two contexts,
-two host threads: both PCIe directions busy); `e2e.value` is the better of the two, both are in the line.
+`e2e.value` is call after call; `e2e.pipelined` repeats the K round trips with the writer call of step i+1 running
+beside the reader call of step i (two contexts, two host threads) and `e2e.pcie` times plain copies over the same
+pinned buffers (each direction alone, both at once) -- together they show how much of the link the calls use.
 One process per GPU (torchrun); ranks own disjoint page ranges of the input and exchange only the
 block-length index (one NCCL all-gather per step) -- weak scaling.
 """
@@ -510,13 +511,35 @@ def main_ours(args):
         pip = {"value": world * en * args.steps / dt2 / 1e9, "ms_per_step": dt2 / args.steps * 1e3}
         if perr is not None or dt2 == float("inf"):
             pip = {"value": 0.0, "ms_per_step": None, "error": perr or "failed on another rank"}
-        best = pip if pip["value"] > seq["value"] else seq
-        e2e = {"value": best["value"], "unit": "GB/s", "h2d_bytes_per_step": en + ec,
-               "d2h_bytes_per_step": ec + en, "bytes_per_step": en, "ms_per_step": best["ms_per_step"],
-               "mode": "pipelined: writer call of step i+1 beside the reader call of step i (two contexts)" if best is pip
-                       else "sequential: writer call, then reader call",
-               "sequential": seq, "pipelined": pip,
-               "compress_GBps": seq["compress_GBps"], "decompress_GBps": seq["decompress_GBps"]}
+        # the link itself, same pinned buffers: one direction alone, then both at once (1 GiB pieces, two streams)
+        pn = min(en, 1 << 30)
+        d_a = torch.empty(pn, dtype=torch.uint8, device="cuda")
+        d_b = torch.empty(pn, dtype=torch.uint8, device="cuda")
+        s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def link(h2d, d2h, reps=4):
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            for _ in range(reps):
+                if h2d:
+                    with torch.cuda.stream(s_a):
+                        d_a.copy_(h_in[:pn], non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(s_b):
+                        h_out[:pn].copy_(d_b, non_blocking=True)
+            torch.cuda.synchronize()
+            return (int(h2d) + int(d2h)) * reps * pn / (time.perf_counter() - t) / 1e9
+        link(True, True, 1)
+        pcie = {"h2d_GBps": link(True, False), "d2h_GBps": link(False, True), "both_GBps": link(True, True)}
+        del d_a, d_b
+        moved = (2 * en + 2 * ec) * args.steps / dt / 1e9      # bytes over the link per second, this rank
+        pcie["e2e_link_GBps"] = moved
+        pcie["e2e_frac_of_both"] = moved / pcie["both_GBps"]
+        e2e = {"value": seq["value"], "unit": "GB/s", "h2d_bytes_per_step": en + ec,
+               "d2h_bytes_per_step": ec + en, "bytes_per_step": en, "ms_per_step": seq["ms_per_step"],
+               "compress_GBps": seq["compress_GBps"], "decompress_GBps": seq["decompress_GBps"],
+               "mode": "writer call, then reader call, per step",
+               "pipelined": pip, "pcie": pcie}
         del h_in, h_comp, h_comp2, h_out
 
     cpu = None

@@ -392,3 +392,58 @@ def test_randomized_round_trips_all_levels_both_containers(ctx, ora, pkg):
                     got += back.raw
                 pos += 12 + c
             assert got == data, (case, kind, n, level)
+
+
+@pytest.mark.parametrize("codec", ["4mc", "4mz"])
+def test_sampled_blocks_of_a_large_run_decode_with_the_reference_cli(ctx, ora, pkg, ref_cli, tmp_path, codec):
+    """SURVEY.md 8(d) verification at bench size: 16 GiB compressed on the device (4096 blocks, the bench's step),
+    64 randomly sampled block records re-assembled into a valid stream (header / EOS / footer regenerated from
+    the sampled lengths -- blocks are independent) -> reference `4mc -d` -> compared with the regenerated
+    originals; the records' checksums against the CPU XXH32; the whole run decoded again on the device."""
+    import numpy as np
+    import torch
+    nb, blk = 4096, 4 * 1024 * 1024
+    n = nb * blk
+    zst = codec == "4mz"
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    cap = pkg.lib().fourmc_4mc_bound(n)
+    comp = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    size = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lens = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.gen_device(src.data_ptr(), n // 4096)
+    (ctx.compress_4mz_device if zst else ctx.compress_device)(src.data_ptr(), n, comp.data_ptr(), cap, size.data_ptr(),
+                                                              d_block_lens=lens.data_ptr())
+    ctx.sync()
+    torch.cuda.synchronize()
+    hl = lens.cpu().numpy().astype(np.int64)
+    offs = 12 + np.concatenate(([0], np.cumsum(hl)[:-1]))
+    assert int(size.item()) == 12 + int(hl.sum()) + 12 + 20 + 4 * nb
+    picks = sorted(random.Random(0x5A).sample(range(nb), 64))
+    records = [bytes(comp[int(offs[b]):int(offs[b] + hl[b])].cpu().numpy().tobytes()) for b in picks]
+    for b, rec in zip(picks, records):
+        u, c, ck = (int.from_bytes(rec[i:i + 4], "big") for i in (0, 4, 8))
+        assert u == blk and c == len(rec) - 12 and c < u
+        assert ck == ora.xxh32(rec[12:])
+    # header + EOS + footer for the sampled blocks, built by the library from their lengths
+    sl = torch.tensor([len(r) for r in records], dtype=torch.int32, device="cuda")
+    head = torch.zeros(12, dtype=torch.uint8, device="cuda")
+    tail = torch.zeros(12 + 20 + 4 * len(picks), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    (ctx.build_index_4mz_device if zst else ctx.build_index_device)(sl.data_ptr(), len(picks), head.data_ptr(), tail.data_ptr())
+    ctx.sync()
+    stream = head.cpu().numpy().tobytes() + b"".join(records) + tail.cpu().numpy().tobytes()
+    want = b"".join(gen_logtext(pkg, blk, first_page=b * 1024) for b in picks)
+    p, q = tmp_path / "s.bin", tmp_path / "s.out"
+    p.write_bytes(stream)
+    subprocess.run([ref_cli, "-f", "-q", "-q"] + (["-z"] if zst else []) + ["-d", str(p), str(q)], check=True)
+    assert q.read_bytes() == want
+    assert (ora.decompress_4mz if zst else ora.decompress_4mc)(stream, len(want)) == (len(want), want)
+    # and the whole 16 GiB back on the device
+    out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    res = torch.zeros(2, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    (ctx.decompress_4mz_device if zst else ctx.decompress_device)(comp.data_ptr(), int(size.item()), out.data_ptr(), n, res.data_ptr())
+    ctx.sync()
+    assert res.cpu().tolist() == [n, -1]
+    assert torch.equal(out, src)
