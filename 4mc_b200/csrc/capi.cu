@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "blockstream.h"
 #include "../../include/fourmc.h"
 #include "container.cuh"
 #include "fourmc_gen.h"
@@ -1266,6 +1267,112 @@ long long fourmc_4mc_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
 long long fourmc_4mz_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, void *out, size_t out_capacity)
 {
     return decompress_host_impl(ctx, CODEC_ZSTD, in, n, out, out_capacity);
+}
+
+// ---- raw codec streams: Hadoop's block-stream framing around the per-block natives ----------
+// Lz4Codec.java:95-104,128-138 / ZstdCodec.java:103-112,136-146 -> BlockCompressorStream / BlockDecompressorStream.
+// The framing (blockstream.h) is host code; chunks are compressed through the per-block calls (one native call per
+// chunk, as the Java stream drives them) and decompressed as ONE batch when the stream is the reference writer's.
+
+namespace {
+
+long long bs_lz4_compress(void *u, int level, const uint8_t *src, uint32_t n, uint8_t *dst, size_t cap)
+{
+    // LZ4_compress(in, out, n) with a bound-sized destination: native/jniCompressor.c:91
+    const int c = (int)std::min<size_t>(cap, (size_t)fourmc_lz4_compress_bound((int)n));
+    return fourmc_lz4_compress((fourmc_ctx *)u, level, src, (int)n, dst, c);
+}
+long long bs_lz4_decompress(void *u, const uint8_t *src, uint32_t c, uint8_t *dst, uint32_t cap)
+{
+    return fourmc_lz4_decompress_safe((fourmc_ctx *)u, src, (int)c, dst, (int)cap);       // native/jniDecompressor.c:88
+}
+long long bs_zstd_compress(void *u, int level, const uint8_t *src, uint32_t n, uint8_t *dst, size_t cap)
+{
+    const long long r = fourmc_zstd_compress((fourmc_ctx *)u, level, src, n, dst, cap);     // native/jniZstdCompressor.c:93
+    return r == 0 ? FOURMC_E_GENERIC : r;
+}
+long long bs_zstd_decompress(void *u, const uint8_t *src, uint32_t c, uint8_t *dst, uint32_t cap)
+{
+    return fourmc_zstd_decompress((fourmc_ctx *)u, src, c, dst, cap);                       // native/jniZstdDecompressor.c:90
+}
+
+fbs::Codec bs_codec(fourmc_ctx *ctx, int codec)
+{
+    if (codec == CODEC_ZSTD)
+        return fbs::Codec{ctx, (uint32_t)fourmc_zstd_compress_bound(fbs::BUFFER), bs_zstd_compress, bs_zstd_decompress};
+    return fbs::Codec{ctx, (uint32_t)fourmc_lz4_compress_bound((int)fbs::BUFFER), bs_lz4_compress, bs_lz4_decompress};
+}
+
+// All chunks at once.  Returns the decoded size, or 1 when the prediction did not hold (the caller then runs the
+// serial reader, whose verdict is the reference's), or a negative FOURMC_E_*.
+long long bs_decode_batch(fourmc_ctx *ctx, int codec, const uint8_t *in, size_t n, const std::vector<fbs::Chunk> &chunks,
+                          size_t total, uint8_t *out)
+{
+    const uint32_t nb = (uint32_t)chunks.size();
+    if (nb == 0) return 0;
+    cudaStream_t st = ctx->stream;
+    DecWs &ws = ctx->dec[0];
+    int r;
+    if ((r = ensure(ctx, ctx->stage_in[0], n + 64))) return r;
+    if ((r = ensure(ctx, ctx->stage_out[0], total + 64))) return r;
+    if ((r = ensure(ctx, ws.desc, (size_t)nb * sizeof(BlockDesc)))) return r;
+    if ((r = ensure(ctx, ws.status, nb))) return r;
+    if ((r = ensure(ctx, ws.outsize, (size_t)nb * 4))) return r;
+    std::vector<BlockDesc> hd(nb);
+    size_t chunk_base = 0;
+    for (uint32_t i = 0; i < nb; ++i) {
+        hd[i].src = (const uint8_t *)ctx->stage_in[0].p + chunks[i].src_off;
+        hd[i].dst = (uint8_t *)ctx->stage_out[0].p + chunks[i].dst_off;
+        hd[i].csize = chunks[i].clen; hd[i].usize = chunks[i].usize;
+        hd[i].chunk_base = (uint32_t)chunk_base; hd[i].stored = 0;            // a chunk is never raw in this format
+        chunk_base += (chunks[i].clen + 15 + LZ4_CHUNK - 1) / LZ4_CHUNK;
+    }
+    if (chunk_base > 0xfffffff0ull) return 1;
+    CK(cudaMemcpyAsync(ctx->stage_in[0].p, in, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ws.desc.p, hd.data(), (size_t)nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));                                            // hd is pageable and about to go away
+    CK(cudaMemsetAsync(ws.status.p, 0, nb, st));
+    if ((r = dec_blocks(ctx, st, ws, nb, chunk_base, 0, (int32_t *)ws.outsize.p, nullptr, nullptr, codec))) return r;
+    std::vector<int32_t> sizes(nb);
+    CK(cudaMemcpyAsync(sizes.data(), ws.outsize.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < nb; ++i)
+        if (sizes[i] != (int32_t)chunks[i].usize) return 1;
+    CK(cudaMemcpyAsync(out, ctx->stage_out[0].p, total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return (long long)total;
+}
+
+}  // namespace
+
+size_t fourmc_blockstream_bound(int zstd, size_t n, size_t write_size)
+{
+    const fbs::Codec c = bs_codec(nullptr, zstd ? CODEC_ZSTD : CODEC_LZ4);
+    return fbs::bound(c, n, write_size);
+}
+
+long long fourmc_blockstream_compress_host(fourmc_ctx *ctx, int zstd, int level, const void *in, size_t n, size_t write_size,
+                                           void *out, size_t out_capacity)
+{
+    if (!ctx) return FOURMC_E_ARG;
+    const fbs::Codec c = bs_codec(ctx, zstd ? CODEC_ZSTD : CODEC_LZ4);
+    return fbs::compress(c, level, (const uint8_t *)in, n, write_size, (uint8_t *)out, out_capacity);
+}
+
+long long fourmc_blockstream_decompress_host(fourmc_ctx *ctx, int zstd, const void *in, size_t n, void *out, size_t out_capacity)
+{
+    if (!ctx || (!in && n) || (!out && out_capacity)) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int codec = zstd ? CODEC_ZSTD : CODEC_LZ4;
+    const fbs::Codec c = bs_codec(ctx, codec);
+    std::vector<fbs::Chunk> chunks;
+    size_t total = 0;
+    const bool serial_only = getenv("FOURMC_BS_SERIAL") != nullptr;          // tests: force the chunk-by-chunk reader
+    if (!serial_only && fbs::predict_chunks(c, (const uint8_t *)in, n, chunks, &total) && total <= out_capacity) {
+        const long long r = bs_decode_batch(ctx, codec, (const uint8_t *)in, n, chunks, total, (uint8_t *)out);
+        if (r != 1) return r;
+    }
+    return fbs::decompress(c, (const uint8_t *)in, n, (uint8_t *)out, out_capacity);
 }
 
 // ---- block index and splits: the step either side of the path (BASELINE.json configs[4]) ------

@@ -229,6 +229,19 @@ int fourmc_gen_device(fourmc_ctx *ctx, void *stream, int kind, uint64_t seed,
                       uint64_t first_page, uint64_t n_pages, void *d_out);
 int fourmc_gen_host(int kind, uint64_t seed, uint64_t first_page, uint64_t n_pages, void *out);
 
+/* ---- raw codec streams (Hadoop block-stream framing): Lz4Codec / ZstdCodec and their level variants ----------
+ * Lz4Codec.java:95-104 (createOutputStream -> BlockCompressorStream(out, compressor, 4 MiB, compressBound(4 MiB) -
+ * 4 MiB)), :128-138 (createInputStream -> BlockDecompressorStream(in, decompressor, 4 MiB)); ZstdCodec.java:103-112,
+ * :136-146.  Wire format and writer / reader rules: 4mc_b200/csrc/blockstream.h.  `zstd`: 0 = LZ4 chunks, 1 = zstd
+ * frames; level 1..4 as in the per-block calls; write_size = the size of the application's write() calls, which
+ * decides where blocks are cut (0 = one write with everything).  Host pointers.  Return the stream / decoded size
+ * or a negative FOURMC_E_*. */
+size_t fourmc_blockstream_bound(int zstd, size_t n, size_t write_size);
+long long fourmc_blockstream_compress_host(fourmc_ctx *ctx, int zstd, int level, const void *in, size_t n,
+                                           size_t write_size, void *out, size_t out_capacity);
+long long fourmc_blockstream_decompress_host(fourmc_ctx *ctx, int zstd, const void *in, size_t n,
+                                             void *out, size_t out_capacity);
+
 #ifdef __cplusplus
 }
 #endif
