@@ -247,9 +247,10 @@ int ensure_ztables(fourmc_ctx *ctx)
 // d_in[0..n) -> block records back to back at d_span (block b at d_span + off[b], off[0] = base).
 // raw_limit >= 0 selects the bare-block mode of the per-block API (single block, no header use).
 int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8_t *d_in, size_t n,
-             uint8_t *d_out_base, uint64_t base, uint32_t *d_block_lens_out, int64_t raw_limit)
+             uint8_t *d_out_base, uint64_t base, uint32_t *d_block_lens_out, int64_t raw_limit,
+             uint32_t block_bytes = FOURMC_BLOCKSIZE)
 {
-    const uint32_t nb = blocks_of(n);
+    const uint32_t nb = (uint32_t)((n + block_bytes - 1) / block_bytes);
     if (nb == 0) {
         int r;
         if ((r = ensure(ctx, ws.misc, 64))) return r;
@@ -285,6 +286,7 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     P.slot_bytes = slot_bytes;
     P.depth = depth; P.lazy = depth > 0;
     P.region_bytes = region_bytes; P.regions_per_block = rpb;
+    P.block_bytes = block_bytes;
     if (P.depth > 0) {
         const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
         KL("lz4_region_chain_kernel", st, lz4_region_kernel<false, true><<<grid, ENC_CHAIN_THREADS, ENC_SMEM_CHAIN, st>>>(P));
@@ -294,13 +296,13 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     }
     uint32_t *lens = d_block_lens_out ? d_block_lens_out : (uint32_t *)ws.lens.p;
     KL("lz4_block_size_kernel", st, lz4_block_size_kernel<<<(nb + 127) / 128, 128, 0, st>>>((const RegionMeta *)ws.meta.p, nb, n,
-                                                           (BlockPlan *)ws.plan.p, lens, raw_limit, rpb));
+                                                           (BlockPlan *)ws.plan.p, lens, raw_limit, rpb, block_bytes));
     KL("scan_lens_kernel", st, scan_lens_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, base, (uint64_t *)ws.off.p,
                                                  (uint64_t *)((uint8_t *)ws.misc.p + 8)));
     KL("lz4_block_write_kernel", st, lz4_block_write_kernel<<<nb, ENC_WRITE_THREADS, 0, st>>>(d_in, (const uint8_t *)ws.scratch.p,
                                                              (const RegionMeta *)ws.meta.p, (const BlockPlan *)ws.plan.p,
                                                              (const uint64_t *)ws.off.p, d_out_base, raw_limit >= 0 ? 1 : 0,
-                                                             rpb, region_bytes, slot_bytes));
+                                                             rpb, region_bytes, slot_bytes, block_bytes));
     return FOURMC_OK;
 }
 
@@ -1351,11 +1353,75 @@ size_t fourmc_blockstream_bound(int zstd, size_t n, size_t write_size)
     return fbs::bound(c, n, write_size);
 }
 
+// LZ4 writer, all chunks at once: possible when every chunk but the last has the same size (a constant write size,
+// or one large write), since the encode kernels then see the input as blocks of `chunk` bytes instead of 4 MiB.
+// Returns the stream size, 1 when the plan is not uniform (the caller goes chunk by chunk), or a negative FOURMC_E_*.
+static long long bs_encode_batch_lz4(fourmc_ctx *ctx, const fbs::Codec &c, int level, const uint8_t *in, size_t n,
+                                     const std::vector<fbs::Block> &blocks, bool trailing_zero, uint8_t *out, size_t cap)
+{
+    const uint32_t MAX = fbs::max_input(c);
+    struct Piece { uint32_t len; bool first; uint32_t raw; };
+    std::vector<Piece> pieces;
+    for (const fbs::Block &b : blocks)
+        for (uint32_t done = 0; done < b.raw;) {
+            const uint32_t len = std::min(MAX, b.raw - done);
+            pieces.push_back(Piece{len, done == 0, b.raw});
+            done += len;
+        }
+    if (pieces.size() < 2) return 1;
+    const uint32_t chunk = pieces[0].len;
+    for (size_t i = 0; i + 1 < pieces.size(); ++i) if (pieces[i].len != chunk) return 1;
+    if (pieces.back().len > chunk || (chunk & 15)) return 1;       // 16-byte multiples keep the regions' bulk copies aligned
+    const uint32_t nb = (uint32_t)pieces.size();
+    const size_t rec_bound = 12 + (size_t)fourmc_lz4_compress_bound((int)chunk);
+    cudaStream_t st = ctx->stream;
+    EncWs &ws = ctx->enc[0];
+    int r;
+    if ((r = ensure(ctx, ctx->stage_in[0], n + 64))) return r;
+    if ((r = ensure(ctx, ctx->stage_out[0], (size_t)nb * rec_bound + 64))) return r;
+    CK(cudaMemcpyAsync(ctx->stage_in[0].p, in, n, cudaMemcpyHostToDevice, st));
+    // records (12-byte header + payload) back to back from stage_out + 4: payloads 16-byte aligned for the first one only,
+    // the write kernel copes with any alignment
+    uint8_t *d_rec = (uint8_t *)ctx->stage_out[0].p + 4;
+    if ((r = enc_span(ctx, st, ws, level, (const uint8_t *)ctx->stage_in[0].p, n, d_rec, 0, nullptr,
+                      (int64_t)fourmc_lz4_compress_bound((int)chunk), chunk)))
+        return r;
+    std::vector<BlockPlan> plan(nb);
+    std::vector<uint64_t> off(nb);
+    CK(cudaMemcpyAsync(plan.data(), ws.plan.p, (size_t)nb * sizeof(BlockPlan), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(off.data(), ws.off.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    size_t op = 0;
+    for (uint32_t i = 0; i < nb; ++i) {
+        if (plan[i].stored || plan[i].usize != pieces[i].len) return fail(ctx, FOURMC_E_GENERIC, "block-stream chunk did not fit its bound");
+        const uint32_t csz = plan[i].payload;
+        if (cap - op < (pieces[i].first ? 8u : 4u) || cap - op - (pieces[i].first ? 8u : 4u) < csz) return FOURMC_E_OUTPUT;
+        if (pieces[i].first) { fbs::put32(out + op, pieces[i].raw); op += 4; }
+        fbs::put32(out + op, csz); op += 4;
+        CK(cudaMemcpyAsync(out + op, d_rec + off[i] + 12, csz, cudaMemcpyDeviceToHost, st));
+        op += csz;
+    }
+    if (trailing_zero) {
+        if (cap - op < 4) return FOURMC_E_OUTPUT;
+        fbs::put32(out + op, 0); op += 4;
+    }
+    CK(cudaStreamSynchronize(st));
+    return (long long)op;
+}
+
 long long fourmc_blockstream_compress_host(fourmc_ctx *ctx, int zstd, int level, const void *in, size_t n, size_t write_size,
                                            void *out, size_t out_capacity)
 {
-    if (!ctx) return FOURMC_E_ARG;
+    if (!ctx || (!in && n) || !out) return FOURMC_E_ARG;
     const fbs::Codec c = bs_codec(ctx, zstd ? CODEC_ZSTD : CODEC_LZ4);
+    if (!zstd && !getenv("FOURMC_BS_SERIAL")) {
+        CK(cudaSetDevice(ctx->device));
+        std::vector<fbs::Block> blocks;
+        bool trailing_zero = false;
+        fbs::plan_blocks(c, n, write_size, blocks, &trailing_zero);
+        const long long r = bs_encode_batch_lz4(ctx, c, level, (const uint8_t *)in, n, blocks, trailing_zero, (uint8_t *)out, out_capacity);
+        if (r != 1) return r;
+    }
     return fbs::compress(c, level, (const uint8_t *)in, n, write_size, (uint8_t *)out, out_capacity);
 }
 

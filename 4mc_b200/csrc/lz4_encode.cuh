@@ -81,6 +81,7 @@ struct EncParams {
     int lazy;                // chain parse: one-step lazy evaluation
     uint32_t region_bytes;   // new bytes per region: ENC_REGION (Fast) or ENC_CHAIN_REGION (chain)
     uint32_t regions_per_block;
+    uint32_t block_bytes;    // bytes per block: 0 = FOURMC_BLOCKSIZE (the containers); the raw codec streams cut smaller chunks
 };
 
 __device__ __forceinline__ uint32_t enc_hash(uint32_t v) { return (v * 2654435761u) >> (32 - ENC_HASH_BITS); }
@@ -173,8 +174,9 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
 
         // ---- locate the region
         const uint32_t blk = rg / P.regions_per_block, rib = rg % P.regions_per_block;
-        const uint64_t blk_off = (uint64_t)blk * FOURMC_BLOCKSIZE;
-        const uint32_t blk_len = (uint32_t)min((uint64_t)FOURMC_BLOCKSIZE, P.n - blk_off);
+        const uint32_t block_bytes = P.block_bytes ? P.block_bytes : (uint32_t)FOURMC_BLOCKSIZE;
+        const uint64_t blk_off = (uint64_t)blk * block_bytes;
+        const uint32_t blk_len = (uint32_t)min((uint64_t)block_bytes, P.n - blk_off);
         const uint32_t r_new = rib * P.region_bytes;               // first new byte, within the block
         if (r_new >= blk_len) {                                    // region beyond a short last block
             if (tid == 0) P.meta[rg] = RegionMeta{0, 0, 0, 0};
@@ -521,12 +523,13 @@ struct BlockPlan {              // produced by E2, consumed by the index scan an
 // raw_limit >= 0: bare LZ4 block for the per-block API; "stored" then means "does not fit in
 // raw_limit bytes" (LZ4_compress_default returns 0, native/lz4/lz4.c:1290-1300).
 __global__ void lz4_block_size_kernel(const RegionMeta *meta, uint32_t n_blocks, uint64_t n,
-                                      BlockPlan *plan, uint32_t *block_lens, int64_t raw_limit, uint32_t regions_per_block)
+                                      BlockPlan *plan, uint32_t *block_lens, int64_t raw_limit, uint32_t regions_per_block,
+                                      uint32_t block_bytes = FOURMC_BLOCKSIZE)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
-    const uint64_t blk_off = (uint64_t)b * FOURMC_BLOCKSIZE;
-    const uint32_t u = (uint32_t)min((uint64_t)FOURMC_BLOCKSIZE, n - blk_off);
+    const uint64_t blk_off = (uint64_t)b * block_bytes;
+    const uint32_t u = (uint32_t)min((uint64_t)block_bytes, n - blk_off);
     const RegionMeta *m = meta + (size_t)b * regions_per_block;
     uint32_t carry = 0, c = 0;
     for (uint32_t r = 0; r < regions_per_block; r++) {
@@ -578,7 +581,8 @@ constexpr int ENC_WRITE_THREADS = 256;
 __global__ void __launch_bounds__(ENC_WRITE_THREADS)
 lz4_block_write_kernel(const uint8_t *in, const uint8_t *scratch, const RegionMeta *meta,
                        const BlockPlan *plan, const uint64_t *block_off, uint8_t *out_base, int raw_mode,
-                       uint32_t regions_per_block, uint32_t region_bytes, uint32_t slot_bytes)
+                       uint32_t regions_per_block, uint32_t region_bytes, uint32_t slot_bytes,
+                       uint32_t block_bytes = FOURMC_BLOCKSIZE)
 {
     __shared__ __align__(16) uint32_t s_stage[XXH_WARP_SMEM_WORDS];
     __shared__ uint32_t s_dst[ENC_MAX_REGIONS_PER_BLOCK + 1];   // payload offset of each region's piece
@@ -586,7 +590,7 @@ lz4_block_write_kernel(const uint8_t *in, const uint8_t *scratch, const RegionMe
 
     const uint32_t b = blockIdx.x;
     const BlockPlan p = plan[b];
-    const uint64_t blk_off = (uint64_t)b * FOURMC_BLOCKSIZE;
+    const uint64_t blk_off = (uint64_t)b * block_bytes;
     const uint8_t *src = in + blk_off;
     uint8_t *rec = out_base + block_off[b];
     uint8_t *pay = rec + 12;

@@ -188,11 +188,16 @@ def _gpu_api(pkg):
     return L
 
 
-def gpu_compress(ctx, pkg, data, zstd=0, level=1, ws=0):
+def gpu_compress(ctx, pkg, data, zstd=0, level=1, ws=0, serial=False):
     L = _gpu_api(pkg)
     cap = L.fourmc_blockstream_bound(zstd, len(data), ws)
     out = C.create_string_buffer(cap)
-    r = L.fourmc_blockstream_compress_host(ctx.handle, zstd, level, bytes(data), len(data), ws, out, cap)
+    if serial:
+        os.environ["FOURMC_BS_SERIAL"] = "1"          # chunk by chunk through the per-block call, like the Java stream
+    try:
+        r = L.fourmc_blockstream_compress_host(ctx.handle, zstd, level, bytes(data), len(data), ws, out, cap)
+    finally:
+        os.environ.pop("FOURMC_BS_SERIAL", None)
     assert r > 0, (r, ctx.last_error())
     return out.raw[:r]
 
@@ -214,7 +219,7 @@ def gpu_decompress(ctx, pkg, stream, cap, zstd=0, serial=False):
 def test_gpu_streams_round_trip_and_cross_decode(ctx, pkg, bs, zstd):
     rnd = random.Random(5).randbytes(MAX_LZ4 + 100000)                 # incompressible: chunks larger than their input
     cases = [(b"", 0), (b"A", 0), (gen_logtext_cached(70000), 1000), (gen_logtext_cached(9 * MIB + 321), 0),
-             (gen_logtext_cached(9 * MIB + 321), 65536), (rnd, 0), (gen_logtext_cached(5 * MIB) + rnd[:MIB] + bytes(3 * MIB), MIB)]
+             (gen_logtext_cached(9 * MIB + 321), 65536), (gen_logtext_cached(12 * MIB), MAX_LZ4), (rnd, 0), (rnd + rnd, 65536), (gen_logtext_cached(5 * MIB) + rnd[:MIB] + bytes(3 * MIB), MIB)]
     mx = MAX_ZSTD if zstd else MAX_LZ4
     for data, ws in cases:
         for level in ((1, 3) if len(data) < 6 * MIB else (1,)):
@@ -224,6 +229,10 @@ def test_gpu_streams_round_trip_and_cross_decode(ctx, pkg, bs, zstd):
             assert bs.decompress(s, len(data), kind=zstd) == (len(data), data)          # CPU reader (oracle codec)
             assert gpu_decompress(ctx, pkg, s, len(data), zstd) == (len(data), data)      # batch
             assert gpu_decompress(ctx, pkg, s, len(data), zstd, serial=True) == (len(data), data)
+            if not zstd and level == 1:                                                  # the LZ4 writer has a batch path
+                s2 = gpu_compress(ctx, pkg, data, zstd, level, ws, serial=True)
+                assert [r for r, _ in walk(s2, mx)] == raws + ([0] if tz else [])
+                assert bs.decompress(s2, len(data)) == (len(data), data)
     assert gpu_compress(ctx, pkg, b"", zstd) == bytes(4)
 
 
