@@ -326,9 +326,10 @@ int zgroup_blocks()
 // per-region scratch (sequence arrays in, block bodies out: 160 KiB per 64 KiB region) stays
 // bounded; each group appends to the stream through a device-side carry (no host round trip).
 int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8_t *d_in, size_t n,
-                  uint8_t *d_out_base, uint64_t base, uint32_t *d_block_lens_out, int64_t raw_limit)
+                  uint8_t *d_out_base, uint64_t base, uint32_t *d_block_lens_out, int64_t raw_limit,
+                  uint32_t block_bytes = FOURMC_BLOCKSIZE)
 {
-    const uint32_t nb = blocks_of(n);
+    const uint32_t nb = (uint32_t)((n + block_bytes - 1) / block_bytes);
     int r;
     if ((r = ensure(ctx, ws.misc, 64))) return r;
     if (nb == 0) { CK(cudaMemsetAsync(ws.misc.p, 0, 64, st)); return FOURMC_OK; }
@@ -357,8 +358,8 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
     uint32_t *lens = d_block_lens_out ? d_block_lens_out : (uint32_t *)ws.lens.p;
     for (uint32_t g0 = 0; g0 < nb; g0 += G) {
         const uint32_t gb = std::min<uint32_t>(G, nb - g0);
-        const size_t goff = (size_t)g0 * FOURMC_BLOCKSIZE;
-        const size_t gn = std::min<size_t>(n - goff, (size_t)gb * FOURMC_BLOCKSIZE);
+        const size_t goff = (size_t)g0 * block_bytes;
+        const size_t gn = std::min<size_t>(n - goff, (size_t)gb * block_bytes);
         const uint32_t nreg = gb * rpb;
         if (g0) CK(cudaMemsetAsync(misc, 0, 4, st));
         EncParams P = {};
@@ -369,6 +370,7 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
         P.slot_bytes = fmz::ze_in_slot(region_bytes);
         P.depth = depth; P.lazy = depth > 0;
         P.region_bytes = region_bytes; P.regions_per_block = rpb;
+        P.block_bytes = block_bytes;
         if (P.depth > 0) {
             const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
             KL("lz4_region_chain_kernel", st, lz4_region_kernel<true, true><<<grid, ENC_CHAIN_THREADS, ENC_SMEM_CHAIN, st>>>(P));
@@ -380,15 +382,15 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
         Z.meta = (const RegionMeta *)ws.meta.p; Z.scratch_in = (const uint8_t *)ws.scratch.p;
         Z.scratch_out = (uint8_t *)ws.zout.p; Z.rout = (fmz::ZRegionOut *)ws.zrout.p;
         Z.tables = (const fmz::Tables *)ctx->ztables.p; Z.n = gn; Z.n_regions = nreg;
-        Z.region_bytes = region_bytes; Z.regions_per_block = rpb;
+        Z.region_bytes = region_bytes; Z.regions_per_block = rpb; Z.block_bytes = block_bytes;
         KL("zstd_entropy_kernel", st, zstd_entropy_kernel<<<nreg, fmz::ZE_THREADS, 0, st>>>(Z));
         KL("zstd_block_size_kernel", st, zstd_block_size_kernel<<<(gb + 127) / 128, 128, 0, st>>>(
-            (const fmz::ZRegionOut *)ws.zrout.p, gb, gn, (BlockPlan *)ws.plan.p + g0, lens + g0, raw_limit, region_bytes, rpb));
+            (const fmz::ZRegionOut *)ws.zrout.p, gb, gn, (BlockPlan *)ws.plan.p + g0, lens + g0, raw_limit, region_bytes, rpb, block_bytes));
         KL("scan_lens_carry_kernel", st, scan_lens_carry_kernel<<<1, SCAN_THREADS, 0, st>>>(
             lens + g0, gb, (uint64_t *)(misc + 24), (uint64_t *)ws.off.p + g0, (uint64_t *)(misc + 8)));
         KL("zstd_block_write_kernel", st, zstd_block_write_kernel<<<gb, ENC_WRITE_THREADS, 0, st>>>(
             d_in + goff, (const uint8_t *)ws.zout.p, (const fmz::ZRegionOut *)ws.zrout.p, (const BlockPlan *)ws.plan.p + g0,
-            (const uint64_t *)ws.off.p + g0, d_out_base, raw_limit >= 0 ? 1 : 0, region_bytes, rpb));
+            (const uint64_t *)ws.off.p + g0, d_out_base, raw_limit >= 0 ? 1 : 0, region_bytes, rpb, block_bytes));
     }
     return FOURMC_OK;
 }
@@ -1353,11 +1355,11 @@ size_t fourmc_blockstream_bound(int zstd, size_t n, size_t write_size)
     return fbs::bound(c, n, write_size);
 }
 
-// LZ4 writer, all chunks at once: possible when every chunk but the last has the same size (a constant write size,
+// Writer, all chunks at once: possible when every chunk but the last has the same size (a constant write size,
 // or one large write), since the encode kernels then see the input as blocks of `chunk` bytes instead of 4 MiB.
 // Returns the stream size, 1 when the plan is not uniform (the caller goes chunk by chunk), or a negative FOURMC_E_*.
-static long long bs_encode_batch_lz4(fourmc_ctx *ctx, const fbs::Codec &c, int level, const uint8_t *in, size_t n,
-                                     const std::vector<fbs::Block> &blocks, bool trailing_zero, uint8_t *out, size_t cap)
+static long long bs_encode_batch(fourmc_ctx *ctx, int codec, const fbs::Codec &c, int level, const uint8_t *in, size_t n,
+                                 const std::vector<fbs::Block> &blocks, bool trailing_zero, uint8_t *out, size_t cap)
 {
     const uint32_t MAX = fbs::max_input(c);
     struct Piece { uint32_t len; bool first; uint32_t raw; };
@@ -1373,7 +1375,8 @@ static long long bs_encode_batch_lz4(fourmc_ctx *ctx, const fbs::Codec &c, int l
     for (size_t i = 0; i + 1 < pieces.size(); ++i) if (pieces[i].len != chunk) return 1;
     if (pieces.back().len > chunk || (chunk & 15)) return 1;       // 16-byte multiples keep the regions' bulk copies aligned
     const uint32_t nb = (uint32_t)pieces.size();
-    const size_t rec_bound = 12 + (size_t)fourmc_lz4_compress_bound((int)chunk);
+    const size_t pay_bound = codec == CODEC_ZSTD ? fourmc_zstd_compress_bound(chunk) : (size_t)fourmc_lz4_compress_bound((int)chunk);
+    const size_t rec_bound = 12 + pay_bound;
     cudaStream_t st = ctx->stream;
     EncWs &ws = ctx->enc[0];
     int r;
@@ -1383,8 +1386,8 @@ static long long bs_encode_batch_lz4(fourmc_ctx *ctx, const fbs::Codec &c, int l
     // records (12-byte header + payload) back to back from stage_out + 4: payloads 16-byte aligned for the first one only,
     // the write kernel copes with any alignment
     uint8_t *d_rec = (uint8_t *)ctx->stage_out[0].p + 4;
-    if ((r = enc_span(ctx, st, ws, level, (const uint8_t *)ctx->stage_in[0].p, n, d_rec, 0, nullptr,
-                      (int64_t)fourmc_lz4_compress_bound((int)chunk), chunk)))
+    if ((r = (codec == CODEC_ZSTD ? enc_span_zstd : enc_span)(ctx, st, ws, level, (const uint8_t *)ctx->stage_in[0].p, n, d_rec, 0,
+                                                              nullptr, (int64_t)pay_bound, chunk)))
         return r;
     std::vector<BlockPlan> plan(nb);
     std::vector<uint64_t> off(nb);
@@ -1414,12 +1417,13 @@ long long fourmc_blockstream_compress_host(fourmc_ctx *ctx, int zstd, int level,
 {
     if (!ctx || (!in && n) || !out) return FOURMC_E_ARG;
     const fbs::Codec c = bs_codec(ctx, zstd ? CODEC_ZSTD : CODEC_LZ4);
-    if (!zstd && !getenv("FOURMC_BS_SERIAL")) {
+    if (!getenv("FOURMC_BS_SERIAL")) {
         CK(cudaSetDevice(ctx->device));
         std::vector<fbs::Block> blocks;
         bool trailing_zero = false;
         fbs::plan_blocks(c, n, write_size, blocks, &trailing_zero);
-        const long long r = bs_encode_batch_lz4(ctx, c, level, (const uint8_t *)in, n, blocks, trailing_zero, (uint8_t *)out, out_capacity);
+        const long long r = bs_encode_batch(ctx, zstd ? CODEC_ZSTD : CODEC_LZ4, c, level, (const uint8_t *)in, n, blocks, trailing_zero,
+                                            (uint8_t *)out, out_capacity);
         if (r != 1) return r;
     }
     return fbs::compress(c, level, (const uint8_t *)in, n, write_size, (uint8_t *)out, out_capacity);

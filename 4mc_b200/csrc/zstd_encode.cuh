@@ -54,6 +54,7 @@ struct ZEncParams {
     uint64_t n;                    // input bytes of the batch
     uint32_t n_regions;
     uint32_t region_bytes, regions_per_block;      // 65536 x 64 (Fast parse) or 32768 x 128 (chain parse)
+    uint32_t block_bytes;                          // 0 = FOURMC_BLOCKSIZE; smaller for the raw codec streams' chunks
 };
 
 __global__ void __launch_bounds__(fmz::ZE_THREADS) zstd_entropy_kernel(ZEncParams P)
@@ -61,8 +62,9 @@ __global__ void __launch_bounds__(fmz::ZE_THREADS) zstd_entropy_kernel(ZEncParam
     __shared__ fmz::ZShared sh;
     const uint32_t rg = blockIdx.x;
     const uint32_t blk = rg / P.regions_per_block, rib = rg % P.regions_per_block;
-    const uint64_t blk_off = (uint64_t)blk * FOURMC_BLOCKSIZE;
-    const uint32_t blk_len = (uint32_t)min((uint64_t)FOURMC_BLOCKSIZE, P.n - blk_off);
+    const uint32_t block_bytes = P.block_bytes ? P.block_bytes : (uint32_t)FOURMC_BLOCKSIZE;
+    const uint64_t blk_off = (uint64_t)blk * block_bytes;
+    const uint32_t blk_len = (uint32_t)min((uint64_t)block_bytes, P.n - blk_off);
     const uint32_t r_off = rib * P.region_bytes;
     if (r_off >= blk_len) return;                                  // region beyond a short last block
     const RegionMeta m = P.meta[rg];
@@ -83,12 +85,13 @@ __global__ void __launch_bounds__(fmz::ZE_THREADS) zstd_entropy_kernel(ZEncParam
 // per-block API; "stored" then means "does not fit in raw_limit bytes".
 __global__ void zstd_block_size_kernel(const fmz::ZRegionOut *rout, uint32_t n_blocks, uint64_t n,
                                        BlockPlan *plan, uint32_t *block_lens, int64_t raw_limit,
-                                       uint32_t region_bytes, uint32_t regions_per_block)
+                                       uint32_t region_bytes, uint32_t regions_per_block,
+                                       uint32_t block_bytes = FOURMC_BLOCKSIZE)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
-    const uint64_t blk_off = (uint64_t)b * FOURMC_BLOCKSIZE;
-    const uint32_t u = (uint32_t)min((uint64_t)FOURMC_BLOCKSIZE, n - blk_off);
+    const uint64_t blk_off = (uint64_t)b * block_bytes;
+    const uint32_t u = (uint32_t)min((uint64_t)block_bytes, n - blk_off);
     const fmz::ZRegionOut *r = rout + (size_t)b * regions_per_block;
     uint32_t c = fmz::ZE_FRAME_HDR;
     const uint32_t nreg = (u + region_bytes - 1) / region_bytes;
@@ -114,14 +117,14 @@ __global__ void zstd_block_size_kernel(const fmz::ZRegionOut *rout, uint32_t n_b
 __global__ void __launch_bounds__(ENC_WRITE_THREADS)
 zstd_block_write_kernel(const uint8_t *in, const uint8_t *scratch_out, const fmz::ZRegionOut *rout,
                         const BlockPlan *plan, const uint64_t *block_off, uint8_t *out_base, int raw_mode,
-                        uint32_t region_bytes, uint32_t regions_per_block)
+                        uint32_t region_bytes, uint32_t regions_per_block, uint32_t block_bytes = FOURMC_BLOCKSIZE)
 {
     __shared__ __align__(16) uint32_t s_stage[XXH_WARP_SMEM_WORDS];
     __shared__ uint32_t s_dst[ENC_MAX_REGIONS_PER_BLOCK + 1];
 
     const uint32_t b = blockIdx.x;
     const BlockPlan p = plan[b];
-    const uint64_t blk_off = (uint64_t)b * FOURMC_BLOCKSIZE;
+    const uint64_t blk_off = (uint64_t)b * block_bytes;
     const uint8_t *src = in + blk_off;
     uint8_t *rec = out_base + block_off[b];
     uint8_t *pay = rec + 12;

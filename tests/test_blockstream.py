@@ -229,10 +229,10 @@ def test_gpu_streams_round_trip_and_cross_decode(ctx, pkg, bs, zstd):
             assert bs.decompress(s, len(data), kind=zstd) == (len(data), data)          # CPU reader (oracle codec)
             assert gpu_decompress(ctx, pkg, s, len(data), zstd) == (len(data), data)      # batch
             assert gpu_decompress(ctx, pkg, s, len(data), zstd, serial=True) == (len(data), data)
-            if not zstd and level == 1:                                                  # the LZ4 writer has a batch path
+            if level == 1:                                                               # the writer's batch path vs chunk by chunk
                 s2 = gpu_compress(ctx, pkg, data, zstd, level, ws, serial=True)
                 assert [r for r, _ in walk(s2, mx)] == raws + ([0] if tz else [])
-                assert bs.decompress(s2, len(data)) == (len(data), data)
+                assert bs.decompress(s2, len(data), kind=zstd) == (len(data), data)
     assert gpu_compress(ctx, pkg, b"", zstd) == bytes(4)
 
 

@@ -41,7 +41,7 @@ def main():
         t4 = time.perf_counter()
         del os.environ["FOURMC_BS_SERIAL"]
         assert d == n
-        print(f"{'zstd' if zstd else 'lz4'} {n / 2**30:.2f} GiB, 64 KiB writes: ratio {n / c:.3f}  compress ({'chunk by chunk' if zstd else 'one batch'}) {n / (t1 - t0) / 1e9:.2f} GB/s  "
+        print(f"{'zstd' if zstd else 'lz4'} {n / 2**30:.2f} GiB, 64 KiB writes: ratio {n / c:.3f}  compress (one batch) {n / (t1 - t0) / 1e9:.2f} GB/s  "
               f"decompress (one batch) {n / (t2 - t1) / 1e9:.2f} GB/s  decompress (chunk by chunk) {n / (t4 - t3) / 1e9:.2f} GB/s")
     assert out.raw == src.raw
     print("equal: True")
