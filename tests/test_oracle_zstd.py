@@ -78,3 +78,57 @@ def test_live_reference_frames(zora, ref, pkg):
             c = ref.ZSTD_compress(out, cap, data, len(data), lvl)
             assert c < cap
             assert zora.frame(out.raw[:c], len(data)) == (len(data), data), (len(data), lvl)
+
+
+def test_mutated_frames_against_the_live_reference(zora, ref, pkg):
+    """Seeded mutations (bit flips, byte substitutions, truncations, insertions) of frames the reference wrote:
+    the strict oracle never accepts what the reference rejects, and where both accept the bytes agree."""
+    ref.ZSTD_compress.restype = C.c_size_t
+    ref.ZSTD_compress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]
+    ref.ZSTD_decompress.restype = C.c_size_t
+    ref.ZSTD_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    ref.ZSTD_isError.restype = C.c_uint
+    ref.ZSTD_isError.argtypes = [C.c_size_t]
+    rng = random.Random(0x0FAC)
+    text = gen_logtext(pkg, 300000)
+    frames = []
+    noisy = b"".join(rng.randbytes(rng.randrange(20, 400)) + text[k * 50:k * 50 + rng.randrange(8, 60)] * rng.randrange(1, 4)
+                     for k in range(300))                       # mostly raw literals: a flipped literal byte still decodes
+    for data in (text[:3000], text[:70000], text, bytes(rng.choice(b"abcd") for _ in range(50000)), b"q" * 40000, noisy,
+                 noisy[:5000]):
+        for lvl in (1, 3, 6):
+            cap = len(data) + 1024
+            out = C.create_string_buffer(cap)
+            c = ref.ZSTD_compress(out, cap, data, len(data), lvl)
+            assert c < cap
+            frames.append((out.raw[:c], len(data)))
+    both = strict_only = rejected = 0
+    for frame, n in frames:
+        for _ in range(120):
+            m = bytearray(frame)
+            kind = rng.randrange(4)
+            at = rng.randrange(len(m))
+            if kind == 0:
+                m[at] ^= 1 << rng.randrange(8)
+            elif kind == 1:
+                m[at] = rng.randrange(256)
+            elif kind == 2:
+                del m[at:]
+            else:
+                m[at:at] = bytes([rng.randrange(256)])
+            m = bytes(m)
+            cap = n + 64
+            back = C.create_string_buffer(cap)
+            r = ref.ZSTD_decompress(back, cap, m, len(m))
+            ro, oo = zora.frame(m, cap)
+            if ref.ZSTD_isError(r):
+                assert ro < 0, (m[:32].hex(), kind, at)
+                rejected += 1
+            elif ro >= 0:
+                assert ro == r and oo == back.raw[:r], (m[:32].hex(), kind, at)
+                both += 1
+            else:
+                strict_only += 1
+    print('both', both, 'strict_only', strict_only, 'rejected', rejected)
+    assert both > 40 and rejected > 500, (both, strict_only, rejected)
+    assert strict_only <= both // 2          # strictness may reject a tolerated frame, but not as a rule
