@@ -96,6 +96,9 @@ def lib() -> C.CDLL:
         "fourmc_index_align_slice_end": (C.c_int64, [vp, i32, C.c_int64, C.c_int64]),
         "fourmc_plan_splits": (i32, [vp, i32, C.c_int64, C.c_int64, vp, vp, i32]),
         "fourmc_read_split_lines_host": (C.c_longlong, [vp, vp, sz, C.c_int64, C.c_int64, vp, sz]),
+        "fourmc_blockstream_bound": (sz, [i32, sz, sz]),
+        "fourmc_blockstream_compress_host": (C.c_longlong, [vp, i32, i32, vp, sz, sz, vp, sz]),
+        "fourmc_blockstream_decompress_host": (C.c_longlong, [vp, i32, vp, sz, vp, sz]),
         "fourmc_gen_device": (i32, [vp, vp, i32, u64, u64, u64, vp]),
         "fourmc_gen_host": (i32, [i32, u64, u64, u64, vp]),
     }
@@ -270,6 +273,23 @@ class Context:
 
     def decompress_4mz_device(self, d_in: int, n: int, d_out: int, out_capacity: int, d_result: int, stream=None):
         self._check(lib().fourmc_4mz_decompress_device(self._h, stream, d_in, n, d_out, out_capacity, d_result))
+
+    # ---- raw codec streams: Lz4Codec / ZstdCodec over Hadoop's BlockCompressorStream framing ----
+    def compress_blockstream(self, data, zstd: bool = False, level: int = 1, write_size: int = 0) -> bytes:
+        """What `Lz4Codec.createOutputStream` (Lz4Codec.java:95-104; `ZstdCodec` with zstd=True) writes when the
+        application hands over `data` in write() calls of `write_size` bytes (0 = one call)."""
+        b = _buf(data)
+        cap = int(lib().fourmc_blockstream_bound(int(zstd), len(b), write_size))
+        out = C.create_string_buffer(cap)
+        rc = self._check(int(lib().fourmc_blockstream_compress_host(self._h, int(zstd), level, b, len(b), write_size, out, cap)))
+        return out.raw[:rc]
+
+    def decompress_blockstream(self, stream, capacity: int, zstd: bool = False) -> bytes:
+        """What `Lz4Codec.createInputStream` (Lz4Codec.java:128-138) reads back; `capacity` bounds the output."""
+        b = _buf(stream)
+        out = C.create_string_buffer(max(capacity, 1))
+        rc = self._check(int(lib().fourmc_blockstream_decompress_host(self._h, int(zstd), b, len(b), out, capacity)))
+        return out.raw[:rc]
 
     # ---- block index, splits, line records (FourMcBlockIndex / FourMcInputFormat / FourMcLineRecordReader) ----
     def read_index(self, stream_bytes) -> list[int]:
