@@ -484,6 +484,12 @@ def shard_blocks(n_blocks: int, world_size: int, rank: int) -> tuple[int, int]:
     return lo, min(n_blocks, lo + per)
 
 
+def shard_splits(n_splits: int, world_size: int, rank: int) -> list[int]:
+    """Indices of the input splits `rank` reads: round-robin, so that every rank gets splits from all over the file
+    (10 000 splits over 8 GPUs).  Splits are independent -- no collective on the read path."""
+    return list(range(rank, n_splits, world_size))
+
+
 def span_base_offsets(span_sizes: list[int]) -> list[int]:
     """File offset of every rank's span in the single output stream: rank r starts at
     12 (file header) + the spans of ranks < r (native/4mc.c:285-293 block offsets)."""
