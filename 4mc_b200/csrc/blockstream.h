@@ -82,13 +82,14 @@ inline void plan_blocks(const Codec &c, size_t n, size_t write_size, std::vector
     *trailing_zero = !open;
 }
 
-// Worst-case size of the stream plan_blocks + compress produce.
+// Worst-case size of the stream plan_blocks + compress produce.  A block is cut before the write that would overflow
+// MAX_INPUT_SIZE, so it holds at least max(write_size, MAX_INPUT_SIZE - write_size + 1) >= MAX_INPUT_SIZE / 2 bytes
+// (a large write is one block of ceil(len / MAX_INPUT_SIZE) chunks): at most 2n / MAX + 2 blocks whatever the write size.
 inline size_t bound(const Codec &c, size_t n, size_t write_size)
 {
+    (void)write_size;
     const uint32_t MAX = max_input(c);
-    if (write_size == 0 || write_size > n) write_size = n;
-    const size_t small = write_size ? std::min<size_t>(write_size, MAX) : MAX;
-    const size_t nblocks = n / std::max<size_t>(1, small) + 2, nchunks = n / MAX + nblocks + 1;
+    const size_t nblocks = 2 * (n / MAX) + 3, nchunks = n / MAX + nblocks + 1;
     return n + n / 255 + (n >> 8) + 4 + nblocks * 4 + nchunks * (4 + 64 + 16);
 }
 

@@ -141,6 +141,17 @@ def test_cpu_round_trip_and_prediction(bs, n, ws):
     assert total == n and sum(us) == n and len(us) == sum(len(c) for _, c in w)
 
 
+def test_bound_holds_for_any_write_size(bs):
+    data = gen_logtext_cached(9 * MIB + 321)
+    rnd = random.Random(11).randbytes(5 * MIB)                     # incompressible: every chunk grows
+    for ws in (1, 7, 4096, MAX_LZ4 // 2, MAX_LZ4 // 2 + 1, MAX_LZ4 - 1, MAX_LZ4, MAX_LZ4 + 1, 6 * MIB):
+        raws, tz = bs.plan(len(data), ws)
+        assert sum(raws) == len(data) and len(raws) <= 2 * (len(data) // MAX_LZ4) + 3
+        assert all(r >= min(MAX_LZ4 // 2, len(data)) for r in raws[:-1])
+    for ws in (0, 1000, MAX_LZ4, 3 * MIB):
+        assert len(bs.compress(rnd, ws)) <= bs.lib.bs_emul_bound(0, len(rnd), ws) < len(rnd) + len(rnd) // 100 + 4096
+
+
 def test_reader_rules(bs):
     data = gen_logtext_cached(200000)
     s = bs.compress(data, 50000)
