@@ -123,6 +123,23 @@ def test_no_cpu_fallback_without_device(pkg):
     assert pkg.lib().fourmc_lz4_compress_bound(4 * 1024 * 1024) == 4210768   # lz4.h:212
 
 
+def test_entry_points_reject_a_missing_context(pkg):
+    """Every call that needs the device takes a context; NULL is an argument error, never a CPU path."""
+    L = pkg.lib()
+    buf = C.create_string_buffer(64)
+    assert L.fourmc_blockstream_compress_host(None, 0, 1, buf, 64, 0, buf, 64) == pkg.E_ARG
+    assert L.fourmc_blockstream_decompress_host(None, 0, buf, 64, buf, 64) == pkg.E_ARG
+    assert L.fourmc_4mc_compress_host(None, 1, buf, 64, buf, 64) == pkg.E_ARG
+    assert L.fourmc_4mc_decompress_host(None, buf, 64, buf, 64) == pkg.E_ARG
+    assert L.fourmc_4mz_compress_host(None, 1, buf, 64, buf, 64) == pkg.E_ARG
+    assert L.fourmc_4mz_decompress_host(None, buf, 64, buf, 64) == pkg.E_ARG
+    assert L.fourmc_zstd_compress(None, 1, buf, 64, buf, 64) == pkg.E_ARG
+    assert L.fourmc_zstd_decompress(None, buf, 64, buf, 64) == pkg.E_ARG
+    # sizes that need no device
+    assert L.fourmc_blockstream_bound(0, 0, 0) >= 4 and L.fourmc_blockstream_bound(1, 1 << 30, 65536) > 1 << 30
+    assert L.fourmc_4mc_bound(0) == 44                                        # header + EOS + footer of an empty file
+
+
 def test_shard_blocks(pkg):
     for nb in (0, 1, 7, 8, 9, 16384, 4096 + 3):
         for g in (1, 2, 4, 8):
