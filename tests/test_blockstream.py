@@ -186,6 +186,32 @@ def test_zstd_streams_from_the_reference_codec(bs, ref):
     assert [r for r, _ in walk(s, MAX_ZSTD)] == [MAX_ZSTD + 1, 0]
 
 
+def random_datum_records(count, seed):
+    """The input of the reference's own codec test (TestFourMcCodec.codecTest, java/hadoop-4mc/src/test/java/com/fing/
+    compression/fourmc/TestFourMcCodec.java): `count` key / value pairs of Hadoop RandomDatum records, each a BE32
+    length of 10 + 10^(3 * U[0,1)) followed by that many random bytes (same shape; Java's PRNG is not reproduced)."""
+    rng = random.Random(seed)
+    parts = []
+    for _ in range(2 * count):
+        n = 10 + int(10.0 ** (rng.random() * 3.0))
+        parts.append(n.to_bytes(4, "big") + rng.randbytes(n))
+    return b"".join(parts)
+
+
+def test_reference_codec_test_shape_cpu(bs, ref):
+    """TestFourMcCodec.testZstdCodec: 100 000 random records through ZstdCodec, handed to the stream in ONE write
+    (DataOutputStream over BufferedOutputStream passes a large array straight through) -> one block of
+    ceil(n / MAX_INPUT_SIZE) chunks and a closing zero, read back record for record."""
+    ref.ZSTD_compress.restype = C.c_size_t
+    cfn = C.cast(ref.ZSTD_compress, C.c_void_p)
+    data = random_datum_records(100000, 20240917)
+    s = bs.compress(data, 0, kind=1, cfn=cfn)
+    w = walk(s, MAX_ZSTD)
+    assert [r for r, _ in w] == [len(data), 0] and len(w[0][1]) == -(-len(data) // MAX_ZSTD)
+    assert len(data) / len(s) < 1.1                               # "Compression ratio should be very small, almost 1"
+    assert bs.decompress(s, len(data), kind=1) == (len(data), data)
+
+
 # ---- GPU: the C-ABI calls ------------------------------------------------------------------------
 
 def _gpu_api(pkg):
@@ -245,6 +271,18 @@ def test_gpu_streams_round_trip_and_cross_decode(ctx, pkg, bs, zstd):
                 assert [r for r, _ in walk(s2, mx)] == raws + ([0] if tz else [])
                 assert bs.decompress(s2, len(data), kind=zstd) == (len(data), data)
     assert gpu_compress(ctx, pkg, b"", zstd) == bytes(4)
+
+
+@pytest.mark.gpu
+def test_gpu_reference_codec_test_shape(ctx, pkg, bs):
+    """TestFourMcCodec.testZstdCodec on the GPU path (and its LZ4 twin): see test_reference_codec_test_shape_cpu."""
+    data = random_datum_records(100000, 20240917)
+    for zstd, mx in ((1, MAX_ZSTD), (0, MAX_LZ4)):
+        s = gpu_compress(ctx, pkg, data, zstd)
+        w = walk(s, mx)
+        assert [r for r, _ in w] == [len(data), 0] and len(w[0][1]) == -(-len(data) // mx)
+        assert gpu_decompress(ctx, pkg, s, len(data), zstd) == (len(data), data)
+        assert bs.decompress(s, len(data), kind=zstd) == (len(data), data)      # the oracle's decoders agree
 
 
 @pytest.mark.gpu
