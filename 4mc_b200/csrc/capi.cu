@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -416,14 +418,16 @@ int ensure_side(fourmc_ctx *ctx, DecWs &ws)
 // Runs verify + D1 + D0 + D2 + finalize over n_blocks descriptors already in ws.desc / ws.xxh /
 // ws.status.  max_chunks bounds the chunk indices used by the descriptors.
 
+// compact: the descriptors' destinations are consecutive (a stream): blocks that decode short are moved down.
 int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t max_chunks, int check_xxh,
-               int32_t *d_out_size, const IndexInfo *d_info, long long *d_result, int codec = CODEC_LZ4)
+               int32_t *d_out_size, const IndexInfo *d_info, long long *d_result, int codec = CODEC_LZ4, int compact = 0)
 {
     int r;
     if (codec == CODEC_ZSTD) max_chunks = 0;
     if ((r = ensure(ctx, ws.tokmap, (max_chunks + 1) * LZ4_CHUNK_WORDS * 4))) return r;
     if ((r = ensure(ctx, ws.chunkop, (max_chunks + 1) * 4))) return r;
     if ((r = ensure(ctx, ws.result, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
+    bool verify_forked = false;
     if (nb) {
         CK(cudaMemsetAsync(ws.tokmap.p, 0, (max_chunks + 1) * LZ4_CHUNK_WORDS * 4, st));
         const BlockDesc *desc = (const BlockDesc *)ws.desc.p;
@@ -436,6 +440,7 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             KL("xxh_verify_kernel", ws.side, xxh_verify_kernel<<<(nb + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, ws.side>>>(
                 desc, (const uint32_t *)ws.xxh.p, nb, status));
             CK(cudaEventRecord(ws.join, ws.side));
+            verify_forked = true;
         }
         if (!ctx->d1_attr_set) {
             CK(cudaFuncSetAttribute(lz4_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D1_SMEM));
@@ -504,9 +509,13 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             else KL("lz4_copy_kernel", st, lz4_copy_kernel<8><<<nb, 256, 0, st>>>(desc, tm, co, rs));
         }
     }
-    if (nb && check_xxh && ws.join) CK(cudaStreamWaitEvent(st, ws.join, 0));
+    if (verify_forked) CK(cudaStreamWaitEvent(st, ws.join, 0));
+    if ((r = ensure(ctx, ws.final_, 16))) return r;
     KL("finalize_kernel", st, finalize_kernel<<<1, SCAN_THREADS, 0, st>>>((const BlockDesc *)ws.desc.p, (const int32_t *)ws.result.p, nb,
-                                                (uint8_t *)ws.status.p, d_out_size, d_info, d_result));
+                                                (uint8_t *)ws.status.p, d_out_size, d_info, d_result, (uint32_t *)ws.final_.p));
+    if (compact && nb)
+        KL("compact_kernel", st, compact_kernel<<<1, SCAN_THREADS, 0, st>>>((const BlockDesc *)ws.desc.p, (const int32_t *)ws.result.p,
+                                                  (const uint8_t *)ws.status.p, nb, (const uint32_t *)ws.final_.p));
     return FOURMC_OK;
 }
 
@@ -521,8 +530,9 @@ build_desc_kernel(uint32_t nb, const uint8_t *src, const uint64_t *src_off, cons
         const uint32_t i = i0 + threadIdx.x;
         const bool live = i < nb;
         const uint32_t c = live ? csize[i] : 0, u = live ? usize[i] : 0;
-        const bool toolarge = c > FOURMC_BLOCKSIZE || (c != u && u > FOURMC_BLOCKSIZE);
-        const uint32_t nch = (live && !toolarge && c != u) ? (c + 15 + LZ4_CHUNK - 1) / LZ4_CHUNK : 0;
+        const bool hash_only = u == 0xffffffffu;          // a footer travelling with the blocks: checksum, no decode
+        const bool toolarge = !hash_only && (c > FOURMC_BLOCKSIZE || (c != u && u > FOURMC_BLOCKSIZE));
+        const uint32_t nch = (live && !toolarge && !hash_only && c != u) ? (c + 15 + LZ4_CHUNK - 1) / LZ4_CHUNK : 0;
         unsigned long long total;
         const unsigned long long incl = cta_incl_scan_u64(nch, tmp, &total);
         if (live) {
@@ -531,6 +541,7 @@ build_desc_kernel(uint32_t nb, const uint8_t *src, const uint64_t *src_off, cons
             d.csize = c; d.usize = u; d.chunk_base = (uint32_t)(carry + incl - nch); d.stored = (c == u) ? 1u : 0u;
             uint8_t s = FOURMC_BLOCK_OK;
             if (toolarge) { s = FOURMC_BLOCK_TOOLARGE; d.csize = 0; d.usize = 0; d.stored = 1; }
+            if (hash_only) { d.usize = 0; d.stored = 2; }
             desc[i] = d; status[i] = s;
         }
         carry += total;
@@ -812,7 +823,7 @@ static int decompress_device_impl(fourmc_ctx *ctx, void *stream, int codec, cons
                                                   (BlockDesc *)ws.desc.p, (uint32_t *)ws.xxh.p, (uint8_t *)ws.status.p,
                                                   (IndexInfo *)ws.info.p, codec == CODEC_ZSTD ? FOURMC_MAGIC_4MZ : FOURMC_MAGIC_4MC));
     const size_t max_chunks = n / LZ4_CHUNK + 2 * (size_t)nb + 2;
-    return dec_blocks(ctx, st, ws, nb, max_chunks, 1, nullptr, (const IndexInfo *)ws.info.p, d_result, codec);
+    return dec_blocks(ctx, st, ws, nb, max_chunks, 1, nullptr, (const IndexInfo *)ws.info.p, d_result, codec, 1);
 }
 
 int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n, void *d_out,
@@ -831,7 +842,7 @@ int fourmc_4mz_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in
 static int dec_batch(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, const void *d_src,
                      const uint64_t *d_src_off, const uint32_t *d_csize, const uint32_t *d_usize, const uint32_t *d_xxh,
                      int check_xxh, void *d_dst, const uint64_t *d_dst_off, int32_t *d_out_size, uint8_t *d_status,
-                     int codec = CODEC_LZ4)
+                     int codec = CODEC_LZ4, int compact = 0)
 {
     int r;
     if ((r = ensure(ctx, ws.desc, (size_t)std::max<uint32_t>(nb, 1) * sizeof(BlockDesc)))) return r;
@@ -843,7 +854,7 @@ static int dec_batch(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, c
     if (check_xxh) CK(cudaMemcpyAsync(ws.xxh.p, d_xxh, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
     // every compressed block has csize <= 4 MiB: bound the chunk count by that
     const size_t max_chunks = (size_t)nb * (FOURMC_BLOCKSIZE / LZ4_CHUNK + 2);
-    if ((r = dec_blocks(ctx, st, ws, nb, max_chunks, check_xxh, d_out_size, nullptr, nullptr, codec))) return r;
+    if ((r = dec_blocks(ctx, st, ws, nb, max_chunks, check_xxh, d_out_size, nullptr, nullptr, codec, compact))) return r;
     if (d_status) CK(cudaMemcpyAsync(d_status, ws.status.p, nb, cudaMemcpyDeviceToDevice, st));
     return FOURMC_OK;
 }
@@ -1123,6 +1134,7 @@ static int walk_streams(const uint8_t *in, size_t n, std::vector<HostBlock> &blo
     size_t pos = 0;
     uint64_t opos = 0;
     while (pos < n) {
+        const uint64_t opos_before = opos;
         if (n - pos < 4) return FOURMC_E_CONTENT;                                  // :868
         if (be32(in + pos) != magic) return FOURMC_E_CONTENT;                      // :873
         if (n - pos < 12) return FOURMC_E_CONTENT;                                 // :577
@@ -1152,6 +1164,10 @@ static int walk_streams(const uint8_t *in, size_t n, std::vector<HostBlock> &blo
         blocks.push_back(HostBlock{(uint64_t)pos, opos, fsize - 4, 0xffffffffu, be32(in + pos + fsize - 4)});
         if (be32(in + pos + 4) != 1) return FOURMC_E_CONTENT;                      // :687 (after the checksum, checked below)
         pos += fsize;
+        // :909-913 `do { ... } while (decodedSize)`: a stream that announces no bytes ends the loop, whatever follows it.
+        // (A stream whose blocks all DECODE to nothing while announcing sizes would also end the reference's loop; the
+        // walk only sees the announced sizes -- such streams are written by no 4mc writer.)
+        if (opos == opos_before) break;
     }
     return FOURMC_OK;
 }
@@ -1199,14 +1215,14 @@ static long long decompress_host_impl(fourmc_ctx *ctx, int codec, const void *in
     // everything the device reads from / writes to the host besides the payload lives in pinned
     // memory, so that no copy blocks the host and the two slice pipelines really overlap
     const size_t tb_host = (max_cnt * 28 + 63) & ~(size_t)63;
-    const size_t pin_need = 4096 + FM_PIPE_MAX * tb_host + blocks.size() * 5 + 64;
+    const size_t pin_need = 4096 + FM_PIPE_MAX * tb_host + blocks.size() * 9 + 64;
     if ((r = pinned_scratch(ctx, pin_need))) return r;
     uint8_t *pin = (uint8_t *)ctx->pinned + 4096;
     const int np = codec == CODEC_ZSTD ? std::min(pipe_depth(), 3) : pipe_depth();
     uint8_t *h_tables[FM_PIPE_MAX];
     for (int i = 0; i < FM_PIPE_MAX; i++) h_tables[i] = pin + (size_t)i * tb_host;
-    uint32_t *hashes = (uint32_t *)(pin + FM_PIPE_MAX * tb_host);
-    uint8_t *status = (uint8_t *)(hashes + blocks.size());
+    int32_t *sizes = (int32_t *)(pin + FM_PIPE_MAX * tb_host);         // decoded size of every item
+    uint8_t *status = (uint8_t *)(sizes + blocks.size());
     for (size_t k = 0; k < slices.size(); k++) {
         const int b = (int)(k % np);
         const Slice &s = slices[k];
@@ -1236,28 +1252,33 @@ static long long decompress_host_impl(fourmc_ctx *ctx, int codec, const void *in
         uint32_t *d_hash = (uint32_t *)(d_x + cnt);
         int32_t *d_osz = (int32_t *)(d_hash + cnt);
         uint8_t *d_st = (uint8_t *)(d_osz + cnt);
-        // XXH32 of every item's payload (blocks and footers), compared with the headers below; it
-        // runs beside the decode on the slot's side stream
-        if ((r = ensure_side(ctx, ws))) return r;
-        CK(cudaEventRecord(ws.fork, st));
-        CK(cudaStreamWaitEvent(ws.side, ws.fork, 0));
-        if ((r = fourmc_xxh32_batch_device(ctx, ws.side, cnt, ctx->stage_in[b].p, d_src_off, d_c, 0, d_hash))) return r;
-        CK(cudaEventRecord(ws.join, ws.side));
-        if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[b].p, d_src_off, d_c, d_u, d_hash, 0,
+        // every item's payload checksum (blocks and footers) is verified inside the decode batch (:637/:645)
+        if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[b].p, d_src_off, d_c, d_u, d_x, 1,
                            ctx->stage_out[b].p, d_dst_off, d_osz, d_st, codec)))
             return r;
-        CK(cudaStreamWaitEvent(st, ws.join, 0));
         if (s.d1 > s.d0)
             CK(cudaMemcpyAsync((uint8_t *)out + s.d0, ctx->stage_out[b].p, s.d1 - s.d0, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(status + s.b0, d_st, cnt, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(hashes + s.b0, d_hash, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sizes + s.b0, d_osz, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < np; i++) CK(cudaStreamSynchronize(ctx->aux[i]));
-    // verdict in stream order: checksum first (:637/:645), then the decoder (:662)
+    // verdict in stream order: the first item whose checksum (:637/:645) or decode (:662) failed
+    bool short_block = false;
     for (size_t i = 0; i < blocks.size(); i++) {
-        if (hashes[i] != blocks[i].xxh) return FOURMC_E_CONTENT;
-        if (blocks[i].usize == 0xffffffffu) continue;        // footer: checksum only
         if (status[i] != FOURMC_BLOCK_OK) return FOURMC_E_CONTENT;
+        if (blocks[i].usize != 0xffffffffu && (uint32_t)sizes[i] != blocks[i].usize) short_block = true;
+    }
+    if (short_block) {
+        // a block that decodes to fewer bytes than announced: the reference writes what the decoder returned
+        // (native/4mc.c:661-666, :810-815), so the following blocks move down
+        uint64_t wpos = 0;
+        for (size_t i = 0; i < blocks.size(); i++) {
+            if (blocks[i].usize == 0xffffffffu) continue;
+            if (wpos != blocks[i].dst_off) memmove((uint8_t *)out + wpos, (uint8_t *)out + blocks[i].dst_off, (size_t)sizes[i]);
+            wpos += (uint64_t)sizes[i];
+        }
+        memset((uint8_t *)out + wpos, 0, (size_t)(total - wpos));      // nothing of the staging buffers is left behind
+        total = wpos;
     }
     if (walk_err) return walk_err;
     return (long long)total;
@@ -1610,21 +1631,27 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
         int32_t *d_osz = (int32_t *)(d_x + cnt);
         uint8_t *d_st = (uint8_t *)(d_osz + cnt);
         unsigned long long *d_first = (unsigned long long *)(((uintptr_t)(d_st + cnt) + 15) & ~(uintptr_t)15);
-        if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[0].p, d_so, d_c, d_u, d_x, 1, ctx->stage_out[0].p, d_do, d_osz, d_st, codec)))
+        if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[0].p, d_so, d_c, d_u, d_x, 1, ctx->stage_out[0].p, d_do, d_osz, d_st, codec, 1)))
             return r;
+        // what the blocks really decoded to (a block may decode short, native/4mc.c:661-666; the batch closed the gaps)
+        std::vector<uint8_t> status(cnt);
+        std::vector<int32_t> osz(cnt);
+        CK(cudaMemcpyAsync(status.data(), d_st, cnt, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(osz.data(), d_osz, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < cnt; i++) if (status[i] != FOURMC_BLOCK_OK) return FOURMC_E_CONTENT;
+        total_u = 0; u_split = 0;
+        for (uint32_t i = 0; i < cnt; i++) { total_u += (uint64_t)osz[i]; if ((int)i < b1 - b0) u_split = total_u; }
         // first line terminator of the split (skipped line) and the first one at or after the split's end
         CK(cudaMemsetAsync(d_first, 0xff, 16, st));
         const uint8_t *d_out = (const uint8_t *)ctx->stage_out[0].p;
-        if (start != 0)
+        if (start != 0 && u_split)
             KL("find_byte_kernel", st, find_byte_kernel<<<1024, 256, 0, st>>>(d_out, u_split, (uint8_t)'\n', d_first));
         if (total_u > u_split)
             KL("find_byte_kernel", st, find_byte_kernel<<<256, 256, 0, st>>>(d_out + u_split, total_u - u_split, (uint8_t)'\n', d_first + 1));
         uint8_t *hs = (uint8_t *)ctx->pinned;
-        std::vector<uint8_t> status(cnt);
         CK(cudaMemcpyAsync(hs, d_first, 16, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(status.data(), d_st, cnt, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        for (uint32_t i = 0; i < cnt; i++) if (status[i] != FOURMC_BLOCK_OK) return FOURMC_E_CONTENT;
         const unsigned long long first_nl = ((unsigned long long *)hs)[0], tail_nl = ((unsigned long long *)hs)[1];
         uint64_t from = 0, to;
         if (start != 0) {
@@ -1681,3 +1708,5 @@ long long fourmc_zstd_decompress(fourmc_ctx *ctx, const void *src, size_t compre
 }
 
 }  // extern "C"
+
+#include "fileio.h"

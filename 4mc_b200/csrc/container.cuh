@@ -239,30 +239,65 @@ xxh_batch_kernel(const uint8_t *base, const uint64_t *off, const uint32_t *len, 
 
 // Folds D1's verdict into the per-block status and reduces to the stream result:
 // result[0] = decoded size or FOURMC_E_*, result[1] = first failing block or -1.  One CTA.
+//
+// A compressed block may decode to FEWER bytes than its header announces: the reference writes what the
+// decoder returned (native/4mc.c:661-666, :810-815 `filesize += decodedBytes`).  *short_blocks counts such
+// blocks; compact_kernel then closes the gaps the way the serial reader's output has none.
 __global__ void __launch_bounds__(SCAN_THREADS)
 finalize_kernel(const BlockDesc *desc, const int32_t *parse_result, uint32_t n_blocks, uint8_t *status,
-                int32_t *out_size, const IndexInfo *info, long long *result)
+                int32_t *out_size, const IndexInfo *info, long long *result, uint32_t *short_blocks)
 {
-    __shared__ unsigned int s_first;
+    __shared__ unsigned int s_first, s_short;
     __shared__ unsigned long long s_total;
-    if (threadIdx.x == 0) { s_first = 0xffffffffu; s_total = 0; }
+    if (threadIdx.x == 0) { s_first = 0xffffffffu; s_total = 0; s_short = 0; }
     __syncthreads();
     unsigned long long mine = 0;
+    unsigned int shorts = 0;
     for (uint32_t i = threadIdx.x; i < n_blocks; i += SCAN_THREADS) {
         uint8_t st = status[i];
         const int32_t r = parse_result[i];
         if (st == FOURMC_BLOCK_OK && r < 0) { st = FOURMC_BLOCK_CORRUPT; status[i] = st; }
         if (out_size) out_size[i] = r;
         if (st != FOURMC_BLOCK_OK) atomicMin(&s_first, i);
-        else mine += (unsigned long long)r;
+        else { mine += (unsigned long long)r; if ((uint32_t)r != desc[i].usize) shorts++; }
     }
     atomicAdd(&s_total, mine);
+    if (shorts) atomicAdd(&s_short, shorts);
     __syncthreads();
+    if (threadIdx.x == 0 && short_blocks) *short_blocks = s_short;
     if (threadIdx.x == 0 && result) {
         const int e = info ? info->status : FOURMC_OK;
         if (e != FOURMC_OK) { result[0] = e; result[1] = -1; }
         else if (s_first != 0xffffffffu) { result[0] = FOURMC_E_CONTENT; result[1] = (long long)s_first; }
         else { result[0] = (long long)s_total; result[1] = -1; }
+    }
+}
+
+// Blocks that decoded short leave gaps between consecutive blocks of a stream (every block was placed at the
+// sum of the ANNOUNCED sizes before it).  One CTA moves the blocks down in stream order; nothing to do -- the
+// common case -- when *short_blocks is zero.  Only for descriptors whose destinations are consecutive.
+__global__ void __launch_bounds__(SCAN_THREADS)
+compact_kernel(const BlockDesc *desc, const int32_t *parse_result, const uint8_t *status, uint32_t n_blocks,
+               const uint32_t *short_blocks)
+{
+    if (*short_blocks == 0) return;
+    size_t shift = 0;
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        if (status[b] != FOURMC_BLOCK_OK) return;                // the stream fails at this block: nothing after it counts
+        const uint32_t got = (uint32_t)parse_result[b];
+        if (shift) {
+            const uint8_t *s = desc[b].dst;
+            uint8_t *d = desc[b].dst - shift;
+            for (uint32_t i0 = 0; i0 < got; i0 += SCAN_THREADS) {    // moving down: read a slab, then write it
+                const uint32_t i = i0 + threadIdx.x;
+                uint8_t v = 0;
+                if (i < got) v = s[i];
+                __syncthreads();
+                if (i < got) d[i] = v;
+                __syncthreads();
+            }
+        }
+        shift += desc[b].usize - got;
     }
 }
 

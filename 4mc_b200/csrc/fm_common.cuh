@@ -70,6 +70,13 @@ __device__ __forceinline__ int warp_min(int v)
     return v;
 }
 
+__device__ __forceinline__ int warp_max(int v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(FM_FULL, v, d));
+    return v;
+}
+
 // Byte copy of a short, non-overlapping range with every load issued before the first store, so a
 // lane pays one memory latency per 8 bytes instead of one per byte (warps issue in order: a store
 // that waits for its load's data blocks the loads behind it).

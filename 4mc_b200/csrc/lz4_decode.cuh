@@ -36,7 +36,7 @@ struct BlockDesc {                         // one per block, built on the device
     uint8_t *dst;
     uint32_t csize, usize;                 // usize = capacity offered to the decoder
     uint32_t chunk_base;                   // first chunk index in tokmap/chunk_op
-    uint32_t stored;                       // 1: raw copy
+    uint32_t stored;                       // 0: compressed, 1: raw copy, 2: nothing to decode (checksum-only item)
 };
 
 // ---- D1 ------------------------------------------------------------------------------------
@@ -424,23 +424,23 @@ __device__ __forceinline__ void smem_copy_seq(uint8_t *dst, const uint8_t *src, 
 constexpr int LZ4_SPAN = 2048;            // output bytes a warp assembles in shared memory at once
 constexpr int LZ4_SCR = 80;               // scratch bytes per lane (64 used; 80 keeps 128-bit stores conflict-free)
 
-// W = warps per block (1, 2, 4 or 8): the host picks it from the batch size -- many blocks in
-// flight need few warps each (and then hardly ever wait on one another), few blocks need many.
+// Shared memory of one copy warp / of the W warps that share a block.
+struct CopyWarpSmem {
+    __align__(16) uint8_t span[LZ4_SPAN + 32];
+    __align__(16) uint8_t scr[32 * LZ4_SCR];      // per lane: 4 aligned 16-byte chunks of a match source
+    uint8_t tokpos[64];
+};
 template <int W>
-__global__ void __launch_bounds__(W * 32)
-lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t *chunk_op,
-                const int32_t *result)
+struct CopyBlockSmem {
+    int owed[W];
+    int ticket;
+};
+
+// The copy of one block by W warps (`warp` = 0 .. W-1 within the block).
+template <int W>
+__device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32_t *tokmap, const uint32_t *chunk_op,
+                                               const int warp, const int lane, CopyBlockSmem<W> *bs, CopyWarpSmem *ws)
 {
-    __shared__ int s_owed[W];
-    __shared__ int s_ticket;
-    __shared__ uint8_t s_tokpos[W][64];
-    __shared__ __align__(16) uint8_t s_span[W][LZ4_SPAN + 32];
-    __shared__ __align__(16) uint8_t s_scr[W][32 * LZ4_SCR];      // per lane: 4 aligned 16-byte chunks of a match source
-
-    const BlockDesc bd = blocks[blockIdx.x];
-    if (bd.stored || result[blockIdx.x] < 0) return;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint8_t *__restrict__ src = bd.src;
     uint8_t *out = bd.dst;
     const int csize = (int)bd.csize;
@@ -448,12 +448,10 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
     const int nchunks = (dq + csize + LZ4_CHUNK - 1) / LZ4_CHUNK;
     const uint4 *maps = (const uint4 *)(tokmap + (size_t)bd.chunk_base * LZ4_CHUNK_WORDS);
     const uint32_t *cops = chunk_op + bd.chunk_base;
-    volatile int *owed = s_owed;
-    uint8_t *span = s_span[warp];
-
-    if (threadIdx.x < W) s_owed[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_ticket = 0;
-    if (W > 1) __syncthreads();
+    volatile int *owed = bs->owed;
+    uint8_t *span = ws->span;
+    uint8_t *s_tokpos_w = ws->tokpos;
+    uint8_t *s_scr_w = ws->scr;
 
     // lowest output position any warp of this block still owes
     auto high_water = [&]() -> int {
@@ -469,28 +467,47 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
         if (lane == 0) owed[warp] = pos;
     };
 
+    // Chunks are taken one AHEAD: while chunk k is copied, the token bits and the output position of the chunk
+    // this warp takes next are already on their way, and the two lines of compressed bytes it will read are
+    // being pulled into L1 -- a warp's chunks are a dependent chain (bits -> tokens -> offsets -> match bytes),
+    // so every load taken off that chain shortens the block's time.
     int kseq = 0;
-    for (;;) {
-        int k = 0;
-        if (W == 1) k = kseq++;
+    auto take = [&]() -> int {
+        int t = 0;
+        if (W == 1) t = kseq++;
         else {
-            if (lane == 0) k = atomicAdd(&s_ticket, 1);
-            k = __shfl_sync(FM_FULL, k, 0);
+            if (lane == 0) t = atomicAdd(&bs->ticket, 1);
+            t = __shfl_sync(FM_FULL, t, 0);
         }
+        return t;
+    };
+    uint4 m_n = make_uint4(0u, 0u, 0u, 0u);
+    int op_n = 0;
+    auto fetch = [&](int kk) {
+        if (kk >= nchunks) return;
+        m_n = maps[kk]; op_n = (int)cops[kk];
+        const int at = kk * LZ4_CHUNK - dq + lane * 128;
+        if (lane < 2 && at >= 0 && at < csize) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + at));
+    };
+    int kn = take();
+    fetch(kn);
+    for (;;) {
+        const int k = kn;
         if (k >= nchunks) break;
-
-        const uint4 m = maps[k];
+        const uint4 m = m_n;
+        int op0 = op_n;
+        kn = take();
+        fetch(kn);
         const int c0 = __popc(m.x), c1 = c0 + __popc(m.y), c2 = c1 + __popc(m.z), ntok = c2 + __popc(m.w);
         if (ntok == 0) continue;
-        int op0 = (int)cops[k];
 
         // lane r takes the r-th token of the chunk: scatter positions by rank
         {
             const uint32_t lt = (1u << lane) - 1u;
-            if ((m.x >> lane) & 1u) s_tokpos[warp][__popc(m.x & lt)] = (uint8_t)lane;
-            if ((m.y >> lane) & 1u) s_tokpos[warp][c0 + __popc(m.y & lt)] = (uint8_t)(32 + lane);
-            if ((m.z >> lane) & 1u) s_tokpos[warp][c1 + __popc(m.z & lt)] = (uint8_t)(64 + lane);
-            if ((m.w >> lane) & 1u) s_tokpos[warp][c2 + __popc(m.w & lt)] = (uint8_t)(96 + lane);
+            if ((m.x >> lane) & 1u) s_tokpos_w[__popc(m.x & lt)] = (uint8_t)lane;
+            if ((m.y >> lane) & 1u) s_tokpos_w[c0 + __popc(m.y & lt)] = (uint8_t)(32 + lane);
+            if ((m.z >> lane) & 1u) s_tokpos_w[c1 + __popc(m.z & lt)] = (uint8_t)(64 + lane);
+            if ((m.w >> lane) & 1u) s_tokpos_w[c2 + __popc(m.w & lt)] = (uint8_t)(96 + lane);
         }
         __syncwarp();
 
@@ -498,7 +515,7 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
             const bool active = batch + lane < ntok;
             int lit = 0, ml = 0, off = 0, lit_src = 0;
             if (active) {
-                int ip = k * LZ4_CHUNK + (int)s_tokpos[warp][batch + lane] - dq;
+                int ip = k * LZ4_CHUNK + (int)s_tokpos_w[batch + lane] - dq;
                 const unsigned tok = src[ip++];
                 lit = (int)(tok >> 4);
                 if (lit == 15) { unsigned s; do { s = src[ip++]; lit += (int)s; } while (s == 255); }
@@ -559,7 +576,7 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
                             const int so = (int)((uintptr_t)gs & 15);
                             const uint4 *gb = (const uint4 *)(gs - so);
                             const int nch = (so + ext + 15) >> 4;
-                            uint4 *scr = (uint4 *)(s_scr[warp] + lane * LZ4_SCR);
+                            uint4 *scr = (uint4 *)(s_scr_w + lane * LZ4_SCR);
                             const uint4 z = make_uint4(0, 0, 0, 0);
                             const uint4 q0 = ldg_v4(gb), q1 = nch > 1 ? ldg_v4(gb + 1) : z;
                             const uint4 q2 = nch > 2 ? ldg_v4(gb + 2) : z, q3 = nch > 3 ? ldg_v4(gb + 3) : z;
@@ -641,13 +658,31 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
     publish(0x7fffffff);
 }
 
+// D2 as a kernel of its own (D1 = lz4_parse_kernel ran before it): one CTA of W warps per block.
+// W = warps per block (1, 2, 4 or 8): the host picks it from the batch size -- many blocks in
+// flight need few warps each (and then hardly ever wait on one another), few blocks need many.
+template <int W>
+__global__ void __launch_bounds__(W * 32)
+lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t *chunk_op,
+                const int32_t *result)
+{
+    __shared__ CopyBlockSmem<W> s_block;
+    __shared__ CopyWarpSmem s_warp[W];
+    const BlockDesc bd = blocks[blockIdx.x];
+    if (bd.stored || result[blockIdx.x] < 0) return;
+    if (threadIdx.x < W) s_block.owed[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_block.ticket = 0;
+    if (W > 1) __syncthreads();
+    lz4_copy_block<W>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, &s_block, &s_warp[threadIdx.x >> 5]);
+}
+
 // ---- D0 ------------------------------------------------------------------------------------
 
 __global__ void lz4_stored_kernel(const BlockDesc *blocks, uint32_t n_blocks)
 {
     // grid.y = block index, grid.x tiles the payload
     const BlockDesc bd = blocks[blockIdx.y];
-    if (!bd.stored) return;
+    if (bd.stored != 1) return;                           // 2 = checksum-only item (a footer): nothing to copy
     const uint32_t n = bd.csize;
     const uint8_t *__restrict__ s = bd.src;
     uint8_t *d = bd.dst;

@@ -8,9 +8,10 @@
 //
 //  E1 lz4_region_kernel   persistent CTAs; each takes 64 KiB REGIONS of a block:
 //       stage   region -> shared memory with one bulk async copy (cp.async.bulk + mbarrier)
-//       index   16384-entry table of the FIRST position of each 4-byte hash in the region,
-//               order-independent (descending sweep, later stores win), so all threads build it
-//               at once; any earlier occurrence is a usable LZ4 match candidate
+//       index   16384-entry table of the FIRST (even) position of each 4-byte hash in the region,
+//               order-independent (descending sweep; inside a step the lowest position wins), so all
+//               threads build it at once and every run produces the same bytes; any earlier
+//               occurrence is a usable LZ4 match candidate
 //       parse   every thread owns a 132-byte SLICE (132 = 33 words: slices start in distinct
 //               shared-memory banks).  Pass 1 tests EVERY position of the slice against the table
 //               (uniform work, one bit per position); pass 2 walks greedily over the set bits only,
@@ -225,8 +226,8 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
             // Chain build.  All threads first store every position's hash in prev[]; then warps 0..3 walk
             // the region in ascending rounds of 128 positions: a position is linked to the head of its
             // bucket as of the previous round, then the round's positions become the heads (for equal
-            // hashes inside a round one of them wins, the others stay reachable only through their own
-            // links -- 0.2 % of ratio on text, tests/native/enc_emul.cpp EMUL_BUILD=128000).
+            // hashes inside a round the highest position wins, the others stay reachable only through their
+            // own links -- 0.2 % of ratio on text, tests/native/enc_emul.cpp EMUL_BUILD=128000).
             const int last = rlen - 4;
             for (int p = tid; p <= last; p += NT) prev[p] = (uint16_t)enc_hash(smem_read4(data32, p));
             __syncthreads();
@@ -238,7 +239,17 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
                     if (live) { h = prev[p]; prev[p] = head[h]; }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                     if (live) head[h] = (uint16_t)p;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    // equal hashes inside a round race: the HIGHEST position (the most recent one) is made the head,
+                    // whoever finds a lower one stores again -- the links, and the bytes, are the same on every run
+                    for (;;) {
+                        uint32_t any;
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        const uint32_t lost = live && head[h] < (uint16_t)p;
+                        asm volatile("{\n\t.reg .pred pa, pq;\n\tsetp.ne.u32 pq, %1, 0;\n\tbar.red.or.pred pa, 1, 128, pq;\n\t"
+                                     "selp.u32 %0, 1, 0, pa;\n\t}" : "=r"(any) : "r"(lost) : "memory");
+                        if (!any) break;
+                        if (lost) head[h] = (uint16_t)p;
+                    }
                 }
             }
             __syncthreads();
@@ -247,14 +258,26 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
             constexpr int STEP = NT * 4;
             for (int base = ((rlen - 1) / STEP) * STEP; base >= 0; base -= STEP) {
                 const int p = base + 4 * tid;
-                if (p <= last) {
+                uint32_t h0 = 0, h2 = 0;
+                const bool live0 = p <= last, live2 = p + 2 <= last;
+                if (live0) {
                     // every second position is enough: a repeat first seen at an odd position is
                     // found one byte later and the backward extension recovers that byte
                     const uint32_t w0 = data32[p >> 2], w1 = data32[(p >> 2) + 1];
-                    if (p + 2 <= last) table[enc_hash(__funnelshift_r(w0, w1, 16))] = (uint16_t)(p + 2);
-                    table[enc_hash(w0)] = (uint16_t)p;
+                    h0 = enc_hash(w0); h2 = enc_hash(__funnelshift_r(w0, w1, 16));
+                    if (live2) table[h2] = (uint16_t)(p + 2);
+                    table[h0] = (uint16_t)p;
                 }
-                __syncthreads();
+                // Equal hashes inside one step race; whoever finds a HIGHER position in its bucket stores again
+                // until the lowest one holds it: the table -- and with it every compressed byte -- is then the
+                // same on every run (one extra round on text, where a step rarely holds a hash twice).
+                for (;;) {
+                    const bool lost0 = live0 && table[h0] > (uint16_t)p, lost2 = live2 && table[h2] > (uint16_t)(p + 2);
+                    if (!__syncthreads_or(lost0 || lost2)) break;
+                    if (lost2) table[h2] = (uint16_t)(p + 2);
+                    if (lost0) table[h0] = (uint16_t)p;
+                    __syncthreads();
+                }
             }
         }
 

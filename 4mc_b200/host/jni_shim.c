@@ -15,7 +15,9 @@
  * of the direct buffer; on success the length field is reset to 0; on failure InternalError is
  * thrown with "<function> returned: <value>"; NULL buffer addresses return 0 silently.
  */
+#include <pthread.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #ifdef FOURMC_REAL_JNI
@@ -38,11 +40,28 @@ static void throw_ie(JNIEnv *env, const char *msg)
 /* one GPU context per calling thread: the Java objects are synchronized per instance, many
  * instances may call from different threads, and a fourmc_ctx is single-threaded */
 static __thread fourmc_ctx *t_ctx;
+static __thread char *t_bounce;            /* xxhash32: the array's bytes leave the critical region through here */
+static __thread size_t t_bounce_cap;
+/* a thread that ends gives its context (streams, device workspaces) and bounce buffer back */
+static pthread_key_t t_key;
+static pthread_once_t t_once = PTHREAD_ONCE_INIT;
+static void thread_exit(void *p)
+{
+    (void)p;
+    if (t_ctx) { fourmc_ctx_destroy(t_ctx); t_ctx = NULL; }
+    free(t_bounce); t_bounce = NULL; t_bounce_cap = 0;
+}
+static void make_key(void) { pthread_key_create(&t_key, thread_exit); }
 static fourmc_ctx *ctx_get(JNIEnv *env)
 {
-    if (!t_ctx && fourmc_ctx_create(&t_ctx, -1) != FOURMC_OK) {
-        t_ctx = NULL;
-        throw_ie(env, "lib4mcgpu: no usable CUDA device (there is no CPU fallback)");
+    if (!t_ctx) {
+        if (fourmc_ctx_create(&t_ctx, -1) != FOURMC_OK) {
+            t_ctx = NULL;
+            throw_ie(env, "lib4mcgpu: no usable CUDA device (there is no CPU fallback)");
+            return NULL;
+        }
+        pthread_once(&t_once, make_key);
+        pthread_setspecific(t_key, (void *)1);          /* non-NULL: the destructor runs at thread exit */
     }
     return t_ctx;
 }
@@ -94,15 +113,23 @@ JNIEXPORT jint JNICALL PKG(Lz4Compressor, compressBound)(JNIEnv *env, jclass cls
 { (void)env; (void)cls; return fourmc_lz4_compress_bound(n); }                  /* :171-174 */
 
 static jint xxhash32_common(JNIEnv *env, jbyteArray buf, jint off, jint len, jint seed)
-{   /* :178-194 */
+{   /* :178-194.  The reference hashes inside the critical region; a GPU round trip (or the creation of a CUDA
+     * context: seconds) there would hold the collector up, so the context is made first and the region is only as
+     * long as one memcpy into this thread's bounce buffer. */
+    fourmc_ctx *ctx = ctx_get(env);
+    if (!ctx) return 0;
+    if (len < 0) len = 0;
+    if ((size_t)len > t_bounce_cap) {
+        char *nb = (char *)realloc(t_bounce, (size_t)len + 4096);
+        if (!nb) { throw_ie(env, "lib4mcgpu: out of memory"); return 0; }
+        t_bounce = nb; t_bounce_cap = (size_t)len + 4096;
+    }
     char *in = (char *)(*env)->GetPrimitiveArrayCritical(env, buf, 0);
     if (in == NULL) return 0;
-    fourmc_ctx *ctx = t_ctx;        /* no JNI calls (ctx_get may throw) inside a critical region */
-    jint h = 0;
-    int st = FOURMC_E_CUDA;
-    if (!ctx && fourmc_ctx_create(&t_ctx, -1) == FOURMC_OK) ctx = t_ctx;
-    if (ctx) h = (jint)fourmc_xxh32(ctx, in + off, (size_t)len, (uint32_t)seed, &st);
+    if (len) memcpy(t_bounce, in + off, (size_t)len);
     (*env)->ReleasePrimitiveArrayCritical(env, buf, in, 0);
+    int st = FOURMC_E_CUDA;
+    const jint h = (jint)fourmc_xxh32(ctx, t_bounce, (size_t)len, (uint32_t)seed, &st);
     if (st != FOURMC_OK) throw_ie(env, "lib4mcgpu: XXH32 failed on the device (there is no CPU fallback)");
     return h;
 }

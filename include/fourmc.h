@@ -242,6 +242,25 @@ long long fourmc_blockstream_compress_host(fourmc_ctx *ctx, int zstd, int level,
 long long fourmc_blockstream_decompress_host(fourmc_ctx *ctx, int zstd, const void *in, size_t n,
                                              void *out, size_t out_capacity);
 
+/* ---- files: the reference's own library entry points (native/4mc.h:36-41, callers native/4mccli.c:342-356) -----
+ * Same arguments, console messages per display level, "stdin" / "stdout" / "/dev/null" names and overwrite
+ * prompt as native/4mc.c:163-211, :220-386, :388-556, :896-966 -- and, like the reference, a fatal error ends
+ * the process with exit(1 generic | 2 input | 3 output | 4 content) (native/4mc.c:135-161); 0 on success.
+ * Files are streamed through pinned bounce buffers in slices of many blocks (a reader thread, the calling
+ * thread on the GPU, a writer thread): any size, pipes included.  The process-wide context they share is
+ * created on first use.  The reference's native/4mccli.c links against these unchanged. */
+int fourMCcompressFilename(int displayLevel, int overwrite, char *input_filename, char *output_filename, int compressionlevel);
+int fourMcDecompressFileName(int displayLevel, int overwrite, char *input_filename, char *output_filename);
+int fourMZcompressFilename(int displayLevel, int overwrite, char *input_filename, char *output_filename, int compressionlevel);
+int fourMZDecompressFileName(int displayLevel, int overwrite, char *input_filename, char *output_filename);
+
+/* The bodies of those four over open descriptors, with status codes instead of exit(): bytes written /
+ * decoded, or FOURMC_E_INPUT (read error, truncated stream), FOURMC_E_OUTPUT (write error), FOURMC_E_CONTENT,
+ * FOURMC_E_GENERIC.  Decoding writes every block that precedes a damaged one before it reports the damage,
+ * like the serial reader (native/4mc.c:603-668).  *in_bytes (may be NULL) = bytes consumed from in_fd. */
+long long fourmc_compress_fd(fourmc_ctx *ctx, int zstd, int level, int in_fd, int out_fd, uint64_t *in_bytes);
+long long fourmc_decompress_fd(fourmc_ctx *ctx, int zstd, int in_fd, int out_fd, uint64_t *in_bytes);
+
 #ifdef __cplusplus
 }
 #endif

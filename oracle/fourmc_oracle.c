@@ -361,6 +361,7 @@ long long fmo_4mc_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t o
     size_t pos = 0, opos = 0;
     while (pos < n) {
         uint32_t fsize;
+        const size_t opos_before = opos;
         if (n - pos < 4) return FMO_ERR_CONTENT;                     /* magic unreadable :868 */
         if (rd_be32(in + pos) != FMO_MAGIC_4MC) return FMO_ERR_CONTENT;       /* :873 */
         if (n - pos < 12) return FMO_ERR_CONTENT;                    /* unreadable header :577 */
@@ -398,6 +399,7 @@ long long fmo_4mc_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t o
         if (fmo_xxh32(in + pos, fsize - 4, 0) != rd_be32(in + pos + fsize - 4)) return FMO_ERR_CONTENT; /* :685 */
         if (rd_be32(in + pos + 4) != 1) return FMO_ERR_CONTENT;      /* :687 */
         pos += fsize;
+        if (opos == opos_before) break;       /* :909-913 `do {...} while (decodedSize)`: a stream that decodes to nothing ends the loop */
     }
     return (long long)opos;
 }

@@ -438,6 +438,7 @@ long long fmo_4mz_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t c
 {
     size_t pos = 0, op = 0;
     while (pos < n) {
+        const size_t op_before = op;
         if (n - pos < 12) return FMO_ERR_CONTENT;
         if (be32(in + pos) != 0x344D5A00u || be32(in + pos + 4) != 1 || be32(in + pos + 8) != fmo_xxh32(in + pos, 8, 0)) return FMO_ERR_CONTENT;
         pos += 12;
@@ -451,9 +452,14 @@ long long fmo_4mz_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t c
             if (n - pos < c) return FMO_ERR_INPUT;
             if (fmo_xxh32(in + pos, c, 0) != ck) return FMO_ERR_CONTENT;
             if (u > cap - op) return FMO_ERR_OUTPUT;
-            if (u == c) memcpy(out + op, in + pos, c);
-            else if (fmo_zstd_decompress(out + op, u, in + pos, c) != (long long)u) return FMO_ERR_CONTENT;
-            op += u; pos += c;
+            if (u == c) { memcpy(out + op, in + pos, c); op += u; }
+            else {
+                /* native/4mc.c:810-815: whatever ZSTD_decompress returns is written (`filesize += decodedBytes`) */
+                const long long dsz = fmo_zstd_decompress(out + op, u, in + pos, c);
+                if (dsz < 0) return FMO_ERR_CONTENT;
+                op += (size_t)dsz;
+            }
+            pos += c;
         }
         {
             uint32_t fsize;
@@ -463,6 +469,7 @@ long long fmo_4mz_decompress(const uint8_t *in, size_t n, uint8_t *out, size_t c
             if (be32(in + pos + fsize - 4) != fmo_xxh32(in + pos, fsize - 4, 0)) return FMO_ERR_CONTENT;
             pos += fsize;
         }
+        if (op == op_before) break;           /* native/4mc.c:943-947 `do {...} while (decodedSize)` */
     }
     return (long long)op;
 }

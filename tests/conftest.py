@@ -180,3 +180,35 @@ def ctx(pkg):
     c = pkg.Context(0)
     yield c
     c.close()
+
+
+def _be32(v):
+    return int(v).to_bytes(4, "big")
+
+
+def make_4mc(ora, records, magic=b"4MC\0"):
+    """A .4mc / .4mz stream from (announced_usize, payload) records (hand-built edge cases: the container
+    fields as native/4mc.c:263-362 writes them, checksums from the oracle's XXH32)."""
+    hdr = magic + _be32(1)
+    out = hdr + _be32(ora.xxh32(hdr))
+    lens = []
+    for usize, payload in records:
+        out += _be32(usize) + _be32(len(payload)) + _be32(ora.xxh32(payload)) + payload
+        lens.append(12 + len(payload))
+    out += bytes(12)
+    fsize = 20 + 4 * len(records)
+    foot = _be32(fsize) + _be32(1)
+    for i in range(len(records)):
+        foot += _be32(12 if i == 0 else lens[i - 1])
+    foot += _be32(fsize) + magic
+    return out + foot + _be32(ora.xxh32(foot))
+
+
+def short_block_stream(ora):
+    """Three blocks, the middle one announcing 100 bytes while its LZ4 payload (a 52-byte literal-only block)
+    decodes to 50: the reference writes what the decoder returned (native/4mc.c:661-666)."""
+    a = bytes(range(65, 91)) * 40                       # 1040 bytes, compressible
+    lits = bytes((i * 7 + 3) & 0xFF for i in range(50))
+    short = bytes([0xF0, 50 - 15]) + lits                # token: 15+ literals, no match
+    c = bytes(reversed(a))
+    return make_4mc(ora, [(len(a), ora.lz4_compress(a)), (100, short), (len(c), c)]), a + lits + c

@@ -107,6 +107,42 @@ def test_container_decode_golden(ctx):
     assert ctx.decompress_4mc(golden_bytes("two_streams.4mc")) == b"A" + text
 
 
+def test_compressed_bytes_are_reproducible(ctx, pkg):
+    """The match finders' tables are filled by racing stores; ties are settled by position (lowest / highest),
+    so two runs -- and two contexts -- give the same bytes (a storage format wants reproducible artefacts)."""
+    data = gen_logtext(pkg, 3 * 4194304 + 4321, seed=77)
+    other = pkg.Context(0)
+    try:
+        for level in (1, 2, 3, 4):
+            a = ctx.compress_4mc(data, level=level)
+            assert ctx.compress_4mc(data, level=level) == a and other.compress_4mc(data, level=level) == a, level
+        for level in (1, 3):
+            z = ctx.compress_4mz(data, level=level)
+            assert ctx.compress_4mz(data, level=level) == z and other.compress_4mz(data, level=level) == z, level
+    finally:
+        other.close()
+
+
+def test_short_block_and_empty_stream(ctx, ora, pkg):
+    """A block that decodes to fewer bytes than its header announces moves the following blocks down
+    (native/4mc.c:661-666); a stream that decodes to nothing ends the loop over streams (:909-913).  Host call,
+    device call and the split reader against the oracle (itself checked against the reference CLI)."""
+    import torch
+    from conftest import short_block_stream
+    stream, expect = short_block_stream(ora)
+    assert ora.decompress_4mc(stream, len(expect) + 4096) == (len(expect), expect)
+    assert ctx.decompress_4mc(stream) == expect
+    d_in = torch.frombuffer(bytearray(stream), dtype=torch.uint8).cuda()
+    d_out = torch.zeros(len(expect) + 4096, dtype=torch.uint8, device="cuda")
+    res = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ctx.decompress_device(d_in.data_ptr(), len(stream), d_out.data_ptr(), d_out.numel(), res.data_ptr())
+    torch.cuda.synchronize()
+    assert res.cpu().tolist() == [len(expect), -1]
+    assert bytes(d_out[:len(expect)].cpu().numpy()) == expect
+    assert ctx.decompress_4mc(golden_bytes("empty.4mc") + golden_bytes("A.4mc")) == b""
+    assert ctx.decompress_4mc(golden_bytes("A.4mc") + golden_bytes("empty.4mc") + golden_bytes("A.4mc")) == b"A"
+
+
 def test_container_decode_errors_match_reference_exit_codes(ctx, ora):
     good = golden_bytes("logtext_128k.l1.4mc")
     n = 128 * 1024

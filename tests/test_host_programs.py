@@ -50,7 +50,80 @@ def test_cli_fails_loudly_without_a_device(tmp_path):
     assert subprocess.run([CLI, "-x"], capture_output=True).returncode == 1          # bad usage -> exit 1
 
 
+REF_CLI_ON_US = os.path.join(ROOT, "tests", "_build", "ref_4mccli_on_lib4mcgpu")
+
+
+def test_reference_cli_source_links_against_this_library():
+    """native/4mc.h:36-41: the four entry points the reference's own CLI calls are exported, so its
+    native/4mccli.c -- unmodified, compiled where it lies -- links against lib4mcgpu.so (the binary travels to
+    the GPU box and is run there by test_reference_cli_binary_runs_on_this_library)."""
+    out = subprocess.run(["nm", "-D", os.path.join(ROOT, "4mc_b200", "lib4mcgpu.so")], capture_output=True, text=True, check=True).stdout
+    have = {l.split()[2] for l in out.splitlines() if " T " in l}
+    assert {"fourMCcompressFilename", "fourMcDecompressFileName", "fourMZcompressFilename", "fourMZDecompressFileName"} <= have
+    ref_src = "/root/reference/native/4mccli.c"
+    if not os.path.exists(ref_src):
+        pytest.skip("reference sources not present")
+    os.makedirs(os.path.dirname(REF_CLI_ON_US), exist_ok=True)
+    subprocess.run(["gcc", "-O2", "-w", "-I/root/reference/native", "-o", REF_CLI_ON_US, ref_src,
+                    "-L" + os.path.join(ROOT, "4mc_b200"), "-l4mcgpu", "-Wl,-rpath," + os.path.join(ROOT, "4mc_b200"),
+                    "-Wl,-rpath,$ORIGIN/../../4mc_b200"], check=True)
+    assert subprocess.run([REF_CLI_ON_US, "-V"], capture_output=True).returncode == 0
+
+
 # ---------------------------------------------------------------- on the GPU box
+
+@pytest.mark.gpu
+def test_reference_cli_binary_runs_on_this_library(ref_cli, pkg, tmp_path):
+    """The reference's 4mccli.c linked against lib4mcgpu.so (built by the CPU test above): round trips of both
+    containers, checked against the reference's own build."""
+    if not os.path.exists(REF_CLI_ON_US):
+        pytest.skip("tests/_build/ref_4mccli_on_lib4mcgpu was not built (no reference sources on the build box)")
+    data = gen_logtext(pkg, 5 * 1024 * 1024 + 77)
+    src = tmp_path / "d.bin"
+    src.write_bytes(data)
+    for flags, ext in (([], ".4mc"), (["-z"], ".4mz"), (["-3"], ".4mc")):
+        comp, back, back2 = tmp_path / ("c" + ext), tmp_path / "back", tmp_path / "back2"
+        assert subprocess.run([REF_CLI_ON_US, "-f", "-q", "-q"] + flags + [str(src), str(comp)]).returncode == 0
+        zd = ["-z"] if ext == ".4mz" else []
+        subprocess.run([ref_cli, "-f", "-q", "-q", "-d"] + zd + [str(comp), str(back)], check=True)
+        assert subprocess.run([REF_CLI_ON_US, "-f", "-q", "-q", "-d"] + zd + [str(comp), str(back2)]).returncode == 0
+        assert back.read_bytes() == data and back2.read_bytes() == data
+
+
+@pytest.mark.gpu
+def test_files_stream_through_in_slices(ref_cli, pkg, tmp_path):
+    """File -> file in slices of many blocks through pinned bounce buffers (4mc_b200/csrc/fileio.h): an input of
+    several slices plus a ragged tail, pipes on both ends, two concatenated streams, and a damaged block in the
+    second slice -- whose predecessors reach the output before the error, like the serial reader."""
+    n = 331 * 1024 * 1024 + 12345                            # > 2 writer slices (128 MiB), > 2 reader chunks (160 MiB)
+    data = gen_logtext(pkg, n)
+    src, ours, theirs = tmp_path / "big.bin", tmp_path / "big.4mc", tmp_path / "ref.4mc"
+    src.write_bytes(data)
+    assert subprocess.run([CLI, "-f", "-q", str(src), str(ours)]).returncode == 0
+    subprocess.run([ref_cli, "-f", "-q", "-q", "-d", str(ours), str(tmp_path / "o1")], check=True)
+    assert (tmp_path / "o1").read_bytes() == data
+    subprocess.run([ref_cli, "-f", "-q", "-q", str(src), str(theirs)], check=True)
+    assert subprocess.run([CLI, "-f", "-q", "-d", str(theirs), str(tmp_path / "o2")]).returncode == 0
+    assert (tmp_path / "o2").read_bytes() == data
+    # pipes: stdin -> stdout, both directions
+    r = subprocess.run([CLI, "-q", "-c"], stdin=open(src, "rb"), capture_output=True)
+    assert r.returncode == 0
+    r2 = subprocess.run([CLI, "-q", "-c", "-d"], input=r.stdout, capture_output=True)
+    assert r2.returncode == 0 and r2.stdout == data
+    # two streams back to back (native/4mc.c:909-913)
+    cat = tmp_path / "two.4mc"
+    cat.write_bytes(ours.read_bytes() + golden_bytes("A.4mc"))
+    assert subprocess.run([CLI, "-f", "-q", "-d", str(cat), str(tmp_path / "o3")]).returncode == 0
+    assert (tmp_path / "o3").read_bytes() == data + b"A"
+    # damage far into the file: same exit code and same partial output as the reference
+    blob = bytearray(theirs.read_bytes())
+    blob[len(blob) * 3 // 4] ^= 0x40
+    bad = tmp_path / "bad.4mc"
+    bad.write_bytes(bytes(blob))
+    a = subprocess.run([CLI, "-f", "-q", "-d", str(bad), str(tmp_path / "p1")], capture_output=True).returncode
+    b = subprocess.run([ref_cli, "-f", "-q", "-q", "-d", str(bad), str(tmp_path / "p2")], capture_output=True).returncode
+    assert a == b == 4
+    assert (tmp_path / "p1").read_bytes() == (tmp_path / "p2").read_bytes()
 
 @pytest.mark.gpu
 def test_cli_round_trip_and_cross_compatibility(ref_cli, pkg, tmp_path):

@@ -49,6 +49,23 @@ def test_container_golden_decode(ora):
     assert out == b"A" + text
 
 
+def test_short_block_and_empty_stream_follow_the_reference(ora, ref_cli, tmp_path):
+    """Two corners of the serial reader: a block that decodes to fewer bytes than it announces is
+    written as decoded (native/4mc.c:661-666), and a stream that decodes to nothing ends the loop over
+    concatenated streams (:909-913).  The oracle against the reference CLI itself."""
+    import subprocess
+    from conftest import short_block_stream
+    stream, expect = short_block_stream(ora)
+    cases = [(stream, expect), (golden_bytes("empty.4mc") + golden_bytes("A.4mc"), b""),
+             (golden_bytes("A.4mc") + golden_bytes("empty.4mc") + golden_bytes("A.4mc"), b"A")]
+    for i, (data, want) in enumerate(cases):
+        assert ora.decompress_4mc(data, len(want) + 4096) == (len(want), want)
+        src, dst = tmp_path / f"c{i}.4mc", tmp_path / f"c{i}.out"
+        src.write_bytes(data)
+        assert subprocess.run([ref_cli, "-d", "-f", "-q", str(src), str(dst)]).returncode == 0
+        assert dst.read_bytes() == want
+
+
 def test_container_golden_layout(ora):
     # SURVEY.md 8c byte layouts
     assert golden_bytes("empty.4mc").hex() == ("344d430000000001a4b73443" "000000000000000000000000"
