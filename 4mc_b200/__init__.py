@@ -64,6 +64,7 @@ def lib() -> C.CDLL:
         "fourmc_kernel_launches": (u64, [vp]),
         "fourmc_sync": (i32, [vp, vp]),
         "fourmc_timing_enable": (i32, [vp, i32]),
+        "fourmc_ctx_set_reproducible": (i32, [vp, i32]),
         "fourmc_timing_collect": (C.c_longlong, [vp, C.c_char_p, sz]),
         "fourmc_lz4_compress_bound": (i32, [i32]),
         "fourmc_lz4_compress": (i32, [vp, i32, vp, i32, vp, i32]),
@@ -77,6 +78,10 @@ def lib() -> C.CDLL:
         "fourmc_4mc_compress_span_device": (i32, [vp, vp, i32, vp, sz, vp, sz, vp, vp]),
         "fourmc_4mc_build_index_device": (i32, [vp, vp, vp, u32, vp, vp]),
         "fourmc_4mc_decompress_device": (i32, [vp, vp, vp, sz, vp, sz, vp]),
+        "fourmc_4mc_decompress_range_device": (i32, [vp, vp, vp, sz, u32, u32, vp, sz, vp]),
+        "fourmc_4mz_decompress_range_device": (i32, [vp, vp, vp, sz, u32, u32, vp, sz, vp]),
+        "fourmc_compress_fd": (C.c_longlong, [vp, i32, i32, i32, i32, C.POINTER(u64)]),
+        "fourmc_decompress_fd": (C.c_longlong, [vp, i32, i32, i32, C.POINTER(u64)]),
         "fourmc_lz4_decompress_batch_device": (i32, [vp, vp, u32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
         "fourmc_xxh32_batch_device": (i32, [vp, vp, u32, vp, vp, vp, u32, vp]),
         "fourmc_4mz_decompress_host": (C.c_longlong, [vp, vp, sz, vp, sz]),
@@ -151,6 +156,10 @@ class Context:
 
     def sync(self, stream=None):
         self._check(lib().fourmc_sync(self._h, stream))
+
+    def set_reproducible(self, mode: int):
+        """-1: per entry point (host-facing calls yes, device-resident calls no), 0 / 1: never / always."""
+        self._check(lib().fourmc_ctx_set_reproducible(self._h, mode))
 
     def timing_enable(self, on: bool = True):
         self._check(lib().fourmc_timing_enable(self._h, 1 if on else 0))
@@ -332,6 +341,12 @@ class Context:
 
     def decompress_device(self, d_in: int, n: int, d_out: int, out_capacity: int, d_result: int, stream=None):
         self._check(lib().fourmc_4mc_decompress_device(self._h, stream, d_in, n, d_out, out_capacity, d_result))
+
+    def decompress_range_device(self, d_in: int, n: int, first_block: int, n_blocks: int, d_out: int, out_capacity: int,
+                                d_result: int, stream=None, zstd: bool = False):
+        """Blocks [first_block, first_block + n_blocks) of ONE stream (a rank's share)."""
+        f = lib().fourmc_4mz_decompress_range_device if zstd else lib().fourmc_4mc_decompress_range_device
+        self._check(f(self._h, stream, d_in, n, first_block, n_blocks, d_out, out_capacity, d_result))
 
     def xxh32_batch_device(self, n_items: int, d_base: int, d_off: int, d_len: int, d_out: int, seed: int = 0, stream=None):
         self._check(lib().fourmc_xxh32_batch_device(self._h, stream, n_items, d_base, d_off, d_len, seed, d_out))

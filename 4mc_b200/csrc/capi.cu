@@ -57,12 +57,16 @@ struct fourmc_ctx {
     cudaEvent_t ev[FM_PIPE_MAX] = {};
     std::string err;
     uint64_t launches = 0;
+    // compressed bytes identical from run to run (ties between racing match-finder stores settled by position):
+    // -1 = per entry point (host / file / per-block calls: yes; device-resident calls: no, they favour speed), 0 / 1 = always
+    int reproducible = -1;
+    int repro_call = 1;                  // what the entry point in progress resolved it to
     EncWs enc[FM_PIPE_MAX];
     DecWs dec[FM_PIPE_MAX];
     DevBuf stage_in[FM_PIPE_MAX], stage_out[FM_PIPE_MAX];    // device staging for the host-pointer entry points
     void *pinned = nullptr;              // small pinned scratch for scalars
     size_t pinned_cap = 0;
-    bool region_attr_set = false, d1_attr_set = false, zd_attr_set = false, gen_attr_set = false;   // per context = per device
+    bool region_attr_set = false, d1_attr_set = false, d2_attr_set = false, d1w_attr_set = false, zd_attr_set = false, gen_attr_set = false;   // per context = per device
     DevBuf ztables;                      // fmz::Tables (constant decode tables), uploaded once
     // optional per-kernel timing (fourmc_timing_enable): CUDA event pairs around every launch
     bool timing = false;
@@ -289,6 +293,7 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     P.depth = depth; P.lazy = depth > 0;
     P.region_bytes = region_bytes; P.regions_per_block = rpb;
     P.block_bytes = block_bytes;
+    P.reproducible = ctx->repro_call;
     if (P.depth > 0) {
         const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
         KL("lz4_region_chain_kernel", st, lz4_region_kernel<false, true><<<grid, ENC_CHAIN_THREADS, ENC_SMEM_CHAIN, st>>>(P));
@@ -373,6 +378,7 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
         P.depth = depth; P.lazy = depth > 0;
         P.region_bytes = region_bytes; P.regions_per_block = rpb;
         P.block_bytes = block_bytes;
+        P.reproducible = ctx->repro_call;
         if (P.depth > 0) {
             const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
             KL("lz4_region_chain_kernel", st, lz4_region_kernel<true, true><<<grid, ENC_CHAIN_THREADS, ENC_SMEM_CHAIN, st>>>(P));
@@ -419,26 +425,32 @@ int ensure_side(fourmc_ctx *ctx, DecWs &ws)
 // ws.status.  max_chunks bounds the chunk indices used by the descriptors.
 
 // compact: the descriptors' destinations are consecutive (a stream): blocks that decode short are moved down.
+// first: the nb blocks are entries [first, first + nb) of the workspace's descriptor / checksum / status tables
+// (a block range of a longer stream).
 int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t max_chunks, int check_xxh,
-               int32_t *d_out_size, const IndexInfo *d_info, long long *d_result, int codec = CODEC_LZ4, int compact = 0)
+               int32_t *d_out_size, const IndexInfo *d_info, long long *d_result, int codec = CODEC_LZ4, int compact = 0,
+               uint32_t first = 0)
 {
     int r;
     if (codec == CODEC_ZSTD) max_chunks = 0;
     if ((r = ensure(ctx, ws.tokmap, (max_chunks + 1) * LZ4_CHUNK_WORDS * 4))) return r;
     if ((r = ensure(ctx, ws.chunkop, (max_chunks + 1) * 4))) return r;
     if ((r = ensure(ctx, ws.result, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
+    const BlockDesc *const desc_all = (const BlockDesc *)ws.desc.p + first;
+    const uint32_t *const xxh_all = (const uint32_t *)ws.xxh.p + first;
+    uint8_t *const status_all = (uint8_t *)ws.status.p + first;
     bool verify_forked = false;
     if (nb) {
         CK(cudaMemsetAsync(ws.tokmap.p, 0, (max_chunks + 1) * LZ4_CHUNK_WORDS * 4, st));
-        const BlockDesc *desc = (const BlockDesc *)ws.desc.p;
-        uint8_t *status = (uint8_t *)ws.status.p;
+        const BlockDesc *desc = desc_all;
+        uint8_t *status = status_all;
         if (check_xxh) {
             int rs;
             if ((rs = ensure_side(ctx, ws))) return rs;
             CK(cudaEventRecord(ws.fork, st));
             CK(cudaStreamWaitEvent(ws.side, ws.fork, 0));
             KL("xxh_verify_kernel", ws.side, xxh_verify_kernel<<<(nb + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, ws.side>>>(
-                desc, (const uint32_t *)ws.xxh.p, nb, status));
+                desc, xxh_all, nb, status));
             CK(cudaEventRecord(ws.join, ws.side));
             verify_forked = true;
         }
@@ -485,9 +497,23 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             }
             KL("zstd_frames_kernel", st, zstd_frames_kernel<<<(nb + 31) / 32, 32, 0, st>>>(desc, nb, (fmz::Work *)ws.zwork.p,
                                                            (const fmz::Tables *)ctx->ztables.p, (int32_t *)ws.result.p, zd_serial ? 0 : 1));
-        } else
-        KL("lz4_parse_kernel", st, lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, D1_SMEM, st>>>(desc, nb, (uint32_t *)ws.tokmap.p, (uint32_t *)ws.chunkop.p,
-                                                       (int32_t *)ws.result.p));
+        } else {
+            // few blocks: a CTA of 16 warps per block (its chain walk is the only serial part, ~1 ms per block and
+            // one block per SM at a time); many blocks: a warp per block.  FOURMC_D1_WIDE=0|1 forces one of them.
+            static int wide_forced = -1;
+            if (wide_forced < 0) { const char *e = getenv("FOURMC_D1_WIDE"); wide_forced = e ? (atoi(e) ? 1 : 0) : 2; }
+            const bool wide = wide_forced == 2 ? nb <= (uint32_t)ctx->sm_count * 6 : wide_forced == 1;
+            if (wide) {
+                if (!ctx->d1w_attr_set) {
+                    CK(cudaFuncSetAttribute(lz4_parse_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D1W_SMEM));
+                    ctx->d1w_attr_set = true;
+                }
+                KL("lz4_parse_wide_kernel", st, lz4_parse_wide_kernel<<<nb, D1W_THREADS, D1W_SMEM, st>>>(desc, nb, (uint32_t *)ws.tokmap.p,
+                                                                       (uint32_t *)ws.chunkop.p, (int32_t *)ws.result.p));
+            } else
+                KL("lz4_parse_kernel", st, lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, D1_SMEM, st>>>(desc, nb, (uint32_t *)ws.tokmap.p,
+                                                               (uint32_t *)ws.chunkop.p, (int32_t *)ws.result.p));
+        }
         for (uint32_t b0 = 0; b0 < nb; b0 += 32768) {
             const uint32_t cnt = std::min<uint32_t>(32768, nb - b0);
             KL("lz4_stored_kernel", st, lz4_stored_kernel<<<dim3(32, cnt), 256, 0, st>>>(desc + b0, cnt));
@@ -497,25 +523,31 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             static int forced = -1;
             if (forced < 0) { const char *e = getenv("FOURMC_D2_WARPS"); forced = e ? atoi(e) : 0; }
             int w = forced;
-            if (w != 1 && w != 2 && w != 4 && w != 8) {
+            if (w != 1 && w != 2 && w != 4 && w != 8 && w != 16 && w != 32) {
                 const uint32_t want = (uint32_t)ctx->sm_count * 24;        // resident warps to aim for (measured, profiles/)
-                w = nb * 1 >= want ? 1 : nb * 2 >= want ? 2 : nb * 4 >= want ? 4 : 8;
+                w = 32;
+                for (int c = 1; c <= 16; c *= 2) if (nb * (uint32_t)c >= want) { w = c; break; }
+            }
+            if (!ctx->d2_attr_set) {
+                CK(cudaFuncSetAttribute(lz4_copy_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_bytes<16>()));
+                CK(cudaFuncSetAttribute(lz4_copy_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_bytes<32>()));
+                ctx->d2_attr_set = true;
             }
             const uint32_t *tm = (const uint32_t *)ws.tokmap.p, *co = (const uint32_t *)ws.chunkop.p;
             const int32_t *rs = (const int32_t *)ws.result.p;
-            if (w == 1) KL("lz4_copy_kernel", st, lz4_copy_kernel<1><<<nb, 32, 0, st>>>(desc, tm, co, rs));
-            else if (w == 2) KL("lz4_copy_kernel", st, lz4_copy_kernel<2><<<nb, 64, 0, st>>>(desc, tm, co, rs));
-            else if (w == 4) KL("lz4_copy_kernel", st, lz4_copy_kernel<4><<<nb, 128, 0, st>>>(desc, tm, co, rs));
-            else KL("lz4_copy_kernel", st, lz4_copy_kernel<8><<<nb, 256, 0, st>>>(desc, tm, co, rs));
+#define D2_LAUNCH(WW) KL("lz4_copy_kernel", st, lz4_copy_kernel<WW><<<nb, WW * 32, d2_smem_bytes<WW>(), st>>>(desc, tm, co, rs))
+            if (w == 1) D2_LAUNCH(1); else if (w == 2) D2_LAUNCH(2); else if (w == 4) D2_LAUNCH(4); else if (w == 8) D2_LAUNCH(8);
+            else if (w == 16) D2_LAUNCH(16); else D2_LAUNCH(32);
+#undef D2_LAUNCH
         }
     }
     if (verify_forked) CK(cudaStreamWaitEvent(st, ws.join, 0));
     if ((r = ensure(ctx, ws.final_, 16))) return r;
-    KL("finalize_kernel", st, finalize_kernel<<<1, SCAN_THREADS, 0, st>>>((const BlockDesc *)ws.desc.p, (const int32_t *)ws.result.p, nb,
-                                                (uint8_t *)ws.status.p, d_out_size, d_info, d_result, (uint32_t *)ws.final_.p));
+    KL("finalize_kernel", st, finalize_kernel<<<1, SCAN_THREADS, 0, st>>>(desc_all, (const int32_t *)ws.result.p, nb,
+                                                status_all, d_out_size, d_info, d_result, (uint32_t *)ws.final_.p));
     if (compact && nb)
-        KL("compact_kernel", st, compact_kernel<<<1, SCAN_THREADS, 0, st>>>((const BlockDesc *)ws.desc.p, (const int32_t *)ws.result.p,
-                                                  (const uint8_t *)ws.status.p, nb, (const uint32_t *)ws.final_.p));
+        KL("compact_kernel", st, compact_kernel<<<1, SCAN_THREADS, 0, st>>>(desc_all, (const int32_t *)ws.result.p,
+                                                  status_all, nb, (const uint32_t *)ws.final_.p));
     return FOURMC_OK;
 }
 
@@ -602,6 +634,7 @@ int fourmc_ctx_create(fourmc_ctx **out, int device)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return FOURMC_E_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("FOURMC_REPRODUCIBLE")) { ctx->reproducible = atoi(e) ? 1 : 0; ctx->repro_call = ctx->reproducible; }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return FOURMC_E_CUDA; }
     for (int i = 0; i < FM_PIPE_MAX; i++) {
         if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
@@ -647,6 +680,14 @@ int fourmc_sync(fourmc_ctx *ctx, void *stream)
 {
     if (!ctx) return FOURMC_E_ARG;
     CK(cudaStreamSynchronize(pick(ctx, stream)));
+    return FOURMC_OK;
+}
+
+int fourmc_ctx_set_reproducible(fourmc_ctx *ctx, int mode)
+{
+    if (!ctx || mode < -1 || mode > 1) return FOURMC_E_ARG;
+    ctx->reproducible = mode;
+    ctx->repro_call = mode < 0 ? 1 : mode;
     return FOURMC_OK;
 }
 
@@ -705,7 +746,9 @@ static int compress_span_impl(fourmc_ctx *ctx, void *stream, int codec, int leve
     if (span_capacity < n + 12ull * nb) return fail(ctx, FOURMC_E_OUTPUT, "span capacity below the all-stored bound");
     cudaStream_t st = pick(ctx, stream);
     EncWs &ws = ctx->enc[0];
+    ctx->repro_call = ctx->reproducible < 0 ? 0 : ctx->reproducible;
     int r = enc_span_codec(ctx, st, ws, codec, level, (const uint8_t *)d_in, n, (uint8_t *)d_span, 0, d_block_lens, -1);
+    ctx->repro_call = ctx->reproducible < 0 ? 1 : ctx->reproducible;
     if (r) return r;
     if (d_span_size)
         CK(cudaMemcpyAsync(d_span_size, (uint8_t *)ws.misc.p + 8, 8, cudaMemcpyDeviceToDevice, st));
@@ -760,7 +803,10 @@ static int compress_device_impl(fourmc_ctx *ctx, void *stream, int codec, int le
     if ((r = ensure(ctx, ws.lens, (size_t)std::max<uint32_t>(nb, 1) * 4))) return r;
     uint32_t *lens = d_block_lens ? d_block_lens : (uint32_t *)ws.lens.p;
     // block b's header lands at d_out + 12 + sum of earlier record lengths
-    if ((r = enc_span_codec(ctx, st, ws, codec, level, (const uint8_t *)d_in, n, (uint8_t *)d_out, 12, lens, -1))) return r;
+    ctx->repro_call = ctx->reproducible < 0 ? 0 : ctx->reproducible;
+    r = enc_span_codec(ctx, st, ws, codec, level, (const uint8_t *)d_in, n, (uint8_t *)d_out, 12, lens, -1);
+    ctx->repro_call = ctx->reproducible < 0 ? 1 : ctx->reproducible;
+    if (r) return r;
     KL("write_index_kernel", st, write_index_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, 12, codec == CODEC_ZSTD ? FOURMC_MAGIC_4MZ : FOURMC_MAGIC_4MC,
                                                    (uint8_t *)d_out, (uint8_t *)d_out + 12,
                                                    (const uint64_t *)((uint8_t *)ws.misc.p + 8),
@@ -782,8 +828,9 @@ int fourmc_4mz_compress_device(fourmc_ctx *ctx, void *stream, int level, const v
     return compress_device_impl(ctx, stream, CODEC_ZSTD, level, d_in, n, d_out, out_capacity, d_out_size, d_block_lens);
 }
 
+// first / count: the block range to decode (count = 0xffffffff: to the end); the output of block `first` lands at d_out.
 static int decompress_device_impl(fourmc_ctx *ctx, void *stream, int codec, const void *d_in, size_t n, void *d_out,
-                                  size_t out_capacity, long long *d_result)
+                                  size_t out_capacity, long long *d_result, uint32_t first = 0, uint32_t count = 0xffffffffu)
 {
     if (!ctx || !d_in || !d_result) return FOURMC_E_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -821,9 +868,13 @@ static int decompress_device_impl(fourmc_ctx *ctx, void *stream, int codec, cons
     CK(cudaMemsetAsync(ws.xxh.p, 0, (size_t)std::max<uint32_t>(nb, 1) * 4, st));
     KL("read_index_kernel", st, read_index_kernel<<<1, SCAN_THREADS, 0, st>>>((const uint8_t *)d_in, n, nb, (uint8_t *)d_out, out_capacity,
                                                   (BlockDesc *)ws.desc.p, (uint32_t *)ws.xxh.p, (uint8_t *)ws.status.p,
-                                                  (IndexInfo *)ws.info.p, codec == CODEC_ZSTD ? FOURMC_MAGIC_4MZ : FOURMC_MAGIC_4MC));
-    const size_t max_chunks = n / LZ4_CHUNK + 2 * (size_t)nb + 2;
-    return dec_blocks(ctx, st, ws, nb, max_chunks, 1, nullptr, (const IndexInfo *)ws.info.p, d_result, codec, 1);
+                                                  (IndexInfo *)ws.info.p, codec == CODEC_ZSTD ? FOURMC_MAGIC_4MZ : FOURMC_MAGIC_4MC,
+                                                  first, count));
+    first = std::min(first, nb);
+    const uint32_t cnt = std::min(count, nb - first);
+    // chunk indices are rebased to the range's first block: the range's payload bounds the side tables
+    const size_t max_chunks = (cnt == nb ? n : std::min<size_t>(n, (size_t)cnt * (FOURMC_BLOCKSIZE + 64))) / LZ4_CHUNK + 2 * (size_t)cnt + 2;
+    return dec_blocks(ctx, st, ws, cnt, max_chunks, 1, nullptr, (const IndexInfo *)ws.info.p, d_result, codec, 1, first);
 }
 
 int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n, void *d_out,
@@ -836,6 +887,18 @@ int fourmc_4mz_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in
                                  size_t out_capacity, long long *d_result)
 {
     return decompress_device_impl(ctx, stream, CODEC_ZSTD, d_in, n, d_out, out_capacity, d_result);
+}
+
+int fourmc_4mc_decompress_range_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n, uint32_t first_block,
+                                       uint32_t n_blocks, void *d_out, size_t out_capacity, long long *d_result)
+{
+    return decompress_device_impl(ctx, stream, CODEC_LZ4, d_in, n, d_out, out_capacity, d_result, first_block, n_blocks);
+}
+
+int fourmc_4mz_decompress_range_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n, uint32_t first_block,
+                                       uint32_t n_blocks, void *d_out, size_t out_capacity, long long *d_result)
+{
+    return decompress_device_impl(ctx, stream, CODEC_ZSTD, d_in, n, d_out, out_capacity, d_result, first_block, n_blocks);
 }
 
 // batch decode over caller tables with an explicit workspace (the host pipeline keeps two in flight)

@@ -107,14 +107,18 @@ struct IndexInfo {              // device-side summary of one parsed stream
 // re-derives it and fails if they disagree.
 __global__ void __launch_bounds__(SCAN_THREADS)
 read_index_kernel(const uint8_t *in, uint64_t n, uint32_t n_blocks_host, uint8_t *out, uint64_t out_cap,
-                  BlockDesc *desc, uint32_t *xxh_expect, uint8_t *status, IndexInfo *info, uint32_t magic)
+                  BlockDesc *desc, uint32_t *xxh_expect, uint8_t *status, IndexInfo *info, uint32_t magic,
+                  uint32_t first = 0, uint32_t count = 0xffffffffu)
 {
+    // [first, first + count): the block range the caller decodes (a rank's share of the stream).
+    // The whole index is validated either way; output offsets and chunk indices count from block `first`.
     __shared__ __align__(16) uint32_t s_stage[XXH_WARP_SMEM_WORDS];
     __shared__ unsigned long long tmp[32];
     __shared__ int s_err;
     __shared__ uint32_t s_foot_hash;
+    __shared__ unsigned long long s_base_out, s_base_chunk;
 
-    if (threadIdx.x == 0) s_err = FOURMC_OK;
+    if (threadIdx.x == 0) { s_err = FOURMC_OK; s_base_out = 0; s_base_chunk = 0; }
     __syncthreads();
 
     // header :577-585, footer :670-688 / FourMcInputStream.java:187-228
@@ -190,14 +194,18 @@ read_index_kernel(const uint8_t *in, uint64_t n, uint32_t n_blocks_host, uint8_t
         const unsigned long long cincl = cta_incl_scan_u64(nch, tmp, &total);
         const unsigned long long chunk_base = c_chunks + cincl - nch;
         c_chunks += total;
+        if (live && i == first) { s_base_out = dst_off; s_base_chunk = chunk_base; }
+        __syncthreads();
         if (live) {
+            const bool mine = i >= first && i - first < count;
+            const unsigned long long my_out = dst_off - s_base_out;
             BlockDesc d;
-            d.src = in + off + 12; d.dst = out + dst_off;
-            d.csize = c; d.usize = u; d.chunk_base = (uint32_t)chunk_base; d.stored = (c == u) ? 1u : 0u;
+            d.src = in + off + 12; d.dst = mine ? out + my_out : nullptr;
+            d.csize = c; d.usize = u; d.chunk_base = mine ? (uint32_t)(chunk_base - s_base_chunk) : 0u; d.stored = (c == u) ? 1u : 0u;
             uint8_t st = FOURMC_BLOCK_OK;
             if (bad) { st = FOURMC_BLOCK_CORRUPT; atomicMin(&s_err, FOURMC_E_CONTENT); d.csize = 0; d.usize = 0; d.stored = 1; }
             else if (toolarge) { st = FOURMC_BLOCK_TOOLARGE; d.csize = 0; d.usize = 0; d.stored = 1; }
-            else if (dst_off + u > out_cap) { atomicMin(&s_err, FOURMC_E_OUTPUT); d.csize = 0; d.usize = 0; d.stored = 1; }
+            else if (mine && my_out + u > out_cap) { atomicMin(&s_err, FOURMC_E_OUTPUT); d.csize = 0; d.usize = 0; d.stored = 1; }
             desc[i] = d; xxh_expect[i] = ck; status[i] = st;
         }
         if (nb == 0) break;

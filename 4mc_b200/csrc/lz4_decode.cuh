@@ -117,6 +117,99 @@ __device__ __forceinline__ SeqDec d1_decode_slow(const RingReader &rd, int ip, i
     return r;
 }
 
+// Phase B of the bulk parse (see lz4_parse_kernel): the exit function of this lane's 64-position sub-chunk of
+// the half at aligned position base_q, folded back to front.  Each position is read AS IF a token started there:
+// a sequence without continued lengths is 3 + lit bytes long and produces lit + ml + 4 bytes; a length continued by
+// ONE byte is folded in (literal runs of 15+ and matches of 19+ are common); longer continuations stop the fold
+// (D1_SPECIAL: the chain walk decodes that sequence byte by byte).
+__device__ __forceinline__ void d1_fold(const uint8_t *ring, uint16_t *X, uint16_t *S, const int base_q, const int lane)
+{
+    const uint4 *mine = (const uint4 *)(ring + ((base_q + lane * D1_SUB) & (D1_RING - 1)));
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const uint4 v = mine[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+    uint16_t *xm = X + lane * D1_X_STRIDE;
+    uint16_t *sm = S + lane * D1_S_STRIDE;
+    const int sub_q = base_q + lane * D1_SUB;
+#pragma unroll
+    for (int jj = D1_SUB - 1; jj >= 0; jj--) {
+        const unsigned tok = (w[jj >> 2] >> ((jj & 3) * 8)) & 0xffu;
+        int lit = (int)(tok >> 4), ml = (int)(tok & 15), n = jj + 3;
+        bool special = false;
+        if (lit == 15) {
+            const unsigned x = (jj + 1 < D1_SUB) ? ((w[(jj + 1) >> 2 & 15] >> (((jj + 1) & 3) * 8)) & 0xffu)
+                                                : (unsigned)ring[(sub_q + D1_SUB) & (D1_RING - 1)];
+            special = x == 255;
+            lit += (int)x; n++;
+        }
+        n += lit;
+        if (ml == 15 && !special) {
+            const unsigned x = ring[(sub_q + n) & (D1_RING - 1)];
+            special = x == 255;
+            ml += (int)x; n++;
+        }
+        int ex, os = lit + ml + 4;
+        if (special) { ex = jj | D1_SPECIAL; os = 0; }
+        else if (n < D1_SUB) { ex = (int)xm[n]; os += (int)sm[n]; }
+        else ex = n;
+        xm[jj] = (uint16_t)ex;
+        sm[jj] = (uint16_t)os;
+    }
+}
+
+// Phase D: this lane's sub-chunk from its real entry (s_entry / s_op, set by the chain walk): token bits, the
+// offset test (lz4.c:2041/:2065) and the first sequence that is not clean (next token beyond clean_ip, or output
+// at or beyond clean_op).
+struct D1Mark { uint32_t w0, w1; int first_op, viol, viol_next, uncl, uncl_op; };
+__device__ __forceinline__ D1Mark d1_mark(const uint8_t *ring, const RingReader &rd, const uint16_t *s_entry, const uint32_t *s_op,
+                                          const int base_q, const int d, const int clean_ip, const int clean_op, const int lane)
+{
+    D1Mark m;
+    m.w0 = 0; m.w1 = 0; m.first_op = -1; m.viol = 0x7fffffff; m.viol_next = 0; m.uncl = 0x7fffffff; m.uncl_op = 0;
+    int p = (int)s_entry[lane];
+    if (p == D1_NONE) return m;
+    int o = (int)s_op[lane];
+    const int s1 = (lane + 1) * D1_SUB;
+    while (p < s1) {
+        const int ip = base_q + p - d;
+        int lit, mlen, off, next;
+        const unsigned tok = ring[(base_q + p) & (D1_RING - 1)];
+        bool slow = false;
+        {
+            int qo = base_q + p + 1;
+            lit = (int)(tok >> 4); mlen = (int)(tok & 15) + 4;
+            if (lit == 15) {                  // continued literal length: one more byte, usually the last
+                const unsigned x = ring[qo & (D1_RING - 1)];
+                slow = x == 255;
+                lit += (int)x; qo++;
+            }
+            qo += lit;
+            // up to 269 literals ahead: still inside the two staged halves
+            off = (int)ring[qo & (D1_RING - 1)] | ((int)ring[(qo + 1) & (D1_RING - 1)] << 8);
+            qo += 2;
+            if (mlen == 19 && !slow) {        // continued match length
+                const unsigned x = ring[qo & (D1_RING - 1)];
+                slow = x == 255;
+                mlen += (int)x; qo++;
+            }
+            next = qo - d;
+        }
+        if (slow) {
+            const SeqDec sd = d1_decode_slow(rd, ip, clean_ip);
+            if (!sd.clean) { m.uncl = p; m.uncl_op = o; break; }
+            lit = sd.lit; mlen = sd.ml; off = sd.off; next = sd.next;
+        }
+        if (next > clean_ip || o + lit + mlen >= clean_op) { m.uncl = p; m.uncl_op = o; break; }
+        if (off > o + lit) { m.viol = p; m.viol_next = next; break; }         // lz4.c:2041/:2065
+        if (m.first_op < 0) m.first_op = o;
+        const int bit = p - lane * D1_SUB;
+        if (bit < 32) m.w0 |= 1u << bit; else m.w1 |= 1u << (bit - 32);
+        o += lit + mlen;
+        p = next + d - base_q;
+    }
+    return m;
+}
+
 // D1.  One WARP per block.  All lanes stream the payload through a double-buffered ring.
 //
 // BULK phase (all of the block except its last few sequences), one 2 KiB half at a time:
@@ -199,45 +292,8 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
             rd.ring = ring; rd.src = bd.src; rd.d = d;
             rd.lo = base_q - d; rd.span = min(base_q + D1_RING - d, csize) - rd.lo;
 
-            // ---- B: exit function of my 64-position sub-chunk, back to front.  Each position is
-            // read AS IF a token started there: a sequence without continued lengths is 3 + lit
-            // bytes long and produces lit + ml + 4 bytes; a token with a length nibble of 15 stops
-            // the fold (the chain walk decodes that sequence byte by byte).
-            {
-                const uint4 *mine = (const uint4 *)(ring + ((base_q + lane * D1_SUB) & (D1_RING - 1)));
-                uint32_t w[16];
-#pragma unroll
-                for (int i = 0; i < 4; i++) { const uint4 v = mine[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
-                uint16_t *xm = X + lane * D1_X_STRIDE;
-                uint16_t *sm = S + lane * D1_S_STRIDE;
-                const int sub_q = base_q + lane * D1_SUB;
-#pragma unroll
-                for (int jj = D1_SUB - 1; jj >= 0; jj--) {
-                    const unsigned tok = (w[jj >> 2] >> ((jj & 3) * 8)) & 0xffu;
-                    int lit = (int)(tok >> 4), ml = (int)(tok & 15), n = jj + 3;
-                    bool special = false;
-                    // a length continued by ONE byte is folded in (literal runs of 15+ and matches of
-                    // 19+ are common); longer continuations stop the fold
-                    if (lit == 15) {
-                        const unsigned x = (jj + 1 < D1_SUB) ? ((w[(jj + 1) >> 2 & 15] >> (((jj + 1) & 3) * 8)) & 0xffu)
-                                                            : (unsigned)ring[(sub_q + D1_SUB) & (D1_RING - 1)];
-                        special = x == 255;
-                        lit += (int)x; n++;
-                    }
-                    n += lit;
-                    if (ml == 15 && !special) {
-                        const unsigned x = ring[(sub_q + n) & (D1_RING - 1)];
-                        special = x == 255;
-                        ml += (int)x; n++;
-                    }
-                    int ex, os = lit + ml + 4;
-                    if (special) { ex = jj | D1_SPECIAL; os = 0; }
-                    else if (n < D1_SUB) { ex = (int)xm[n]; os += (int)sm[n]; }
-                    else ex = n;
-                    xm[jj] = (uint16_t)ex;
-                    sm[jj] = (uint16_t)os;
-                }
-            }
+            // ---- B: exit function of my 64-position sub-chunk, back to front
+            d1_fold(ring, X, S, base_q, lane);
             s_entry[lane] = (uint16_t)D1_NONE;
             __syncwarp();
             // ---- C: lane 0 hops sub-chunk to sub-chunk along the real chain
@@ -260,52 +316,9 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
             e = __shfl_sync(FM_FULL, e, 0); op = __shfl_sync(FM_FULL, op, 0);
             __syncwarp();
             // ---- D: my sub-chunk from its real entry: bits, offset test, first unclean sequence
-            uint32_t w0 = 0, w1 = 0;
-            int first_op = -1, viol = 0x7fffffff, viol_next = 0, uncl = 0x7fffffff, uncl_op = 0;
-            {
-                int p = (int)s_entry[lane];
-                if (p != D1_NONE) {
-                    int o = (int)s_op[lane];
-                    const int s1 = (lane + 1) * D1_SUB;
-                    while (p < s1) {
-                        const int ip = base_q + p - d;
-                        int lit, mlen, off, next;
-                        const unsigned tok = ring[(base_q + p) & (D1_RING - 1)];
-                        bool slow = false;
-                        {
-                            int qo = base_q + p + 1;
-                            lit = (int)(tok >> 4); mlen = (int)(tok & 15) + 4;
-                            if (lit == 15) {                  // continued literal length: one more byte, usually the last
-                                const unsigned x = ring[qo & (D1_RING - 1)];
-                                slow = x == 255;
-                                lit += (int)x; qo++;
-                            }
-                            qo += lit;
-                            // up to 269 literals ahead: still inside the two staged halves
-                            off = (int)ring[qo & (D1_RING - 1)] | ((int)ring[(qo + 1) & (D1_RING - 1)] << 8);
-                            qo += 2;
-                            if (mlen == 19 && !slow) {        // continued match length
-                                const unsigned x = ring[qo & (D1_RING - 1)];
-                                slow = x == 255;
-                                mlen += (int)x; qo++;
-                            }
-                            next = qo - d;
-                        }
-                        if (slow) {
-                            const SeqDec sd = d1_decode_slow(rd, ip, clean_ip);
-                            if (!sd.clean) { uncl = p; uncl_op = o; break; }
-                            lit = sd.lit; mlen = sd.ml; off = sd.off; next = sd.next;
-                        }
-                        if (next > clean_ip || o + lit + mlen >= clean_op) { uncl = p; uncl_op = o; break; }
-                        if (off > o + lit) { viol = p; viol_next = next; break; }         // lz4.c:2041/:2065
-                        if (first_op < 0) first_op = o;
-                        const int bit = p - lane * D1_SUB;
-                        if (bit < 32) w0 |= 1u << bit; else w1 |= 1u << (bit - 32);
-                        o += lit + mlen;
-                        p = next + d - base_q;
-                    }
-                }
-            }
+            const D1Mark mk = d1_mark(ring, rd, s_entry, s_op, base_q, d, clean_ip, clean_op, lane);
+            const uint32_t w0 = mk.w0, w1 = mk.w1;
+            const int first_op = mk.first_op, viol = mk.viol, viol_next = mk.viol_next, uncl = mk.uncl, uncl_op = mk.uncl_op;
             const int pu = warp_min(uncl), pv = warp_min(viol);
             if (pv < pu) {                                // corrupt: offset before the start of the output
                 const int src_lane = __ffs(__ballot_sync(FM_FULL, viol == pv)) - 1;
@@ -366,6 +379,223 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
                 rd.lo = k * D1_HALF - d;
                 rd.span = min((k + 2) * D1_HALF - d, csize) - rd.lo;
                 // tokens below the middle of the window keep their next 32 bytes staged
+                const int stop = more ? (k + 1) * D1_HALF - d : 0x7fffffff;
+                lz4_parse_run(st, rd, sink, csize, oend, stop);
+            }
+            if (__shfl_sync(FM_FULL, st.status, 0)) break;
+            __syncwarp();
+            if (more) store_half(k + 2);
+            __syncwarp();
+        }
+    }
+    if (lane == 0) { sink.flush(); result[b] = st.result; }
+}
+
+// D1 for FEW blocks: one CTA of 16 warps per block (lz4_parse_kernel gives a block one warp: 9 ms however few blocks
+// there are -- the per-block call of the JNI path, a split of two or three blocks, the slices of the host pipeline).
+// The three phases of the bulk parse become a pipeline over the block's 2 KiB halves:
+//   warps 1..15  WORKERS: worker i takes halves i, i + 15, ...: stages the half (and the next one, for look-ahead) in
+//                its own ring, folds it (phase B), hands it to the chain warp, and when the chain has passed through
+//                it marks its tokens (phase D);
+//   warp 0       CHAIN: walks the real chain through the halves in order (phase C), one table lookup per 64-byte
+//                sub-chunk -- the only serial part: about 1 ms for a 4 MiB block.
+// The first sequence that is not clean (and any offset violation) is reported through shared memory; after the
+// pipeline has drained, warp 0 runs the exact state machine from there, exactly like lz4_parse_kernel's tail.
+constexpr int D1W_WORKERS = 15;
+constexpr int D1W_THREADS = (D1W_WORKERS + 1) * 32;
+constexpr int D1W_SLOT = (D1_WARP_SMEM + 15) & ~15;
+constexpr int D1W_SMEM = (D1W_WORKERS + 1) * D1W_SLOT + 256;
+
+struct D1WCtl {
+    volatile int b_ready[D1W_WORKERS];     // half whose exit tables stand in the worker's slot
+    volatile int c_done[D1W_WORKERS];      // half the chain has passed through
+    int stop_h;                            // halves beyond this one need no work (first unclean sequence / violation / end)
+    unsigned long long uncl, viol;         // (aligned position << 32) | op, resp. | next token
+};
+
+__global__ void __launch_bounds__(D1W_THREADS, 1)
+lz4_parse_wide_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, uint32_t *chunk_op, int32_t *result)
+{
+    extern __shared__ __align__(16) uint8_t d1w_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x;
+    if (b >= n_blocks) return;
+    const BlockDesc bd = blocks[b];
+    if (bd.stored) { if (threadIdx.x == 0) result[b] = (int32_t)bd.usize; return; }
+
+    D1WCtl *ctl = (D1WCtl *)(d1w_smem + (size_t)(D1W_WORKERS + 1) * D1W_SLOT);
+    uint8_t *ring = d1w_smem + (size_t)warp * D1W_SLOT;             // this warp's slot
+    uint16_t *X = (uint16_t *)(ring + D1_RING);
+    uint16_t *S = X + 32 * D1_X_STRIDE;
+    uint32_t *s_op = (uint32_t *)(S + 32 * D1_S_STRIDE);
+    uint16_t *s_entry = (uint16_t *)(s_op + 32);
+
+    const uintptr_t a = (uintptr_t)bd.src;
+    const uint4 *base = (const uint4 *)(a & ~(uintptr_t)15);
+    const int d = (int)(a & 15);
+    const int csize = (int)bd.csize, oend = (int)bd.usize;
+    const int nchunks = (d + csize + 15) >> 4;
+    constexpr int HC = D1_HALF / 16;
+    const int n_halves = (d + csize + D1_HALF - 1) / D1_HALF;
+    uint32_t *my_map = tokmap + (size_t)bd.chunk_base * LZ4_CHUNK_WORDS;
+    uint32_t *my_cop = chunk_op + bd.chunk_base;
+
+    uint4 r0, r1, r2, r3;
+    auto load_half = [&](int h) {
+        const int c = h * HC + lane;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        r0 = (c < nchunks) ? ldg_nc_v4(base + c) : z;
+        r1 = (c + 32 < nchunks) ? ldg_nc_v4(base + c + 32) : z;
+        r2 = (c + 64 < nchunks) ? ldg_nc_v4(base + c + 64) : z;
+        r3 = (c + 96 < nchunks) ? ldg_nc_v4(base + c + 96) : z;
+    };
+    auto store_half = [&](int h) {
+        uint4 *q = (uint4 *)(ring + (h & 1) * D1_HALF);
+        q[lane] = r0; q[lane + 32] = r1; q[lane + 64] = r2; q[lane + 96] = r3;
+    };
+
+    ParseState st;
+    TokSink sink;
+    sink.tokmap = my_map; sink.chunk_op = my_cop; sink.d = d;
+    sink.cur_word = 0; sink.bits = 0; sink.cur_chunk = 0xffffffffu;
+    lz4_parse_init(st, bd.src == nullptr, csize, oend, (bd.src != nullptr && csize > 0) ? (unsigned)bd.src[0] : 0u);
+    const int clean_ip = csize - 32, clean_op = oend - 64;
+    const bool bulk = !st.status && clean_ip > 0 && clean_op > 0;
+
+    if (threadIdx.x < D1W_WORKERS) { ctl->b_ready[threadIdx.x] = -1; ctl->c_done[threadIdx.x] = -1; }
+    if (threadIdx.x == 0) { ctl->stop_h = n_halves - 1; ctl->uncl = ~0ull; ctl->viol = ~0ull; }
+    __syncthreads();
+    volatile int *stop_h = &ctl->stop_h;
+
+    if (bulk && warp > 0) {
+        // ================= WORKER =================
+        const int me = warp - 1;
+        for (int h = me; h < n_halves; h += D1W_WORKERS) {
+            if (h > *stop_h) break;
+            const int base_q = h * D1_HALF;
+            load_half(h); store_half(h);
+            load_half(h + 1); store_half(h + 1);
+            __syncwarp();
+            d1_fold(ring, X, S, base_q, lane);
+            s_entry[lane] = (uint16_t)D1_NONE;
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) ctl->b_ready[me] = h;
+            bool go = true;
+            while (ctl->c_done[me] != h) {
+                if (h > *stop_h) { go = false; break; }
+                __nanosleep(64);
+            }
+            if (!go) break;
+            __threadfence_block();
+            RingReader rd;
+            rd.ring = ring; rd.src = bd.src; rd.d = d;
+            rd.lo = base_q - d; rd.span = min(base_q + D1_RING - d, csize) - rd.lo;
+            const D1Mark mk = d1_mark(ring, rd, s_entry, s_op, base_q, d, clean_ip, clean_op, lane);
+            {
+                uint32_t *mw = my_map + (base_q >> 5) + 2 * lane;
+                if (mk.w0) mw[0] = mk.w0;
+                if (mk.w1) mw[1] = mk.w1;
+                const int f_even = __shfl_sync(FM_FULL, mk.first_op, lane & ~1), f_odd = __shfl_sync(FM_FULL, mk.first_op, lane | 1);
+                const int f = f_even >= 0 ? f_even : f_odd;
+                if (!(lane & 1) && f >= 0) my_cop[(base_q >> 7) + (lane >> 1)] = (uint32_t)f;
+            }
+            const int pu = warp_min(mk.uncl), pv = warp_min(mk.viol);
+            if (pv != 0x7fffffff) {
+                const int src_lane = __ffs(__ballot_sync(FM_FULL, mk.viol == pv)) - 1;
+                const int vn = __shfl_sync(FM_FULL, mk.viol_next, src_lane);
+                if (lane == 0) { atomicMin(&ctl->viol, ((unsigned long long)(base_q + pv) << 32) | (uint32_t)vn); atomicMin(&ctl->stop_h, h); }
+            }
+            if (pu != 0x7fffffff) {
+                const int src_lane = __ffs(__ballot_sync(FM_FULL, mk.uncl == pu)) - 1;
+                const int uo = __shfl_sync(FM_FULL, mk.uncl_op, src_lane);
+                if (lane == 0) { atomicMin(&ctl->uncl, ((unsigned long long)(base_q + pu) << 32) | (uint32_t)uo); atomicMin(&ctl->stop_h, h); }
+            }
+            __syncwarp();
+        }
+    } else if (bulk) {
+        // ================= CHAIN =================
+        int e_q = d, op = 0;
+        for (int h = 0; h < n_halves; h++) {
+            if (h > *stop_h) break;
+            const int me = h % D1W_WORKERS;
+            uint8_t *wring = d1w_smem + (size_t)(me + 1) * D1W_SLOT;
+            const uint16_t *wX = (const uint16_t *)(wring + D1_RING);
+            const uint16_t *wS = wX + 32 * D1_X_STRIDE;
+            uint32_t *w_op = (uint32_t *)(wS + 32 * D1_S_STRIDE);
+            uint16_t *w_entry = (uint16_t *)(w_op + 32);
+            bool go = true;
+            while (ctl->b_ready[me] != h) {
+                if (h > *stop_h) { go = false; break; }
+                __nanosleep(32);
+            }
+            if (!go) break;
+            __threadfence_block();
+            const int base_q = h * D1_HALF;
+            int e = e_q - base_q;
+            if (lane == 0 && e < D1_HALF) {
+                RingReader rd;
+                rd.ring = wring; rd.src = bd.src; rd.d = d;
+                rd.lo = base_q - d; rd.span = min(base_q + D1_RING - d, csize) - rd.lo;
+                int last_sc = -1;
+                while (e < D1_HALF) {
+                    const int sc = e >> 6, jj = e & (D1_SUB - 1);
+                    if (sc != last_sc) { w_entry[sc] = (uint16_t)e; w_op[sc] = (uint32_t)op; last_sc = sc; }
+                    const int x = (int)wX[sc * D1_X_STRIDE + jj];
+                    op += (int)wS[sc * D1_S_STRIDE + jj];
+                    if (x & D1_SPECIAL) {
+                        const SeqDec sd = d1_decode_slow(rd, base_q + sc * D1_SUB + (x & (D1_SUB - 1)) - d, clean_ip);
+                        if (!sd.clean) { e = 0x40000000; break; }      // phase D finds it and reports; nothing clean follows
+                        op += sd.lit + sd.ml;
+                        e = sd.next + d - base_q;
+                    } else e = sc * D1_SUB + x;
+                }
+            }
+            e = __shfl_sync(FM_FULL, e, 0); op = __shfl_sync(FM_FULL, op, 0);
+            __threadfence_block();
+            if (lane == 0) ctl->c_done[me] = h;
+            if (e >= 0x40000000) { if (lane == 0) atomicMin(&ctl->stop_h, h); break; }
+            e_q = base_q + e;
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+
+    // ================= hand-over and TAIL (warp 0) =================
+    if (bulk) {
+        const unsigned long long u = ctl->uncl, v = ctl->viol;
+        if ((uint32_t)(v >> 32) < (uint32_t)(u >> 32)) {          // corrupt: offset before the start of the output
+            st.status = 1; st.result = -(int)(uint32_t)v - 1;     // lz4.c:2337 with ip at the next token
+        } else if (u != ~0ull) {
+            const uint32_t q = (uint32_t)(u >> 32);
+            st.ip = (int)q - d; st.op = (int)(uint32_t)u;
+            // the chunk holding the hand-over token may already carry earlier tokens (then its position is set)
+            const uint32_t c = q >> 7;
+            bool chunk_has = false;
+            for (uint32_t w = c * 4; w <= (q >> 5); w++) {
+                uint32_t bits = my_map[w];
+                if (w == (q >> 5)) bits &= (1u << (q & 31)) - 1u;
+                chunk_has |= bits != 0;
+            }
+            sink.cur_word = q >> 5; sink.bits = 0;
+            sink.cur_chunk = chunk_has ? c : 0xffffffffu;
+        }
+        // neither reported (cannot happen: the last sequence of a block is never clean): the exact machine from the start
+    }
+    if (!st.status) {
+        int k = (st.ip + d) >> 11;
+        __syncwarp();
+        load_half(k); store_half(k);
+        load_half(k + 1); store_half(k + 1);
+        __syncwarp();
+        for (;; k++) {
+            const bool more = (k + 2) * HC < nchunks;
+            if (more) load_half(k + 2);
+            if (lane == 0 && !st.status) {
+                RingReader rd;
+                rd.ring = ring; rd.src = bd.src; rd.d = d;
+                rd.lo = k * D1_HALF - d;
+                rd.span = min((k + 2) * D1_HALF - d, csize) - rd.lo;
                 const int stop = more ? (k + 1) * D1_HALF - d : 0x7fffffff;
                 lz4_parse_run(st, rd, sink, csize, oend, stop);
             }
@@ -658,22 +888,26 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
     publish(0x7fffffff);
 }
 
-// D2 as a kernel of its own (D1 = lz4_parse_kernel ran before it): one CTA of W warps per block.
-// W = warps per block (1, 2, 4 or 8): the host picks it from the batch size -- many blocks in
-// flight need few warps each (and then hardly ever wait on one another), few blocks need many.
+// D2 as a kernel of its own (D1 ran before it): one CTA of W warps per block.
+// W = warps per block (1 .. 32): the host picks it from the batch size -- many blocks in flight need few warps each
+// (and then hardly ever wait on one another), few blocks need many.
+template <int W>
+constexpr size_t d2_smem_bytes() { return sizeof(CopyBlockSmem<W>) + 16 + (size_t)W * sizeof(CopyWarpSmem); }
+
 template <int W>
 __global__ void __launch_bounds__(W * 32)
 lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t *chunk_op,
                 const int32_t *result)
 {
-    __shared__ CopyBlockSmem<W> s_block;
-    __shared__ CopyWarpSmem s_warp[W];
+    extern __shared__ __align__(16) uint8_t d2_smem[];
+    CopyBlockSmem<W> *s_block = (CopyBlockSmem<W> *)d2_smem;
+    CopyWarpSmem *s_warp = (CopyWarpSmem *)(((uintptr_t)(s_block + 1) + 15) & ~(uintptr_t)15);
     const BlockDesc bd = blocks[blockIdx.x];
     if (bd.stored || result[blockIdx.x] < 0) return;
-    if (threadIdx.x < W) s_block.owed[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_block.ticket = 0;
+    if (threadIdx.x < W) s_block->owed[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_block->ticket = 0;
     if (W > 1) __syncthreads();
-    lz4_copy_block<W>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, &s_block, &s_warp[threadIdx.x >> 5]);
+    lz4_copy_block<W>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, s_block, &s_warp[threadIdx.x >> 5]);
 }
 
 // ---- D0 ------------------------------------------------------------------------------------

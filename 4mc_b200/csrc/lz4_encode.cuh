@@ -83,6 +83,7 @@ struct EncParams {
     uint32_t region_bytes;   // new bytes per region: ENC_REGION (Fast) or ENC_CHAIN_REGION (chain)
     uint32_t regions_per_block;
     uint32_t block_bytes;    // bytes per block: 0 = FOURMC_BLOCKSIZE (the containers); the raw codec streams cut smaller chunks
+    int reproducible;        // ties between racing table stores are settled by position: the same bytes on every run
 };
 
 __device__ __forceinline__ uint32_t enc_hash(uint32_t v) { return (v * 2654435761u) >> (32 - ENC_HASH_BITS); }
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
                     for (;;) {
                         uint32_t any;
                         asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (!P.reproducible) break;
                         const uint32_t lost = live && head[h] < (uint16_t)p;
                         asm volatile("{\n\t.reg .pred pa, pq;\n\tsetp.ne.u32 pq, %1, 0;\n\tbar.red.or.pred pa, 1, 128, pq;\n\t"
                                      "selp.u32 %0, 1, 0, pa;\n\t}" : "=r"(any) : "r"(lost) : "memory");
@@ -271,6 +273,9 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
                 // Equal hashes inside one step race; whoever finds a HIGHER position in its bucket stores again
                 // until the lowest one holds it: the table -- and with it every compressed byte -- is then the
                 // same on every run (one extra round on text, where a step rarely holds a hash twice).
+                // (P.reproducible; costs a third of this kernel's time on text.  Without it any of the racing positions
+                // stays -- all of them are legal candidates, only the bytes differ from run to run.)
+                if (!P.reproducible) { __syncthreads(); continue; }
                 for (;;) {
                     const bool lost0 = live0 && table[h0] > (uint16_t)p, lost2 = live2 && table[h2] > (uint16_t)(p + 2);
                     if (!__syncthreads_or(lost0 || lost2)) break;

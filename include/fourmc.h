@@ -61,6 +61,13 @@ uint64_t fourmc_kernel_launches(const fourmc_ctx *ctx);
  * counters and returns the text length. */
 int  fourmc_timing_enable(fourmc_ctx *ctx, int on);
 long long fourmc_timing_collect(fourmc_ctx *ctx, char *buf, size_t cap);
+/* Reproducible compressed bytes.  The match finders fill their tables with racing stores; with this on, ties are
+ * settled by position (lowest / highest) and every run -- any context, any GPU of the type -- writes the same bytes,
+ * at the price of a few extra barrier rounds per region (a third of the Fast encode kernel's time on text; nothing
+ * where the call is bound by PCIe or the file system).  mode -1 (default): on for everything that hands bytes to the
+ * host -- whole-stream host calls, per-block calls, files, the JNI library -- and off for the device-resident calls;
+ * 0 / 1: off / on everywhere.  Environment FOURMC_REPRODUCIBLE=0|1 sets the default of new contexts. */
+int  fourmc_ctx_set_reproducible(fourmc_ctx *ctx, int mode);
 /* Blocks until everything queued on the context's stream (or `stream`) has finished. */
 int  fourmc_sync(fourmc_ctx *ctx, void *stream);
 
@@ -143,6 +150,15 @@ int fourmc_4mc_build_index_device(fourmc_ctx *ctx, void *stream, const uint32_t 
 int fourmc_4mc_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n,
                                  void *d_out, size_t out_capacity, long long *d_result);
 
+/* A block range of one stream: blocks [first_block, first_block + n_blocks) of the .4mc stream at d_in, located
+ * through the footer index like the call above (the whole index is validated); the range's first block decodes
+ * to d_out.  This is how the ranks of a multi-GPU reader share ONE stream (contiguous block ranges,
+ * no collective); n_blocks = 0xffffffff means "to the end".  d_result as above, sizes and block numbers counted
+ * within the range. */
+int fourmc_4mc_decompress_range_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n,
+                                       uint32_t first_block, uint32_t n_blocks,
+                                       void *d_out, size_t out_capacity, long long *d_result);
+
 /* Batch of independent blocks.  Block i: payload at d_src + src_off[i] (csize[i] bytes, raw when
  * csize[i] == usize[i]), expected checksum xxh[i] (ignored when check_xxh == 0), output at
  * d_dst + dst_off[i] with capacity usize[i].  The five tables are DEVICE arrays.
@@ -170,6 +186,9 @@ long long fourmc_4mz_decompress_host(fourmc_ctx *ctx, const void *in, size_t n, 
 long long fourmc_4mz_decoded_size_host(const void *in, size_t n);
 int fourmc_4mz_decompress_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n,
                                  void *d_out, size_t out_capacity, long long *d_result);
+int fourmc_4mz_decompress_range_device(fourmc_ctx *ctx, void *stream, const void *d_in, size_t n,
+                                       uint32_t first_block, uint32_t n_blocks,
+                                       void *d_out, size_t out_capacity, long long *d_result);
 /* ZSTD_decompress on one block (host pointers): native/4mc.c:810, native/jniZstdDecompressor.c.
  * Returns the decoded size, or a negative value where ZSTD_isError() is true for the reference. */
 long long fourmc_zstd_decompress(fourmc_ctx *ctx, const void *src, size_t compressed_size,

@@ -107,6 +107,66 @@ def test_container_decode_golden(ctx):
     assert ctx.decompress_4mc(golden_bytes("two_streams.4mc")) == b"A" + text
 
 
+@pytest.mark.parametrize("zstd", [False, True])
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_writer_and_reader_share_one_stream(ctx, ora, ref_cli, pkg, tmp_path, world, zstd):
+    """SURVEY.md 8e on the GPU, the ranks played by separate contexts in one process: contiguous block ranges, every
+    rank's span from fourmc_*_compress_span_device, the gathered block lengths give the span offsets and the footer
+    (fourmc_*_build_index_device), the spans are placed -- and the result is ONE stream: the oracle and the reference CLI
+    decode it to the input, and every rank decodes its own block range of it through the footer index
+    (fourmc_*_decompress_range_device).  bench.py --gpus N runs the same steps with NCCL between processes."""
+    import subprocess
+    import torch
+    n = 11 * 4194304 + 33333                                       # a ragged last block
+    data = gen_logtext(pkg, n, seed=5)
+    nb = (n + 4194304 - 1) // 4194304
+    ranks = [pkg.Context(0) for _ in range(world)]
+    try:
+        d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        spans, lens_all, sizes = [], [], []
+        for r, c in enumerate(ranks):
+            lo, hi = pkg.shard_blocks(nb, world, r)
+            off, cnt = lo * 4194304, min(n, hi * 4194304) - lo * 4194304
+            cap = cnt + 12 * (hi - lo) + 64
+            d_span = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+            d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+            d_l = torch.zeros(max(hi - lo, 1), dtype=torch.int32, device="cuda")
+            f = c.compress_4mz_span_device if zstd else c.compress_span_device
+            f(d_in.data_ptr() + off, cnt, d_span.data_ptr(), cap, d_sz.data_ptr(), d_l.data_ptr())
+            c.sync()
+            spans.append(d_span[:int(d_sz.item())].clone()); sizes.append(int(d_sz.item())); lens_all.append(d_l[:hi - lo])
+        lens = torch.cat(lens_all)
+        assert [int(x.sum()) for x in lens_all] == sizes            # a span is exactly its block records
+        offs = pkg.span_base_offsets(sizes)
+        total = 12 + sum(sizes) + 12 + 20 + 4 * nb
+        d_stream = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
+        for r in range(world):
+            d_stream[offs[r]:offs[r] + sizes[r]].copy_(spans[r])
+        build = ranks[0].build_index_4mz_device if zstd else ranks[0].build_index_device
+        build(lens.data_ptr(), nb, d_stream.data_ptr(), d_stream.data_ptr() + 12 + sum(sizes))
+        ranks[0].sync()
+        stream = bytes(d_stream[:total].cpu().numpy())
+        dec = ora.decompress_4mz if zstd else ora.decompress_4mc
+        assert dec(stream, n + 16) == (n, data)
+        p, q = tmp_path / ("s.4mz" if zstd else "s.4mc"), tmp_path / "s.out"
+        p.write_bytes(stream)
+        subprocess.run([ref_cli, "-f", "-q", "-q", "-d"] + (["-z"] if zstd else []) + [str(p), str(q)], check=True)
+        assert q.read_bytes() == data
+        # the readers: every rank its own range of the ONE stream
+        for r, c in enumerate(ranks):
+            lo, hi = pkg.shard_blocks(nb, world, r)
+            want = data[lo * 4194304:min(n, hi * 4194304)]
+            d_out = torch.zeros(len(want) + 64, dtype=torch.uint8, device="cuda")
+            res = torch.zeros(2, dtype=torch.int64, device="cuda")
+            c.decompress_range_device(d_stream.data_ptr(), total, lo, hi - lo, d_out.data_ptr(), len(want), res.data_ptr(), zstd=zstd)
+            c.sync()
+            assert res.cpu().tolist() == [len(want), -1]
+            assert bytes(d_out[:len(want)].cpu().numpy()) == want
+    finally:
+        for c in ranks:
+            c.close()
+
+
 def test_compressed_bytes_are_reproducible(ctx, pkg):
     """The match finders' tables are filled by racing stores; ties are settled by position (lowest / highest),
     so two runs -- and two contexts -- give the same bytes (a storage format wants reproducible artefacts)."""
@@ -119,7 +179,22 @@ def test_compressed_bytes_are_reproducible(ctx, pkg):
         for level in (1, 3):
             z = ctx.compress_4mz(data, level=level)
             assert ctx.compress_4mz(data, level=level) == z and other.compress_4mz(data, level=level) == z, level
+        # the device-resident calls favour speed unless asked (fourmc_ctx_set_reproducible)
+        import torch
+        d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        cap = pkg.lib().fourmc_4mc_bound(len(data))
+        outs = []
+        for c in (ctx, other):
+            c.set_reproducible(1)
+            d_out = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+            d_sz = torch.zeros(1, dtype=torch.int64, device="cuda")
+            c.compress_device(d_in.data_ptr(), len(data), d_out.data_ptr(), cap, d_sz.data_ptr())
+            c.sync()
+            outs.append(bytes(d_out[:int(d_sz.item())].cpu().numpy()))
+            c.set_reproducible(-1)
+        assert outs[0] == outs[1] == ctx.compress_4mc(data, level=1)
     finally:
+        ctx.set_reproducible(-1)
         other.close()
 
 

@@ -31,12 +31,20 @@ def main():
     src = os.path.join(d, "in.bin")
     buf = C.create_string_buffer(n)
     assert pkg.lib().fourmc_gen_host(0, 0x4D43, 0, n // 4096, buf) == 0
+    t = time.perf_counter()
     with open(src, "wb") as f:
         f.write(buf.raw)
+    t_w = time.perf_counter() - t
+    t = time.perf_counter()
+    with open(src, "rb") as f:
+        while f.read(1 << 26):
+            pass
+    t_r = time.perf_counter() - t
     del buf
     ours, ref = os.path.join(ROOT, "4mc_b200", "host", "4mc"), os.path.join(ROOT, "oracle", "_ref", "4mc")
     ext = ".4mz" if z else ".4mc"
-    res = {"bytes": n, "codec": "4mz" if z else "4mc", "storage": "tmpfs"}
+    res = {"bytes": n, "codec": "4mz" if z else "4mc", "storage": "tmpfs",
+           "storage_one_thread_GBps": {"write": n / t_w / 1e9, "read": n / t_r / 1e9}}
     for name, exe in (("gpu_cli", ours), ("reference_cli_1_core", ref)):
         comp, back = os.path.join(d, name + ext), os.path.join(d, name + ".out")
         tc = min(run([exe, "-f", "-q", "-q"] + z + ["-1", src, comp]) for _ in range(2))
