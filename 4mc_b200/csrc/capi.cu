@@ -47,7 +47,7 @@ struct DecWs {
 
 }  // namespace
 
-constexpr int FM_PIPE_MAX = 4;
+constexpr int FM_PIPE_MAX = 8;
 
 struct fourmc_ctx {
     int device = 0;
@@ -61,12 +61,17 @@ struct fourmc_ctx {
     // -1 = per entry point (host / file / per-block calls: yes; device-resident calls: no, they favour speed), 0 / 1 = always
     int reproducible = -1;
     int repro_call = 1;                  // what the entry point in progress resolved it to
+    // the block index of the file the split reader saw last (a reader works through many splits of one file)
+    const void *idx_file = nullptr;
+    size_t idx_size = 0;
+    uint8_t idx_tail[12] = {};
+    std::vector<int64_t> idx_offs;
     EncWs enc[FM_PIPE_MAX];
     DecWs dec[FM_PIPE_MAX];
     DevBuf stage_in[FM_PIPE_MAX], stage_out[FM_PIPE_MAX];    // device staging for the host-pointer entry points
     void *pinned = nullptr;              // small pinned scratch for scalars
     size_t pinned_cap = 0;
-    bool region_attr_set = false, d1_attr_set = false, d2_attr_set = false, d1w_attr_set = false, zd_attr_set = false, gen_attr_set = false;   // per context = per device
+    bool region_attr_set = false, d1_attr_set = false, d1w_attr_set = false, zd_attr_set = false, gen_attr_set = false;   // per context = per device
     DevBuf ztables;                      // fmz::Tables (constant decode tables), uploaded once
     // optional per-kernel timing (fourmc_timing_enable): CUDA event pairs around every launch
     bool timing = false;
@@ -429,7 +434,7 @@ int ensure_side(fourmc_ctx *ctx, DecWs &ws)
 // (a block range of a longer stream).
 int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t max_chunks, int check_xxh,
                int32_t *d_out_size, const IndexInfo *d_info, long long *d_result, int codec = CODEC_LZ4, int compact = 0,
-               uint32_t first = 0)
+               uint32_t first = 0, bool pipelined = false)
 {
     int r;
     if (codec == CODEC_ZSTD) max_chunks = 0;
@@ -502,14 +507,23 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             // one block per SM at a time); many blocks: a warp per block.  FOURMC_D1_WIDE=0|1 forces one of them.
             static int wide_forced = -1;
             if (wide_forced < 0) { const char *e = getenv("FOURMC_D1_WIDE"); wide_forced = e ? (atoi(e) ? 1 : 0) : 2; }
-            const bool wide = wide_forced == 2 ? nb <= (uint32_t)ctx->sm_count * 6 : wide_forced == 1;
+            // r02i: 2.7 ms per wave of 148 blocks, the warp-per-block kernel 9.4 ms up to ~600 blocks.  Not for the slices of
+            // the host pipeline: several of them are in flight, and a 16-warp CTA with 200 KiB of shared memory keeps the
+            // other slices' kernels off its SM (r02j: host-buffer decode 37 GB/s with it, 42-45 without)
+            const uint32_t sm = (uint32_t)ctx->sm_count;
+            const bool wide = wide_forced == 2 ? (!pipelined && nb <= sm * 4) : wide_forced == 1;
             if (wide) {
                 if (!ctx->d1w_attr_set) {
-                    CK(cudaFuncSetAttribute(lz4_parse_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D1W_SMEM));
+                    CK(cudaFuncSetAttribute(lz4_parse_wide_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, d1w_smem_bytes<15>()));
+                    CK(cudaFuncSetAttribute(lz4_parse_wide_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, d1w_smem_bytes<7>()));
                     ctx->d1w_attr_set = true;
                 }
-                KL("lz4_parse_wide_kernel", st, lz4_parse_wide_kernel<<<nb, D1W_THREADS, D1W_SMEM, st>>>(desc, nb, (uint32_t *)ws.tokmap.p,
-                                                                       (uint32_t *)ws.chunkop.p, (int32_t *)ws.result.p));
+                if (nb <= sm)
+                    KL("lz4_parse_wide_kernel", st, lz4_parse_wide_kernel<15><<<nb, 16 * 32, d1w_smem_bytes<15>(), st>>>(desc, nb, (uint32_t *)ws.tokmap.p,
+                                                                               (uint32_t *)ws.chunkop.p, (int32_t *)ws.result.p));
+                else
+                    KL("lz4_parse_wide_kernel", st, lz4_parse_wide_kernel<7><<<nb, 8 * 32, d1w_smem_bytes<7>(), st>>>(desc, nb, (uint32_t *)ws.tokmap.p,
+                                                                              (uint32_t *)ws.chunkop.p, (int32_t *)ws.result.p));
             } else
                 KL("lz4_parse_kernel", st, lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, D1_SMEM, st>>>(desc, nb, (uint32_t *)ws.tokmap.p,
                                                                (uint32_t *)ws.chunkop.p, (int32_t *)ws.result.p));
@@ -523,21 +537,14 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             static int forced = -1;
             if (forced < 0) { const char *e = getenv("FOURMC_D2_WARPS"); forced = e ? atoi(e) : 0; }
             int w = forced;
-            if (w != 1 && w != 2 && w != 4 && w != 8 && w != 16 && w != 32) {
+            if (w != 1 && w != 2 && w != 4 && w != 8) {
                 const uint32_t want = (uint32_t)ctx->sm_count * 24;        // resident warps to aim for (measured, profiles/)
-                w = 32;
-                for (int c = 1; c <= 16; c *= 2) if (nb * (uint32_t)c >= want) { w = c; break; }
-            }
-            if (!ctx->d2_attr_set) {
-                CK(cudaFuncSetAttribute(lz4_copy_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_bytes<16>()));
-                CK(cudaFuncSetAttribute(lz4_copy_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d2_smem_bytes<32>()));
-                ctx->d2_attr_set = true;
+                w = nb * 1 >= want ? 1 : nb * 2 >= want ? 2 : nb * 4 >= want ? 4 : 8;
             }
             const uint32_t *tm = (const uint32_t *)ws.tokmap.p, *co = (const uint32_t *)ws.chunkop.p;
             const int32_t *rs = (const int32_t *)ws.result.p;
-#define D2_LAUNCH(WW) KL("lz4_copy_kernel", st, lz4_copy_kernel<WW><<<nb, WW * 32, d2_smem_bytes<WW>(), st>>>(desc, tm, co, rs))
-            if (w == 1) D2_LAUNCH(1); else if (w == 2) D2_LAUNCH(2); else if (w == 4) D2_LAUNCH(4); else if (w == 8) D2_LAUNCH(8);
-            else if (w == 16) D2_LAUNCH(16); else D2_LAUNCH(32);
+#define D2_LAUNCH(WW) KL("lz4_copy_kernel", st, lz4_copy_kernel<WW><<<nb, WW * 32, 0, st>>>(desc, tm, co, rs))
+            if (w == 1) D2_LAUNCH(1); else if (w == 2) D2_LAUNCH(2); else if (w == 4) D2_LAUNCH(4); else D2_LAUNCH(8);
 #undef D2_LAUNCH
         }
     }
@@ -905,7 +912,7 @@ int fourmc_4mz_decompress_range_device(fourmc_ctx *ctx, void *stream, const void
 static int dec_batch(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, const void *d_src,
                      const uint64_t *d_src_off, const uint32_t *d_csize, const uint32_t *d_usize, const uint32_t *d_xxh,
                      int check_xxh, void *d_dst, const uint64_t *d_dst_off, int32_t *d_out_size, uint8_t *d_status,
-                     int codec = CODEC_LZ4, int compact = 0)
+                     int codec = CODEC_LZ4, int compact = 0, bool pipelined = false)
 {
     int r;
     if ((r = ensure(ctx, ws.desc, (size_t)std::max<uint32_t>(nb, 1) * sizeof(BlockDesc)))) return r;
@@ -917,7 +924,7 @@ static int dec_batch(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, c
     if (check_xxh) CK(cudaMemcpyAsync(ws.xxh.p, d_xxh, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
     // every compressed block has csize <= 4 MiB: bound the chunk count by that
     const size_t max_chunks = (size_t)nb * (FOURMC_BLOCKSIZE / LZ4_CHUNK + 2);
-    if ((r = dec_blocks(ctx, st, ws, nb, max_chunks, check_xxh, d_out_size, nullptr, nullptr, codec, compact))) return r;
+    if ((r = dec_blocks(ctx, st, ws, nb, max_chunks, check_xxh, d_out_size, nullptr, nullptr, codec, compact, 0, pipelined))) return r;
     if (d_status) CK(cudaMemcpyAsync(d_status, ws.status.p, nb, cudaMemcpyDeviceToDevice, st));
     return FOURMC_OK;
 }
@@ -1317,7 +1324,7 @@ static long long decompress_host_impl(fourmc_ctx *ctx, int codec, const void *in
         uint8_t *d_st = (uint8_t *)(d_osz + cnt);
         // every item's payload checksum (blocks and footers) is verified inside the decode batch (:637/:645)
         if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[b].p, d_src_off, d_c, d_u, d_x, 1,
-                           ctx->stage_out[b].p, d_dst_off, d_osz, d_st, codec)))
+                           ctx->stage_out[b].p, d_dst_off, d_osz, d_st, codec, 0, slices.size() > 1)))
             return r;
         if (s.d1 > s.d0)
             CK(cudaMemcpyAsync((uint8_t *)out + s.d0, ctx->stage_out[b].p, s.d1 - s.d0, cudaMemcpyDeviceToHost, st));
@@ -1614,11 +1621,20 @@ long long fourmc_read_index_host(fourmc_ctx *ctx, const void *file, size_t file_
 }
 
 namespace {
-__global__ void find_byte_kernel(const uint8_t *p, unsigned long long n, uint8_t v, unsigned long long *first)
-{
+// First line terminator of p[0, n) the way Hadoop's LineReader sees it (the reader behind FourMcLineRecordReader):
+// a line ends at LF, at CR, or at CR LF.  *first = 2 * (index of the terminator's first byte) + (1 if it is CR LF);
+// the smallest key is the first terminator.
+__global__ void find_eol_kernel(const uint8_t *p, unsigned long long n, unsigned long long n_avail, unsigned long long *first)
+{   // n: positions searched; n_avail >= n: bytes that may be looked at (the LF of a CR LF straddling the range's end)
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        if (p[i] == v) { atomicMin(first, i); break; }
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint8_t c = p[i];
+        if (c == '\n' || c == '\r') {
+            const unsigned long long crlf = (c == '\r' && i + 1 < n_avail && p[i + 1] == '\n') ? 1ull : 0ull;
+            atomicMin(first, 2 * i + crlf);
+            break;
+        }
+    }
 }
 }  // namespace
 
@@ -1637,12 +1653,18 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
     const uint32_t magic = be32(f);
     if (magic != FOURMC_MAGIC_4MC && magic != FOURMC_MAGIC_4MZ) return FOURMC_E_CONTENT;
     const int codec = magic == FOURMC_MAGIC_4MZ ? CODEC_ZSTD : CODEC_LZ4;
-    const long long nb_ll = fourmc_read_index_host(ctx, file, file_size, nullptr, 0);
-    if (nb_ll < 0) return nb_ll;
-    if (nb_ll == 0) return 0;
-    std::vector<int64_t> offs((size_t)nb_ll);
-    fourmc_read_index_host(ctx, file, file_size, offs.data(), offs.size());
-    const int n = (int)nb_ll;
+    // the index is read (and its checksum verified on the device) once per file, not once per split
+    if (ctx->idx_file != file || ctx->idx_size != file_size || memcmp(ctx->idx_tail, f + file_size - 12, 12) != 0) {
+        ctx->idx_file = nullptr;
+        const long long nb_ll = fourmc_read_index_host(ctx, file, file_size, nullptr, 0);
+        if (nb_ll < 0) return nb_ll;
+        ctx->idx_offs.assign((size_t)nb_ll, 0);
+        if (nb_ll) fourmc_read_index_host(ctx, file, file_size, ctx->idx_offs.data(), ctx->idx_offs.size());
+        ctx->idx_file = file; ctx->idx_size = file_size; memcpy(ctx->idx_tail, f + file_size - 12, 12);
+    }
+    const std::vector<int64_t> &offs = ctx->idx_offs;
+    if (offs.empty()) return 0;
+    const int n = (int)offs.size();
     const int64_t end = start + length;
     // first block of the split: the reader seeks to `start`, which the planner put on a block start
     int b0 = 0;
@@ -1709,9 +1731,9 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
         CK(cudaMemsetAsync(d_first, 0xff, 16, st));
         const uint8_t *d_out = (const uint8_t *)ctx->stage_out[0].p;
         if (start != 0 && u_split)
-            KL("find_byte_kernel", st, find_byte_kernel<<<1024, 256, 0, st>>>(d_out, u_split, (uint8_t)'\n', d_first));
+            KL("find_eol_kernel", st, find_eol_kernel<<<1024, 256, 0, st>>>(d_out, u_split, total_u, d_first));
         if (total_u > u_split)
-            KL("find_byte_kernel", st, find_byte_kernel<<<256, 256, 0, st>>>(d_out + u_split, total_u - u_split, (uint8_t)'\n', d_first + 1));
+            KL("find_eol_kernel", st, find_eol_kernel<<<256, 256, 0, st>>>(d_out + u_split, total_u - u_split, total_u - u_split, d_first + 1));
         uint8_t *hs = (uint8_t *)ctx->pinned;
         CK(cudaMemcpyAsync(hs, d_first, 16, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1720,9 +1742,9 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
         if (start != 0) {
             // the skipped line must end inside the split's own blocks, else the reader's position is past `end`
             if (first_nl == ~0ull) return 0;
-            from = first_nl + 1;
+            from = (first_nl >> 1) + 1 + (first_nl & 1);
         }
-        if (tail_nl != ~0ull) to = u_split + tail_nl + 1;
+        if (tail_nl != ~0ull) to = u_split + (tail_nl >> 1) + 1 + (tail_nl & 1);
         else if (t1 < n) { t1 = std::min(n, t1 + 4); continue; }    // the open line runs through every block decoded so far
         else to = total_u;                                         // end of the file: the last line has no terminator
         if (to < from) to = from;

@@ -401,19 +401,21 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
 //                sub-chunk -- the only serial part: about 1 ms for a 4 MiB block.
 // The first sequence that is not clean (and any offset violation) is reported through shared memory; after the
 // pipeline has drained, warp 0 runs the exact state machine from there, exactly like lz4_parse_kernel's tail.
-constexpr int D1W_WORKERS = 15;
-constexpr int D1W_THREADS = (D1W_WORKERS + 1) * 32;
+// The chain warp, not the workers, bounds a block's time (2.7 ms); 7 workers keep up with it as well as 15 do and leave
+// room for a second CTA on the SM: D1W_WORKERS = 15 for up to one block per SM, 7 for up to two.
 constexpr int D1W_SLOT = (D1_WARP_SMEM + 15) & ~15;
-constexpr int D1W_SMEM = (D1W_WORKERS + 1) * D1W_SLOT + 256;
+constexpr int D1W_MAX_WORKERS = 15;
+template <int D1W_WORKERS> constexpr int d1w_smem_bytes() { return (D1W_WORKERS + 1) * D1W_SLOT + 256; }
 
 struct D1WCtl {
-    volatile int b_ready[D1W_WORKERS];     // half whose exit tables stand in the worker's slot
-    volatile int c_done[D1W_WORKERS];      // half the chain has passed through
+    volatile int b_ready[D1W_MAX_WORKERS]; // half whose exit tables stand in the worker's slot
+    volatile int c_done[D1W_MAX_WORKERS];  // half the chain has passed through
     int stop_h;                            // halves beyond this one need no work (first unclean sequence / violation / end)
     unsigned long long uncl, viol;         // (aligned position << 32) | op, resp. | next token
 };
 
-__global__ void __launch_bounds__(D1W_THREADS, 1)
+template <int D1W_WORKERS>
+__global__ void __launch_bounds__((D1W_WORKERS + 1) * 32, D1W_WORKERS > 7 ? 1 : 2)
 lz4_parse_wide_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, uint32_t *chunk_op, int32_t *result)
 {
     extern __shared__ __align__(16) uint8_t d1w_smem[];
@@ -889,25 +891,23 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
 }
 
 // D2 as a kernel of its own (D1 ran before it): one CTA of W warps per block.
-// W = warps per block (1 .. 32): the host picks it from the batch size -- many blocks in flight need few warps each
-// (and then hardly ever wait on one another), few blocks need many.
-template <int W>
-constexpr size_t d2_smem_bytes() { return sizeof(CopyBlockSmem<W>) + 16 + (size_t)W * sizeof(CopyWarpSmem); }
-
+// W = warps per block (1, 2, 4 or 8): the host picks it from the batch size -- many blocks in flight need few warps
+// each (and then hardly ever wait on one another), few blocks need many.  More than 8 only wait for one another: a
+// chunk's matches mostly point into the last few KiB, i.e. into the chunks the sibling warps still work on
+// (r02i, one block: 8 warps 8.5 ms, 32 warps 12.5 ms).
 template <int W>
 __global__ void __launch_bounds__(W * 32)
 lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t *chunk_op,
                 const int32_t *result)
 {
-    extern __shared__ __align__(16) uint8_t d2_smem[];
-    CopyBlockSmem<W> *s_block = (CopyBlockSmem<W> *)d2_smem;
-    CopyWarpSmem *s_warp = (CopyWarpSmem *)(((uintptr_t)(s_block + 1) + 15) & ~(uintptr_t)15);
+    __shared__ CopyBlockSmem<W> s_block;
+    __shared__ CopyWarpSmem s_warp[W];
     const BlockDesc bd = blocks[blockIdx.x];
     if (bd.stored || result[blockIdx.x] < 0) return;
-    if (threadIdx.x < W) s_block->owed[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_block->ticket = 0;
+    if (threadIdx.x < W) s_block.owed[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_block.ticket = 0;
     if (W > 1) __syncthreads();
-    lz4_copy_block<W>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, s_block, &s_warp[threadIdx.x >> 5]);
+    lz4_copy_block<W>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, &s_block, &s_warp[threadIdx.x >> 5]);
 }
 
 // ---- D0 ------------------------------------------------------------------------------------

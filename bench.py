@@ -349,6 +349,9 @@ class Dist:
         self.json_fd = os.dup(1)
         os.dup2(2, 1)
         if self.world > 1:
+            # the span exchange is pairwise send / recv of hundreds of MB: give a pair more than NCCL's default two channels
+            os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
+            os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
     def barrier(self):

@@ -235,7 +235,12 @@ int fourmc_plan_splits(const int64_t *offsets, int n, int64_t file_size, int64_t
 
 /* FourMcLineRecordReader over one split (FourMcLineRecordReader.java:116-163): every record (line, with its
  * terminator) the reader returns for [start, start + length), concatenated into out.  The split's blocks
- * (and the block(s) that finish its last line) are decoded on the device.  Returns the byte count. */
+ * (and the block(s) that finish its last line) are decoded on the device.  Returns the byte count.
+ * Lines end like Hadoop's LineReader ends them: at LF, at CR, or at CR LF.  Splits are expected as fourmc_plan_splits
+ * makes them (both ends on block starts or the end of the file); for other ranges the blocks that START inside the range
+ * are read.  One corner is deliberately not reproduced: when a block's last byte is a lone CR, Hadoop 1.x's reader
+ * stops there and the next split skips the following line (which is then returned by nobody); here that line is
+ * returned with the split that ends at the CR, as for LF. */
 long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t file_size, int64_t start,
                                        int64_t length, void *out, size_t out_capacity);
 

@@ -41,6 +41,47 @@ def test_splits_return_every_line_once(ctx, pkg, oracle, codec):
         ctx.read_index(bytes(bad))
 
 
+def test_line_terminators_like_hadoop_line_reader(ctx, pkg):
+    """LF, CR and CR LF all end a line (Hadoop's LineReader, behind FourMcLineRecordReader.java:136-163): every split
+    against a model of the reader's rules on the decoded bytes -- skip the first line unless the split starts the
+    file, finish the line that is open at the split's end."""
+    import random
+    rng = random.Random(9)
+    words = gen_logtext(pkg, 64 * 1024).split(b"\n")
+    parts = []
+    size = 0
+    while size < 13 * MIB:
+        ln = words[rng.randrange(len(words))] + rng.choice([b"\n", b"\r\n", b"\r", b"\n"])
+        parts.append(ln); size += len(ln)
+    data = b"".join(parts)
+    stream = ctx.compress_4mc(data)
+    offs = ctx.read_index(stream)
+    ix = pkg.FourMcBlockIndex(offs)
+
+    def eol_end(pos):                                   # end of the first terminator at or after pos, None if there is none
+        a, b = data.find(b"\n", pos), data.find(b"\r", pos)
+        cands = [x for x in (a, b) if x >= 0]
+        if not cands:
+            return None
+        i = min(cands)
+        return i + 2 if data[i:i + 2] == b"\r\n" else i + 1
+
+    for split_size in (3 * MIB, 1 * MIB + 11):
+        splits = ix.plan_splits(len(stream), split_size)
+        got_all = b""
+        for s, ln in splits:
+            b0 = offs.index(s) if s else 0
+            b1 = len([o for o in offs if o < s + ln])
+            u0, u1 = b0 * 4 * MIB, min(len(data), b1 * 4 * MIB)
+            frm = 0 if s == 0 else eol_end(u0)
+            to = len(data) if u1 >= len(data) else (eol_end(u1) or len(data))
+            want = b"" if frm is None or to <= frm else data[frm:to]
+            got = ctx.read_split_lines(stream, s, ln)
+            assert got == want, (split_size, s, ln, len(got), len(want))
+            got_all += got
+        assert got_all == data
+
+
 def test_split_of_reference_written_file(ctx, pkg):
     stream = golden_bytes("logtext_128k.l3.4mc")
     want = golden_bytes("logtext_128k.bin")
