@@ -101,6 +101,7 @@ def lib() -> C.CDLL:
         "fourmc_index_align_slice_end": (C.c_int64, [vp, i32, C.c_int64, C.c_int64]),
         "fourmc_plan_splits": (i32, [vp, i32, C.c_int64, C.c_int64, vp, vp, i32]),
         "fourmc_read_split_lines_host": (C.c_longlong, [vp, vp, sz, C.c_int64, C.c_int64, vp, sz]),
+        "fourmc_read_splits_lines_host": (C.c_longlong, [vp, vp, sz, i32, vp, vp, vp, sz, vp]),
         "fourmc_blockstream_bound": (sz, [i32, sz, sz]),
         "fourmc_blockstream_compress_host": (C.c_longlong, [vp, i32, i32, vp, sz, sz, vp, sz]),
         "fourmc_blockstream_decompress_host": (C.c_longlong, [vp, i32, vp, sz, vp, sz]),
@@ -321,6 +322,23 @@ class Context:
                 continue
             self._check(rc)
             return out.raw[:rc]
+
+    def read_splits_lines(self, stream_bytes, splits) -> list[bytes]:
+        """fourmc_read_splits_lines_host: the records of every (start, length) split, all blocks decoded as one batch."""
+        b = _buf(stream_bytes)
+        n = len(splits)
+        st = (C.c_int64 * max(n, 1))(*[s for s, _ in splits])
+        ln = (C.c_int64 * max(n, 1))(*[l for _, l in splits])
+        offs = (C.c_int64 * (n + 1))()
+        cap = sum(l for _, l in splits) * 8 + (n + 4) * 3 * BLOCKSIZE
+        while True:
+            out = C.create_string_buffer(cap)
+            rc = int(lib().fourmc_read_splits_lines_host(self._h, b, len(b), n, st, ln, out, cap, offs))
+            if rc == E_OUTPUT and cap < (1 << 36):
+                cap *= 4
+                continue
+            self._check(rc)
+            return [out.raw[offs[i]:offs[i + 1]] for i in range(n)]
 
     # ---- device-resident calls: raw device pointers (ints) and an optional CUDA stream handle ----
     def gen_device(self, d_out: int, n_pages: int, seed: int = 0x4D43, first_page: int = 0, kind: int = 0, stream=None):

@@ -127,8 +127,14 @@ void ktime_mark(fourmc_ctx *ctx, const char *name, cudaStream_t st, int which)
     if (!ctx->timing) return;
     if (which == 0) {
         if (ctx->tused * 2 + 2 > ctx->tev.size()) {
-            cudaEvent_t a, b;
-            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) {
+                // no events: stop timing for this context rather than leave the closing mark without a slot
+                if (a) cudaEventDestroy(a);
+                (void)cudaGetLastError();
+                ctx->timing = 0;
+                return;
+            }
             ctx->tev.push_back(a); ctx->tev.push_back(b); ctx->tname.push_back(name);
         }
         ctx->tname[ctx->tused] = name;
@@ -222,6 +228,18 @@ int pipe_depth()
     return v;
 }
 
+// threads per CTA of the block write kernels (one CTA per block: copies, then one warp hashes the payload)
+int write_threads()
+{
+    static int v = 0;
+    if (!v) {
+        const char *e = getenv("FOURMC_WRITE_THREADS");
+        v = e ? atoi(e) : ENC_WRITE_THREADS;
+        if (v != 64 && v != 128 && v != 256) v = ENC_WRITE_THREADS;
+    }
+    return v;
+}
+
 int level_min_match(int level)
 {
     // level 1 (Fast): minimum match 5 gives fewer, longer sequences at the same ratio on text
@@ -311,7 +329,7 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
                                                            (BlockPlan *)ws.plan.p, lens, raw_limit, rpb, block_bytes));
     KL("scan_lens_kernel", st, scan_lens_kernel<<<1, SCAN_THREADS, 0, st>>>(lens, nb, base, (uint64_t *)ws.off.p,
                                                  (uint64_t *)((uint8_t *)ws.misc.p + 8)));
-    KL("lz4_block_write_kernel", st, lz4_block_write_kernel<<<nb, ENC_WRITE_THREADS, 0, st>>>(d_in, (const uint8_t *)ws.scratch.p,
+    KL("lz4_block_write_kernel", st, lz4_block_write_kernel<<<nb, write_threads(), 0, st>>>(d_in, (const uint8_t *)ws.scratch.p,
                                                              (const RegionMeta *)ws.meta.p, (const BlockPlan *)ws.plan.p,
                                                              (const uint64_t *)ws.off.p, d_out_base, raw_limit >= 0 ? 1 : 0,
                                                              rpb, region_bytes, slot_bytes, block_bytes));
@@ -401,7 +419,7 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
             (const fmz::ZRegionOut *)ws.zrout.p, gb, gn, (BlockPlan *)ws.plan.p + g0, lens + g0, raw_limit, region_bytes, rpb, block_bytes));
         KL("scan_lens_carry_kernel", st, scan_lens_carry_kernel<<<1, SCAN_THREADS, 0, st>>>(
             lens + g0, gb, (uint64_t *)(misc + 24), (uint64_t *)ws.off.p + g0, (uint64_t *)(misc + 8)));
-        KL("zstd_block_write_kernel", st, zstd_block_write_kernel<<<gb, ENC_WRITE_THREADS, 0, st>>>(
+        KL("zstd_block_write_kernel", st, zstd_block_write_kernel<<<gb, write_threads(), 0, st>>>(
             d_in + goff, (const uint8_t *)ws.zout.p, (const fmz::ZRegionOut *)ws.zrout.p, (const BlockPlan *)ws.plan.p + g0,
             (const uint64_t *)ws.off.p + g0, d_out_base, raw_limit >= 0 ? 1 : 0, region_bytes, rpb, block_bytes));
     }
@@ -1643,8 +1661,8 @@ __global__ void find_eol_kernel(const uint8_t *p, unsigned long long n, unsigned
 // .4mc / .4mz file in host memory -- when start != 0 the first (partial) line is skipped, and the line that is
 // being read when the position passes the split end is finished from the following block(s).  The split's
 // blocks are decoded on the device in one batch; the two line boundaries are found there too.
-long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t file_size, int64_t start, int64_t length,
-                                       void *out, size_t out_capacity)
+static long long read_split_impl(fourmc_ctx *ctx, const void *file, size_t file_size, int64_t start, int64_t length,
+                                 void *out, size_t out_capacity, const int slot)
 {
     if (!ctx || !file || start < 0 || length < 0 || (!out && out_capacity)) return FOURMC_E_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -1684,7 +1702,7 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
         return h.c <= FOURMC_BLOCKSIZE && (h.u == h.c || h.u <= FOURMC_BLOCKSIZE) && h.src + h.c <= file_size && h.u != 0;
     };
     cudaStream_t st = ctx->stream;
-    DecWs &ws = ctx->dec[0];
+    DecWs &ws = ctx->dec[slot];
     int r;
     if ((r = pinned_scratch(ctx, 4096))) return r;
     int t1 = std::min(n, b1 + 1);                                  // decode through block t1 - 1
@@ -1694,8 +1712,8 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
         uint64_t total_u = 0;
         for (uint32_t i = 0; i < cnt; i++) { if (!header(b0 + (int)i, hb[i])) return FOURMC_E_CONTENT; total_u += hb[i].u; }
         const uint64_t src0 = hb[0].src, src1 = hb[cnt - 1].src + hb[cnt - 1].c;
-        if ((r = ensure(ctx, ctx->stage_in[0], (size_t)(src1 - src0) + 64))) return r;
-        if ((r = ensure(ctx, ctx->stage_out[0], (size_t)total_u + 64))) return r;
+        if ((r = ensure(ctx, ctx->stage_in[slot], (size_t)(src1 - src0) + 64))) return r;
+        if ((r = ensure(ctx, ctx->stage_out[slot], (size_t)total_u + 64))) return r;
         const size_t tb = (size_t)cnt * 33 + 64 + 16;
         if ((r = ensure(ctx, ws.tables, tb))) return r;
         std::vector<uint8_t> ht((size_t)cnt * 28);
@@ -1708,7 +1726,7 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
             if ((int)i < b1 - b0) u_split = dpos;                  // decoded bytes of the split's own blocks
         }
         uint8_t *d_tb = (uint8_t *)ws.tables.p;
-        CK(cudaMemcpyAsync(ctx->stage_in[0].p, f + src0, (size_t)(src1 - src0), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->stage_in[slot].p, f + src0, (size_t)(src1 - src0), cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_tb, ht.data(), ht.size(), cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));                             // ht is pageable host memory
         const uint64_t *d_so = (const uint64_t *)d_tb, *d_do = d_so + cnt;
@@ -1716,7 +1734,7 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
         int32_t *d_osz = (int32_t *)(d_x + cnt);
         uint8_t *d_st = (uint8_t *)(d_osz + cnt);
         unsigned long long *d_first = (unsigned long long *)(((uintptr_t)(d_st + cnt) + 15) & ~(uintptr_t)15);
-        if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[0].p, d_so, d_c, d_u, d_x, 1, ctx->stage_out[0].p, d_do, d_osz, d_st, codec, 1)))
+        if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[slot].p, d_so, d_c, d_u, d_x, 1, ctx->stage_out[slot].p, d_do, d_osz, d_st, codec, 1)))
             return r;
         // what the blocks really decoded to (a block may decode short, native/4mc.c:661-666; the batch closed the gaps)
         std::vector<uint8_t> status(cnt);
@@ -1729,7 +1747,7 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
         for (uint32_t i = 0; i < cnt; i++) { total_u += (uint64_t)osz[i]; if ((int)i < b1 - b0) u_split = total_u; }
         // first line terminator of the split (skipped line) and the first one at or after the split's end
         CK(cudaMemsetAsync(d_first, 0xff, 16, st));
-        const uint8_t *d_out = (const uint8_t *)ctx->stage_out[0].p;
+        const uint8_t *d_out = (const uint8_t *)ctx->stage_out[slot].p;
         if (start != 0 && u_split)
             KL("find_eol_kernel", st, find_eol_kernel<<<1024, 256, 0, st>>>(d_out, u_split, total_u, d_first));
         if (total_u > u_split)
@@ -1755,6 +1773,196 @@ long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t
         }
         return (long long)(to - from);
     }
+}
+
+long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t file_size, int64_t start, int64_t length,
+                                       void *out, size_t out_capacity)
+{
+    return read_split_impl(ctx, file, file_size, start, length, out, out_capacity, 0);
+}
+
+namespace {
+struct EolJob { unsigned long long off, n, n_avail; };        // a search of d_out + off .. for the first line end
+__global__ void find_eol_batch_kernel(const uint8_t *base, const EolJob *jobs, unsigned long long *first)
+{
+    const EolJob j = jobs[blockIdx.y];
+    const uint8_t *p = base + j.off;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < j.n; i += stride) {
+        const uint8_t c = p[i];
+        if (c == '\n' || c == '\r') {
+            const unsigned long long crlf = (c == '\r' && i + 1 < j.n_avail && p[i + 1] == '\n') ? 1ull : 0ull;
+            atomicMin(&first[blockIdx.y], 2 * i + crlf);
+            break;
+        }
+    }
+}
+}  // namespace
+
+// Many splits of one file in one call (what a node running many map tasks over one file asks for; BASELINE.json
+// configs[4]).  Same records per split as fourmc_read_split_lines_host; the blocks of ALL the splits are decoded as one
+// batch, which is what the GPU is good at -- a split alone is two or three blocks and those take 13 ms however idle the
+// chip is.  The records of split i land at out + out_offsets[i] (back to back, split order); out_offsets has
+// n_splits + 1 entries, the last one is the total, which is also the return value.
+long long fourmc_read_splits_lines_host(fourmc_ctx *ctx, const void *file, size_t file_size, int n_splits, const int64_t *starts,
+                                        const int64_t *lengths, void *out, size_t out_capacity, int64_t *out_offsets)
+{
+    if (!ctx || !file || n_splits < 0 || (n_splits && (!starts || !lengths)) || !out_offsets || (!out && out_capacity)) return FOURMC_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint8_t *f = (const uint8_t *)file;
+    out_offsets[0] = 0;
+    if (n_splits == 0) return 0;
+    if (file_size < 12) return FOURMC_E_CONTENT;
+    const uint32_t magic = be32(f);
+    if (magic != FOURMC_MAGIC_4MC && magic != FOURMC_MAGIC_4MZ) return FOURMC_E_CONTENT;
+    const int codec = magic == FOURMC_MAGIC_4MZ ? CODEC_ZSTD : CODEC_LZ4;
+    if (ctx->idx_file != file || ctx->idx_size != file_size || memcmp(ctx->idx_tail, f + file_size - 12, 12) != 0) {
+        ctx->idx_file = nullptr;
+        const long long nb_ll = fourmc_read_index_host(ctx, file, file_size, nullptr, 0);
+        if (nb_ll < 0) return nb_ll;
+        ctx->idx_offs.assign((size_t)nb_ll, 0);
+        if (nb_ll) fourmc_read_index_host(ctx, file, file_size, ctx->idx_offs.data(), ctx->idx_offs.size());
+        ctx->idx_file = file; ctx->idx_size = file_size; memcpy(ctx->idx_tail, f + file_size - 12, 12);
+    }
+    const std::vector<int64_t> &offs = ctx->idx_offs;
+    const int n = (int)offs.size();
+    struct HB { uint64_t src; uint32_t c, u, x; };
+    auto header = [&](int b, HB &h) -> bool {
+        const uint64_t o = (uint64_t)offs[b];
+        if (o + 12 > file_size) return false;
+        h.u = be32(f + o); h.c = be32(f + o + 4); h.x = be32(f + o + 8); h.src = o + 12;
+        return h.c <= FOURMC_BLOCKSIZE && (h.u == h.c || h.u <= FOURMC_BLOCKSIZE) && h.src + h.c <= file_size && h.u != 0;
+    };
+    // per split: its blocks [b0, b1) plus one more that finishes the open line
+    struct Sp { int b0, b1, t1; uint32_t first_item; uint64_t in_off, out_off, u_split, u_total; bool empty, fallback; };
+    std::vector<Sp> sp((size_t)n_splits);
+    std::vector<HB> hb;
+    uint64_t in_total = 0, out_total = 0;
+    for (int i = 0; i < n_splits; i++) {
+        Sp &q = sp[i];
+        q.empty = true; q.fallback = false;
+        if (n == 0 || starts[i] < 0 || lengths[i] < 0) { if (starts[i] < 0 || lengths[i] < 0) return FOURMC_E_ARG; continue; }
+        const int64_t start = starts[i], end = start + lengths[i];
+        int b0 = 0;
+        if (start != 0) {
+            const int64_t s0 = fourmc_index_find_next_position(offs.data(), n, start);
+            if (s0 == FOURMC_NOT_FOUND || s0 >= end) continue;
+            b0 = (int)(std::lower_bound(offs.begin(), offs.end(), s0) - offs.begin());
+        }
+        const int b1 = (int)(std::lower_bound(offs.begin(), offs.end(), end) - offs.begin());
+        if (b0 >= b1) continue;
+        q.empty = false; q.b0 = b0; q.b1 = b1; q.t1 = std::min(n, b1 + 1);
+        q.first_item = (uint32_t)hb.size(); q.in_off = in_total; q.out_off = out_total; q.u_split = 0; q.u_total = 0;
+        for (int b = b0; b < q.t1; b++) {
+            HB h;
+            if (!header(b, h)) return FOURMC_E_CONTENT;
+            hb.push_back(h);
+            q.u_total += h.u;
+            if (b < b1) q.u_split = q.u_total;
+        }
+        const HB &h0 = hb[q.first_item], &h1 = hb.back();
+        in_total += ((h1.src + h1.c - h0.src) + 15) & ~(uint64_t)15;
+        out_total += (q.u_total + 15) & ~(uint64_t)15;
+    }
+    const uint32_t cnt = (uint32_t)hb.size();
+    std::vector<std::vector<uint8_t>> fb((size_t)n_splits);        // records of the splits that went through the single-split call
+    std::vector<uint64_t> from((size_t)n_splits, 0), to((size_t)n_splits, 0);
+    cudaStream_t st = ctx->stream;
+    DecWs &ws = ctx->dec[0];
+    int r;
+    if (cnt) {
+        if ((r = ensure(ctx, ctx->stage_in[0], (size_t)in_total + 64))) return r;
+        if ((r = ensure(ctx, ctx->stage_out[0], (size_t)out_total + 64))) return r;
+        const size_t tb = (size_t)cnt * 33 + 64 + (size_t)n_splits * 2 * (sizeof(EolJob) + 8) + 64;
+        if ((r = ensure(ctx, ws.tables, tb))) return r;
+        std::vector<uint8_t> ht((size_t)cnt * 28);
+        uint64_t *t_src = (uint64_t *)ht.data(), *t_dst = t_src + cnt;
+        uint32_t *t_c = (uint32_t *)(t_dst + cnt), *t_u = t_c + cnt, *t_x = t_u + cnt;
+        std::vector<EolJob> jobs((size_t)n_splits * 2, EolJob{0, 0, 0});
+        for (int i = 0; i < n_splits; i++) {
+            const Sp &q = sp[i];
+            if (q.empty) continue;
+            const HB &h0 = hb[q.first_item];
+            const uint32_t k = (uint32_t)(q.t1 - q.b0);
+            const uint64_t bytes = hb[q.first_item + k - 1].src + hb[q.first_item + k - 1].c - h0.src;
+            CK(cudaMemcpyAsync((uint8_t *)ctx->stage_in[0].p + q.in_off, f + h0.src, (size_t)bytes, cudaMemcpyHostToDevice, st));
+            uint64_t dpos = q.out_off;
+            for (uint32_t j = 0; j < k; j++) {
+                const HB &h = hb[q.first_item + j];
+                t_src[q.first_item + j] = q.in_off + (h.src - h0.src); t_dst[q.first_item + j] = dpos;
+                t_c[q.first_item + j] = h.c; t_u[q.first_item + j] = h.u; t_x[q.first_item + j] = h.x;
+                dpos += h.u;
+            }
+            if (starts[i] != 0) jobs[2 * i] = EolJob{q.out_off, q.u_split, q.u_total};
+            if (q.u_total > q.u_split) jobs[2 * i + 1] = EolJob{q.out_off + q.u_split, q.u_total - q.u_split, q.u_total - q.u_split};
+        }
+        uint8_t *d_tb = (uint8_t *)ws.tables.p;
+        CK(cudaMemcpyAsync(d_tb, ht.data(), ht.size(), cudaMemcpyHostToDevice, st));
+        const uint64_t *d_so = (const uint64_t *)d_tb, *d_do = d_so + cnt;
+        const uint32_t *d_c = (const uint32_t *)(d_do + cnt), *d_u = d_c + cnt, *d_x = d_u + cnt;
+        int32_t *d_osz = (int32_t *)(d_x + cnt);
+        uint8_t *d_st = (uint8_t *)(d_osz + cnt);
+        EolJob *d_jobs = (EolJob *)(((uintptr_t)(d_st + cnt) + 15) & ~(uintptr_t)15);
+        unsigned long long *d_first = (unsigned long long *)(d_jobs + (size_t)n_splits * 2);
+        CK(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(EolJob), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                                 // ht and jobs are pageable
+        if ((r = dec_batch(ctx, st, ws, cnt, ctx->stage_in[0].p, d_so, d_c, d_u, d_x, 1, ctx->stage_out[0].p, d_do, d_osz, d_st, codec)))
+            return r;
+        CK(cudaMemsetAsync(d_first, 0xff, (size_t)n_splits * 16, st));
+        KL("find_eol_batch_kernel", st, find_eol_batch_kernel<<<dim3(32, (unsigned)n_splits * 2), 256, 0, st>>>(
+            (const uint8_t *)ctx->stage_out[0].p, d_jobs, d_first));
+        std::vector<uint8_t> status(cnt);
+        std::vector<int32_t> osz(cnt);
+        std::vector<unsigned long long> first((size_t)n_splits * 2);
+        CK(cudaMemcpyAsync(status.data(), d_st, cnt, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(osz.data(), d_osz, (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(first.data(), d_first, first.size() * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < cnt; i++) if (status[i] != FOURMC_BLOCK_OK) return FOURMC_E_CONTENT;
+        for (int i = 0; i < n_splits; i++) {
+            Sp &q = sp[i];
+            if (q.empty) continue;
+            // a block that decoded short, or a line still open after the extra block: the single-split call knows how
+            for (int j = 0; j < q.t1 - q.b0; j++) if ((uint32_t)osz[q.first_item + j] != hb[q.first_item + j].u) q.fallback = true;
+            const unsigned long long first_nl = first[2 * i], tail_nl = first[2 * i + 1];
+            if (starts[i] != 0) {
+                if (first_nl == ~0ull) { q.empty = true; continue; }
+                from[i] = (first_nl >> 1) + 1 + (first_nl & 1);
+            }
+            if (tail_nl != ~0ull) to[i] = q.u_split + (tail_nl >> 1) + 1 + (tail_nl & 1);
+            else if (q.t1 < n) q.fallback = true;
+            else to[i] = q.u_total;
+            if (to[i] < from[i]) to[i] = from[i];
+        }
+    }
+    // splits that need the general path
+    for (int i = 0; i < n_splits; i++) {
+        if (sp[i].empty || !sp[i].fallback) continue;
+        size_t cap = (size_t)(sp[i].u_total + 4 * FOURMC_BLOCKSIZE);
+        for (;;) {
+            fb[i].resize(cap);
+            const long long got = read_split_impl(ctx, file, file_size, starts[i], lengths[i], fb[i].data(), cap, 1);   // slot 1: slot 0 holds the batch
+            if (got == FOURMC_E_OUTPUT && cap < ((size_t)1 << 34)) { cap *= 4; continue; }
+            if (got < 0) return got;
+            fb[i].resize((size_t)got);
+            break;
+        }
+    }
+    // pack in split order
+    uint64_t pos = 0;
+    for (int i = 0; i < n_splits; i++) {
+        out_offsets[i] = (int64_t)pos;
+        if (sp[i].empty) continue;
+        const uint64_t len = sp[i].fallback ? fb[i].size() : to[i] - from[i];
+        if (pos + len > out_capacity) return fail(ctx, FOURMC_E_OUTPUT, "destination too small");
+        if (sp[i].fallback) memcpy((uint8_t *)out + pos, fb[i].data(), (size_t)len);
+        else if (len) CK(cudaMemcpyAsync((uint8_t *)out + pos, (const uint8_t *)ctx->stage_out[0].p + sp[i].out_off + from[i], (size_t)len,
+                                         cudaMemcpyDeviceToHost, st));
+        pos += len;
+    }
+    out_offsets[n_splits] = (int64_t)pos;
+    CK(cudaStreamSynchronize(st));
+    return (long long)pos;
 }
 
 // ZSTD_decompress on one block (native/4mc.c:810, native/jniZstdDecompressor.c): decoded size, or a

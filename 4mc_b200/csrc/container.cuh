@@ -173,7 +173,11 @@ read_index_kernel(const uint8_t *in, uint64_t n, uint32_t n_blocks_host, uint8_t
         c_off += total;
         uint32_t u = 0, c = 0, ck = 0;
         bool bad = false;
-        if (live) {
+        // a range reader looks at its own blocks only (the others may not even be there: the ranks of a multi-GPU
+        // reader each hold their part of the stream); the index itself is validated as a whole either way
+        const bool looked_at = live && (count == 0xffffffffu || (i >= first && i - first < count));
+        if (live && !looked_at) { u = FOURMC_BLOCKSIZE; c = 0; }
+        if (looked_at) {
             if (off + 12 > eos_pos) bad = true;
             else {
                 u = ld_be32(in + off); c = ld_be32(in + off + 4); ck = ld_be32(in + off + 8);

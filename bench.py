@@ -12,10 +12,12 @@ stream is decompressed again (index parse, XXH32 verify, block decode), everythi
 `value` = uncompressed bytes of the batch / step time.
 
 Multi-GPU (one process per GPU, torchrun): STRONG scaling of that one step.  The batch's blocks are split into
-contiguous ranges, one per rank; every rank compresses its range into a span, the block lengths and
-span sizes are all-gathered, the spans are exchanged over NVLink (NCCL send / recv straight into place) so that the
-single stream -- header, all spans in order, end mark, footer index -- stands assembled in HBM; then every rank decodes
-ITS block range of that one stream, found through the shared footer index (no collective on the read path).
+contiguous ranges, one per rank; every rank compresses its range into a span; the block lengths and
+span sizes are all-gathered (the only collectives), which gives every rank the footer index and every span's offset;
+the spans travel over NVLink (NCCL send / recv straight into place) to rank 0, where the single stream -- header, all
+spans in order, end mark, footer index -- stands assembled in HBM when the step ends (and is decoded as a whole and
+compared with the input after the timed region); meanwhile every rank decodes ITS block range of that stream, found
+through the shared footer index -- the bytes of its range are the ones it wrote, so it reads its local copy.
 `weak` in the line is the former figure (every rank round-trips a private stream of its own data).
 
 `e2e` is the same round trip through the host-buffer C-ABI calls (fourmc_4mc_compress_host / fourmc_4mc_decompress_host)
@@ -67,7 +69,9 @@ def parse_args():
     ap.add_argument("--batch-gib", type=float, default=None, help="bytes per step over all GPUs")
     ap.add_argument("--e2e-gib", type=float, default=8.0, help="bytes per end-to-end step over all GPUs")
     ap.add_argument("--cpu-gib", type=float, default=None, help="bytes per CPU step (reference arm / cpu_baseline)")
-    ap.add_argument("--split-threads", type=int, default=8, help="configs[4]: reader threads (contexts) per GPU")
+    ap.add_argument("--split-threads", type=int, default=2, help="configs[4]: reader threads (contexts) per GPU")
+    ap.add_argument("--splits-per-call", type=int, default=64, help="configs[4]: splits handed to one fourmc_read_splits_lines_host call "
+                    "(1 = the single-split call)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-weak", action="store_true")
@@ -460,33 +464,33 @@ def main_ours(args):
             csz = int(size.item())                # the stream length the reader needs (one 8-byte D2H)
             decompress_device(comp.data_ptr(), csz, out.data_ptr(), batch_g, res.data_ptr(), stream=st)
         else:
-            # writer: my block range -> a span; lengths and span sizes to everybody; spans straight into place
+            # writer: my block range -> a span; block lengths and span sizes to everybody (the only collectives)
             compress_span_device(s_ptr, my_bytes, span.data_ptr(), span_cap, size.data_ptr(), d_block_lens=lens.data_ptr(),
                                  level=level, stream=st)
             dist.all_gather_into_tensor(all_lens, lens)
             dist.all_gather_into_tensor(all_sizes, size)
             sizes = all_sizes.cpu().tolist()      # span sizes are needed on the host: they size the transfers
             offs = pkg.span_base_offsets(sizes)
-            ops = []
-            for p in range(world):
-                if p == rank or sizes[p] == 0:
-                    continue
-                ops.append(dist.P2POp(dist.irecv, comp[offs[p]:offs[p] + sizes[p]], p))
-            for p in range(world):
-                if p != rank and sizes[rank]:
-                    ops.append(dist.P2POp(dist.isend, span[:sizes[rank]], p))
-            reqs = dist.batch_isend_irecv(ops) if ops else []
+            spans_end = 12 + sum(sizes)
+            csz = spans_end + 12 + 20 + 4 * nb_g
+            # every rank: its own span at its place in the stream, header + end mark + footer index from the gathered lengths
             comp[offs[rank]:offs[rank] + sizes[rank]].copy_(span[:sizes[rank]], non_blocking=True)
             torch.index_select(all_lens, 0, keep, out=packed_lens)
-            spans_end = 12 + sum(sizes)
             build_index_device(packed_lens.data_ptr(), nb_g, comp.data_ptr(), comp.data_ptr() + spans_end, stream=st)
-            for r in reqs:
-                r.wait()
-            csz = spans_end + 12 + 20 + 4 * nb_g
             if record:
                 record[1].record(stream)
-            # reader: my block range of that one stream, through its footer index
+            # the ONE stream is assembled on rank 0: the other ranks' spans travel there over NVLink (NCCL send / recv
+            # straight into place) while ...
+            if rank == 0:
+                ops = [dist.P2POp(dist.irecv, comp[offs[p]:offs[p] + sizes[p]], p) for p in range(1, world) if sizes[p]]
+            else:
+                ops = [dist.P2POp(dist.isend, span[:sizes[rank]], 0)] if sizes[rank] else []
+            reqs = dist.batch_isend_irecv(ops) if ops else []
+            # ... every rank reads ITS block range of that stream, located through the shared footer index; the bytes of
+            # its range are the ones it has just written, so it reads its local copy of them (no collective, no transfer)
             ctx.decompress_range_device(comp.data_ptr(), csz, lo, my_nb, out.data_ptr(), my_bytes, res.data_ptr(), stream=st, zstd=zst)
+            for r in reqs:
+                r.wait()                          # the step ends when the assembled stream stands on rank 0
         if record:
             record[2].record(stream)
         last.update(b=b, csz=csz)
@@ -522,14 +526,24 @@ def main_ours(args):
     t_c = D.max(sum(e[0].elapsed_time(e[1]) for e in evs))
     t_d = D.max(sum(e[1].elapsed_time(e[2]) for e in evs))
 
-    # verification outside the timed region: every rank's decoded range equals its input range; the assembled stream's
-    # container fields are in order (rank 0 holds the whole stream like every other rank)
+    # verification outside the timed region: every rank's decoded range equals its input range; and the stream that was
+    # assembled on rank 0 is decoded there as a whole and compared with the regenerated input of the whole batch
     r = res.cpu().tolist()
     ok = r == [my_bytes, -1] and bool(torch.equal(out, src[last["b"] * my_bytes:(last["b"] + 1) * my_bytes]))
     if rank == 0:
         csz = last["csz"]
         tail_len = 12 + 20 + 4 * nb_g
         check_stream_layout(bytes(comp[:12].cpu().numpy()), bytes(comp[csz - tail_len:csz].cpu().numpy()), csz, nb_g, magic)
+        if world > 1:
+            whole = torch.empty(batch_g, dtype=torch.uint8, device="cuda")
+            want = torch.empty(batch_g, dtype=torch.uint8, device="cuda")
+            ctx.gen_device(want.data_ptr(), batch_g // 4096, seed=cfg["seed"], first_page=last["b"] * nb_g * (BLOCK // 4096),
+                           kind=cfg["kind"], stream=st)
+            res2 = torch.zeros(2, dtype=torch.int64, device="cuda")
+            decompress_device(comp.data_ptr(), csz, whole.data_ptr(), batch_g, res2.data_ptr(), stream=st)
+            torch.cuda.synchronize()
+            ok = ok and res2.cpu().tolist() == [batch_g, -1] and bool(torch.equal(whole, want))
+            del whole, want
     if D.sum(0.0 if ok else 1.0) > 0:
         raise SystemExit(f"round trip FAILED on some rank (rank {rank}: result {r})")
 
@@ -669,7 +683,7 @@ def main_ours(args):
                    "ratio": ratio, "level": level, "verified_round_trip": True, "single_stream_bytes": last["csz"],
                    "blocks_per_step": nb_g, "blocks_per_step_per_gpu": my_nb, "resident_input_gib_per_gpu": len(src) / GIB,
                    "parallelism": f"one stream, contiguous block ranges x{world}" + ("" if world == 1 else
-                                  "; spans exchanged by NCCL send/recv, lengths all-gathered, every rank decodes its range of the assembled stream"),
+                                  "; lengths + span sizes all-gathered, spans gathered to rank 0 by NCCL send/recv while every rank decodes its block range"),
                    "step_ms_rank0": [[round(e[0].elapsed_time(e[1]), 2), round(e[1].elapsed_time(e[2]), 2)] for e in evs],
                    "kernel_ms_rank0": {k: {"launches": v[0], "total_ms": round(v[1], 3)} for k, v in sorted(ktimes.items())}},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "weak": weak, "gpu_launches": launches, "clocks": clocks,
@@ -680,9 +694,11 @@ def main_ours(args):
 def main_splits(args):
     """configs[4]: one .4mc file (log text, written by this repo's writer) in host memory; the splits Hadoop would
     plan for it (FourMcInputFormat.getSplits over byte ranges of file/10000 bytes) are dealt round-robin to the ranks
-     and read through fourmc_read_split_lines_host -- per split: index lookup, the split's blocks
-    decoded on the GPU, line boundaries found there, the records copied back.  A step = `batch_gib` worth of splits;
-    a rank keeps `--split-threads` splits in flight (one context per thread, as a node runs several map tasks)."""
+     and read through fourmc_read_splits_lines_host, `--splits-per-call` at a time (a node runs many map
+    tasks over one file: their splits are handed over together and decoded as one batch) -- per split: index lookup,
+    its blocks decoded on the GPU, line boundaries found there, the records copied back.  --splits-per-call 1 is the
+    single-split call (fourmc_read_split_lines_host).  A step = `batch_gib` worth of splits, over `--split-threads`
+    reader threads (one context each)."""
     cfg = args.cfg
     D = Dist()
     torch, rank, world = D.torch, D.rank, D.world
@@ -734,17 +750,25 @@ def main_splits(args):
     mine = pkg.shard_splits(ns, world, rank)
     per_step = max(1, int(len(mine) * min(1.0, cfg["batch_gib"] * GIB / n_in)))
     T = max(1, args.split_threads)
+    B = max(1, args.splits_per_call)
     ctxs = [ctx] + [pkg.Context(D.local) for _ in range(T - 1)]
-    out_cap = int(split_size * 8 + 3 * BLOCK)
+    out_cap = int(B * (split_size * 8 + 3 * BLOCK))
     bufs = [torch.empty(out_cap, dtype=torch.uint8, pin_memory=True) for _ in range(T)]
     pool = ThreadPoolExecutor(T)
 
     def read_some(t, idxs):
         got = 0
-        for i in idxs:
-            r = lib.fourmc_read_split_lines_host(ctxs[t].handle, fptr, file_size, st_arr[i], ln_arr[i], bufs[t].data_ptr(), out_cap)
+        for j0 in range(0, len(idxs), B):
+            part = idxs[j0:j0 + B]
+            if B == 1:
+                r = lib.fourmc_read_split_lines_host(ctxs[t].handle, fptr, file_size, st_arr[part[0]], ln_arr[part[0]], bufs[t].data_ptr(), out_cap)
+            else:
+                a = (C.c_int64 * len(part))(*[st_arr[i] for i in part])
+                b = (C.c_int64 * len(part))(*[ln_arr[i] for i in part])
+                o = (C.c_int64 * (len(part) + 1))()
+                r = lib.fourmc_read_splits_lines_host(ctxs[t].handle, fptr, file_size, len(part), a, b, bufs[t].data_ptr(), out_cap, o)
             if r < 0:
-                raise RuntimeError(f"split {i}: error {r}")
+                raise RuntimeError(f"splits {part[:3]}..: error {r}")
             got += r
         return got
 
@@ -753,7 +777,8 @@ def main_splits(args):
     def step():
         idxs = [mine[(cursor[0] + j) % len(mine)] for j in range(per_step)]
         cursor[0] += per_step
-        return sum(pool.map(lambda t: read_some(t, idxs[t::T]), range(T)))
+        chunk = -(-len(idxs) // T)
+        return sum(pool.map(lambda t: read_some(t, idxs[t * chunk:(t + 1) * chunk]), range(T)))
 
     for _ in range(min(args.warmup, 2)):
         step()
@@ -788,10 +813,10 @@ def main_splits(args):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": config_dict(cfg),
         "detail": {"file_gib": file_size / GIB, "uncompressed_gib": n_in / GIB, "blocks": nb, "splits_planned": ns,
-                   "split_bytes": split_size, "splits_per_step_per_gpu": per_step, "threads_per_gpu": T,
+                   "split_bytes": split_size, "splits_per_step_per_gpu": per_step, "threads_per_gpu": T, "splits_per_call": B,
                    "splits_per_s": splits_done / dt, "host_copy": "the file is replicated in every rank's host memory (pageable)",
                    "note": "file scaled to the host memory of this box when 40 GiB x ranks does not fit"},
-        "roofline": {"bound": "hbm", "kernel": "per-split decode (lz4_parse_kernel + lz4_copy_kernel on 2-3 blocks)",
+        "roofline": {"bound": "hbm", "kernel": "split decode (parse + copy kernels over the blocks of one call)",
                      "achieved": (total_got + comp_read) / dt / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": (total_got + comp_read) / dt / 1e9 / peak, "traffic": None, "peak_source": peak_src},
         "cpu_baseline": cpu,

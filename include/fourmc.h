@@ -244,6 +244,14 @@ int fourmc_plan_splits(const int64_t *offsets, int n, int64_t file_size, int64_t
 long long fourmc_read_split_lines_host(fourmc_ctx *ctx, const void *file, size_t file_size, int64_t start,
                                        int64_t length, void *out, size_t out_capacity);
 
+/* Many splits of one file in one call: the same records per split, the blocks of all the splits decoded as ONE batch
+ * (a split alone is two or three blocks -- a latency-bound call; a node that runs many map tasks over one file hands
+ * their splits over together).  The records of split i land at out + out_offsets[i], back to back in split order;
+ * out_offsets has n_splits + 1 entries, the last one being the total, which is also the return value. */
+long long fourmc_read_splits_lines_host(fourmc_ctx *ctx, const void *file, size_t file_size, int n_splits,
+                                        const int64_t *starts, const int64_t *lengths,
+                                        void *out, size_t out_capacity, int64_t *out_offsets);
+
 /* ---- synthetic inputs, bit-identical on host and device ---------------------- */
 
 /* kind 0 = log-text (configs[0], [1]), 1 = JSON lines (configs[2]), 2 = silesia-like mix of block types

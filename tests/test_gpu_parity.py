@@ -162,6 +162,17 @@ def test_sharded_writer_and_reader_share_one_stream(ctx, ora, ref_cli, pkg, tmp_
             c.sync()
             assert res.cpu().tolist() == [len(want), -1]
             assert bytes(d_out[:len(want)].cpu().numpy()) == want
+            # a rank that holds only ITS part of the stream (header, own span, end mark + footer): a range reader
+            # looks at its own blocks only
+            d_part = torch.full((total + 64,), 0xAB, dtype=torch.uint8, device="cuda")
+            d_part[:12].copy_(d_stream[:12])
+            d_part[offs[r]:offs[r] + sizes[r]].copy_(spans[r])
+            d_part[12 + sum(sizes):total].copy_(d_stream[12 + sum(sizes):total])
+            d_out.zero_()
+            c.decompress_range_device(d_part.data_ptr(), total, lo, hi - lo, d_out.data_ptr(), len(want), res.data_ptr(), zstd=zstd)
+            c.sync()
+            assert res.cpu().tolist() == [len(want), -1]
+            assert bytes(d_out[:len(want)].cpu().numpy()) == want
     finally:
         for c in ranks:
             c.close()

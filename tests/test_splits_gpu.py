@@ -82,6 +82,23 @@ def test_line_terminators_like_hadoop_line_reader(ctx, pkg):
         assert got_all == data
 
 
+@pytest.mark.parametrize("codec", ["4mc", "4mz"])
+def test_many_splits_in_one_call(ctx, pkg, codec):
+    """fourmc_read_splits_lines_host: the blocks of all the splits decoded as one batch; per split the same records as
+    the single-split call (including the three-block line, which takes the general path inside)."""
+    data = make_input(pkg)
+    stream = ctx.compress_4mc(data) if codec == "4mc" else ctx.compress_4mz(data)
+    ix = pkg.FourMcBlockIndex(ctx.read_index(stream))
+    for split_size in (2 * MIB, 700 * 1024, len(stream)):
+        splits = ix.plan_splits(len(stream), split_size)
+        one_by_one = [ctx.read_split_lines(stream, s, ln) for s, ln in splits]
+        assert ctx.read_splits_lines(stream, splits) == one_by_one
+        assert b"".join(one_by_one) == data
+        picked = splits[::-2]                                   # any subset, any order
+        assert ctx.read_splits_lines(stream, picked) == one_by_one[::-2]
+    assert ctx.read_splits_lines(stream, []) == []
+
+
 def test_split_of_reference_written_file(ctx, pkg):
     stream = golden_bytes("logtext_128k.l3.4mc")
     want = golden_bytes("logtext_128k.bin")
