@@ -12,6 +12,7 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "blockstream.h"
@@ -71,6 +72,8 @@ struct fourmc_ctx {
     DevBuf stage_in[FM_PIPE_MAX], stage_out[FM_PIPE_MAX];    // device staging for the host-pointer entry points
     void *pinned = nullptr;              // small pinned scratch for scalars
     size_t pinned_cap = 0;
+    void *pin_up[2] = {nullptr, nullptr};   // pinned bounce buffers for uploads from pageable host memory (upload_pieces), per staging slot
+    size_t pin_up_cap[2] = {0, 0};
     bool region_attr_set = false, d1_attr_set = false, d1w_attr_set = false, zd_attr_set = false, gen_attr_set = false;   // per context = per device
     DevBuf ztables;                      // fmz::Tables (constant decode tables), uploaded once
     // optional per-kernel timing (fourmc_timing_enable): CUDA event pairs around every launch
@@ -693,6 +696,7 @@ void fourmc_ctx_destroy(fourmc_ctx *ctx)
     release(ctx->ztables);
     for (auto e : ctx->tev) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (void *q : ctx->pin_up) if (q) cudaFreeHost(q);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1661,6 +1665,72 @@ __global__ void find_eol_kernel(const uint8_t *p, unsigned long long n, unsigned
 // .4mc / .4mz file in host memory -- when start != 0 the first (partial) line is skipped, and the line that is
 // being read when the position passes the split end is finished from the following block(s).  The split's
 // blocks are decoded on the device in one batch; the two line boundaries are found there too.
+// Host -> device for a list of pieces.  Pinned sources go straight to the copy engine.  Pageable ones (a file read
+// into ordinary memory, a Java byte array) would pass through the driver's own bounce buffer at the speed of ONE
+// copying thread (r02k: 7 GB/s, the whole of a split read's time); here FOURMC_COPY_THREADS (default 4) threads move
+// 1 MiB chunks into a pinned buffer of the context and queue each chunk's transfer as soon as it is there.
+struct UpPiece { size_t dev_off; const uint8_t *src; size_t len; };
+static int upload_pieces(fourmc_ctx *ctx, cudaStream_t st, uint8_t *dev, const std::vector<UpPiece> &pieces, const int slot)
+{
+    if (pieces.empty()) return FOURMC_OK;
+    size_t total = 0;
+    for (const UpPiece &q : pieces) total += q.len;
+    cudaPointerAttributes at;
+    bool is_pinned = false;
+    if (cudaPointerGetAttributes(&at, pieces[0].src) == cudaSuccess) is_pinned = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+    else (void)cudaGetLastError();
+    static int n_threads = -1;
+    if (n_threads < 0) {
+        const char *e = getenv("FOURMC_COPY_THREADS");
+        n_threads = e ? atoi(e) : 4;
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && n_threads > hw) n_threads = hw;
+        if (n_threads > 16) n_threads = 16;
+    }
+    if (is_pinned || n_threads <= 0 || total < ((size_t)4 << 20)) {
+        for (const UpPiece &q : pieces) if (q.len) CK(cudaMemcpyAsync(dev + q.dev_off, q.src, q.len, cudaMemcpyHostToDevice, st));
+        return FOURMC_OK;
+    }
+    if (ctx->pin_up_cap[slot] < total) {
+        if (ctx->pin_up[slot]) { cudaFreeHost(ctx->pin_up[slot]); ctx->pin_up[slot] = nullptr; ctx->pin_up_cap[slot] = 0; }
+        const size_t cap = total + total / 8 + ((size_t)1 << 20);
+        CK(cudaMallocHost(&ctx->pin_up[slot], cap));
+        ctx->pin_up_cap[slot] = cap;
+    }
+    struct Chunk { size_t dev_off, pin_off; const uint8_t *src; size_t len; };
+    std::vector<Chunk> chunks;
+    size_t pin_off = 0;
+    constexpr size_t CH = (size_t)1 << 20;
+    for (const UpPiece &q : pieces)
+        for (size_t o = 0; o < q.len; o += CH) {
+            const size_t l = std::min(CH, q.len - o);
+            chunks.push_back(Chunk{q.dev_off + o, pin_off, q.src + o, l});
+            pin_off += l;
+        }
+    std::atomic<size_t> next{0};
+    std::atomic<int> err{(int)cudaSuccess};
+    uint8_t *pin = (uint8_t *)ctx->pin_up[slot];
+    auto work = [&]() {
+        cudaSetDevice(ctx->device);
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= chunks.size()) break;
+            const Chunk &c = chunks[i];
+            memcpy(pin + c.pin_off, c.src, c.len);
+            const cudaError_t e = cudaMemcpyAsync(dev + c.dev_off, pin + c.pin_off, c.len, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) { err.store((int)e); break; }
+        }
+    };
+    std::vector<std::thread> th;
+    const int nt = (int)std::min<size_t>((size_t)n_threads, chunks.size());
+    for (int t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (std::thread &t : th) t.join();
+    if (err.load() != (int)cudaSuccess) return fail(ctx, FOURMC_E_CUDA, "upload", (cudaError_t)err.load());
+    return FOURMC_OK;
+}
+
+
 static long long read_split_impl(fourmc_ctx *ctx, const void *file, size_t file_size, int64_t start, int64_t length,
                                  void *out, size_t out_capacity, const int slot)
 {
@@ -1726,7 +1796,9 @@ static long long read_split_impl(fourmc_ctx *ctx, const void *file, size_t file_
             if ((int)i < b1 - b0) u_split = dpos;                  // decoded bytes of the split's own blocks
         }
         uint8_t *d_tb = (uint8_t *)ws.tables.p;
-        CK(cudaMemcpyAsync(ctx->stage_in[slot].p, f + src0, (size_t)(src1 - src0), cudaMemcpyHostToDevice, st));
+        const std::vector<UpPiece> up{UpPiece{0, f + src0, (size_t)(src1 - src0)}};
+        r = upload_pieces(ctx, st, (uint8_t *)ctx->stage_in[slot].p, up, slot);
+        if (r) return r;
         CK(cudaMemcpyAsync(d_tb, ht.data(), ht.size(), cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));                             // ht is pageable host memory
         const uint64_t *d_so = (const uint64_t *)d_tb, *d_do = d_so + cnt;
@@ -1879,13 +1951,14 @@ long long fourmc_read_splits_lines_host(fourmc_ctx *ctx, const void *file, size_
         uint64_t *t_src = (uint64_t *)ht.data(), *t_dst = t_src + cnt;
         uint32_t *t_c = (uint32_t *)(t_dst + cnt), *t_u = t_c + cnt, *t_x = t_u + cnt;
         std::vector<EolJob> jobs((size_t)n_splits * 2, EolJob{0, 0, 0});
+        std::vector<UpPiece> up;
         for (int i = 0; i < n_splits; i++) {
             const Sp &q = sp[i];
             if (q.empty) continue;
             const HB &h0 = hb[q.first_item];
             const uint32_t k = (uint32_t)(q.t1 - q.b0);
             const uint64_t bytes = hb[q.first_item + k - 1].src + hb[q.first_item + k - 1].c - h0.src;
-            CK(cudaMemcpyAsync((uint8_t *)ctx->stage_in[0].p + q.in_off, f + h0.src, (size_t)bytes, cudaMemcpyHostToDevice, st));
+            up.push_back(UpPiece{(size_t)q.in_off, f + h0.src, (size_t)bytes});
             uint64_t dpos = q.out_off;
             for (uint32_t j = 0; j < k; j++) {
                 const HB &h = hb[q.first_item + j];
@@ -1898,6 +1971,7 @@ long long fourmc_read_splits_lines_host(fourmc_ctx *ctx, const void *file, size_
         }
         uint8_t *d_tb = (uint8_t *)ws.tables.p;
         CK(cudaMemcpyAsync(d_tb, ht.data(), ht.size(), cudaMemcpyHostToDevice, st));
+        if ((r = upload_pieces(ctx, st, (uint8_t *)ctx->stage_in[0].p, up, 0))) return r;
         const uint64_t *d_so = (const uint64_t *)d_tb, *d_do = d_so + cnt;
         const uint32_t *d_c = (const uint32_t *)(d_do + cnt), *d_u = d_c + cnt, *d_x = d_u + cnt;
         int32_t *d_osz = (int32_t *)(d_x + cnt);

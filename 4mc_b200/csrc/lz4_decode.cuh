@@ -69,9 +69,10 @@ constexpr int D1_HALF = 2048;             // bytes per ring half
 constexpr int D1_RING = 2 * D1_HALF;
 constexpr int D1_WARPS = 4;               // blocks per CTA
 constexpr int D1_SUB = 64;                // positions per lane per half (32 lanes x 64 = one half)
-constexpr int D1_X_STRIDE = D1_SUB + 2;                    // u16 exit table, 1 word of padding per sub-chunk
-constexpr int D1_S_STRIDE = D1_SUB + 2;                    // u16 output table, 1 word of padding per sub-chunk
-constexpr int D1_WARP_SMEM = D1_RING + 32 * D1_X_STRIDE * 2 + 32 * D1_S_STRIDE * 2 + 32 * 4 + 32 * 2;
+constexpr int D1_XS_STRIDE = D1_SUB + 1;                   // exit table: one word per position (bytes produced << 16 |
+                                                           // exit), one word of padding per sub-chunk: both halves of
+                                                           // an entry come with ONE scattered load
+constexpr int D1_WARP_SMEM = D1_RING + 32 * D1_XS_STRIDE * 4 + 32 * 4 + 32 * 2;
 constexpr int D1_SMEM = D1_WARPS * ((D1_WARP_SMEM + 15) & ~15);
 constexpr int D1_SPECIAL = 0x8000;         // exit-table flag: the chain stops at a token with a long continued length
 constexpr int D1_NONE = 0xffff;
@@ -122,14 +123,13 @@ __device__ __forceinline__ SeqDec d1_decode_slow(const RingReader &rd, int ip, i
 // a sequence without continued lengths is 3 + lit bytes long and produces lit + ml + 4 bytes; a length continued by
 // ONE byte is folded in (literal runs of 15+ and matches of 19+ are common); longer continuations stop the fold
 // (D1_SPECIAL: the chain walk decodes that sequence byte by byte).
-__device__ __forceinline__ void d1_fold(const uint8_t *ring, uint16_t *X, uint16_t *S, const int base_q, const int lane)
+__device__ __forceinline__ void d1_fold(const uint8_t *ring, uint32_t *XS, const int base_q, const int lane)
 {
     const uint4 *mine = (const uint4 *)(ring + ((base_q + lane * D1_SUB) & (D1_RING - 1)));
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 4; i++) { const uint4 v = mine[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
-    uint16_t *xm = X + lane * D1_X_STRIDE;
-    uint16_t *sm = S + lane * D1_S_STRIDE;
+    uint32_t *xs = XS + lane * D1_XS_STRIDE;
     const int sub_q = base_q + lane * D1_SUB;
 #pragma unroll
     for (int jj = D1_SUB - 1; jj >= 0; jj--) {
@@ -148,12 +148,11 @@ __device__ __forceinline__ void d1_fold(const uint8_t *ring, uint16_t *X, uint16
             special = x == 255;
             ml += (int)x; n++;
         }
-        int ex, os = lit + ml + 4;
-        if (special) { ex = jj | D1_SPECIAL; os = 0; }
-        else if (n < D1_SUB) { ex = (int)xm[n]; os += (int)sm[n]; }
-        else ex = n;
-        xm[jj] = (uint16_t)ex;
-        sm[jj] = (uint16_t)os;
+        // (bytes produced << 16) | exit: at most 21 sequences of at most 544 bytes each fit the upper half
+        uint32_t e = ((uint32_t)(lit + ml + 4) << 16) | (uint32_t)n;
+        if (special) e = (uint32_t)(jj | D1_SPECIAL);
+        else if (n < D1_SUB) e = xs[n] + ((uint32_t)(lit + ml + 4) << 16);
+        xs[jj] = e;
     }
 }
 
@@ -239,9 +238,8 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
     if (bd.stored) { if (lane == 0) result[b] = (int32_t)bd.usize; return; }
 
     uint8_t *ring = d1_smem + (size_t)warp * ((D1_WARP_SMEM + 15) & ~15);
-    uint16_t *X = (uint16_t *)(ring + D1_RING);                    // [32][D1_X_STRIDE] exit of the sub-chunk from each entry
-    uint16_t *S = X + 32 * D1_X_STRIDE;                            // [32][D1_S_STRIDE] bytes produced on the way
-    uint32_t *s_op = (uint32_t *)(S + 32 * D1_S_STRIDE);           // per sub-chunk: op at its entry
+    uint32_t *XS = (uint32_t *)(ring + D1_RING);                   // [32][D1_XS_STRIDE] from each entry: bytes produced << 16 | exit
+    uint32_t *s_op = XS + 32 * D1_XS_STRIDE;                       // per sub-chunk: op at its entry
     uint16_t *s_entry = (uint16_t *)(s_op + 32);                   // per sub-chunk: entry position
 
     const uintptr_t a = (uintptr_t)bd.src;
@@ -293,7 +291,7 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
             rd.lo = base_q - d; rd.span = min(base_q + D1_RING - d, csize) - rd.lo;
 
             // ---- B: exit function of my 64-position sub-chunk, back to front
-            d1_fold(ring, X, S, base_q, lane);
+            d1_fold(ring, XS, base_q, lane);
             s_entry[lane] = (uint16_t)D1_NONE;
             __syncwarp();
             // ---- C: lane 0 hops sub-chunk to sub-chunk along the real chain
@@ -303,8 +301,9 @@ lz4_parse_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokmap, u
                 while (e < D1_HALF) {
                     const int sc = e >> 6, jj = e & (D1_SUB - 1);
                     if (sc != last_sc) { s_entry[sc] = (uint16_t)e; s_op[sc] = (uint32_t)op; last_sc = sc; }
-                    const int x = (int)X[sc * D1_X_STRIDE + jj];
-                    op += (int)S[sc * D1_S_STRIDE + jj];
+                    const uint32_t xs = XS[sc * D1_XS_STRIDE + jj];
+                    const int x = (int)(xs & 0xffffu);
+                    op += (int)(xs >> 16);
                     if (x & D1_SPECIAL) {
                         const SeqDec sd = d1_decode_slow(rd, base_q + sc * D1_SUB + (x & (D1_SUB - 1)) - d, clean_ip);   // flag | position 0..63
                         if (!sd.clean) break;             // phase D finds it too and ends the bulk phase
@@ -427,9 +426,8 @@ lz4_parse_wide_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokm
 
     D1WCtl *ctl = (D1WCtl *)(d1w_smem + (size_t)(D1W_WORKERS + 1) * D1W_SLOT);
     uint8_t *ring = d1w_smem + (size_t)warp * D1W_SLOT;             // this warp's slot
-    uint16_t *X = (uint16_t *)(ring + D1_RING);
-    uint16_t *S = X + 32 * D1_X_STRIDE;
-    uint32_t *s_op = (uint32_t *)(S + 32 * D1_S_STRIDE);
+    uint32_t *XS = (uint32_t *)(ring + D1_RING);
+    uint32_t *s_op = XS + 32 * D1_XS_STRIDE;
     uint16_t *s_entry = (uint16_t *)(s_op + 32);
 
     const uintptr_t a = (uintptr_t)bd.src;
@@ -478,7 +476,7 @@ lz4_parse_wide_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokm
             load_half(h); store_half(h);
             load_half(h + 1); store_half(h + 1);
             __syncwarp();
-            d1_fold(ring, X, S, base_q, lane);
+            d1_fold(ring, XS, base_q, lane);
             s_entry[lane] = (uint16_t)D1_NONE;
             __syncwarp();
             __threadfence_block();
@@ -522,9 +520,8 @@ lz4_parse_wide_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokm
             if (h > *stop_h) break;
             const int me = h % D1W_WORKERS;
             uint8_t *wring = d1w_smem + (size_t)(me + 1) * D1W_SLOT;
-            const uint16_t *wX = (const uint16_t *)(wring + D1_RING);
-            const uint16_t *wS = wX + 32 * D1_X_STRIDE;
-            uint32_t *w_op = (uint32_t *)(wS + 32 * D1_S_STRIDE);
+            uint32_t *wXS = (uint32_t *)(wring + D1_RING);
+            uint32_t *w_op = wXS + 32 * D1_XS_STRIDE;
             uint16_t *w_entry = (uint16_t *)(w_op + 32);
             bool go = true;
             while (ctl->b_ready[me] != h) {
@@ -543,8 +540,9 @@ lz4_parse_wide_kernel(const BlockDesc *blocks, uint32_t n_blocks, uint32_t *tokm
                 while (e < D1_HALF) {
                     const int sc = e >> 6, jj = e & (D1_SUB - 1);
                     if (sc != last_sc) { w_entry[sc] = (uint16_t)e; w_op[sc] = (uint32_t)op; last_sc = sc; }
-                    const int x = (int)wX[sc * D1_X_STRIDE + jj];
-                    op += (int)wS[sc * D1_S_STRIDE + jj];
+                    const uint32_t xs = wXS[sc * D1_XS_STRIDE + jj];
+                    const int x = (int)(xs & 0xffffu);
+                    op += (int)(xs >> 16);
                     if (x & D1_SPECIAL) {
                         const SeqDec sd = d1_decode_slow(rd, base_q + sc * D1_SUB + (x & (D1_SUB - 1)) - d, clean_ip);
                         if (!sd.clean) { e = 0x40000000; break; }      // phase D finds it and reports; nothing clean follows

@@ -346,7 +346,11 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
                         const int p = p0 + b;
                         const uint32_t v = __funnelshift_r(w_lo, w_hi, (p & 3) * 8);
                         const int c = (int)table[enc_hash(v)];
-                        if (c < p && smem_read4(data32, c) == v) m |= 1ull << b;
+                        // filter on the ONE word that holds the candidate's first byte (4 - (c & 3) of the four
+                        // bytes): half the scattered loads of a full compare; pass 2 checks the rest
+                        const uint32_t cw = data32[c >> 2];
+                        const int cs = (c & 3) * 8;
+                        if (c < p && ((((cw >> cs) ^ v) << cs) == 0)) m |= 1ull << b;
                         if ((p & 3) == 3) { w_lo = w_hi; w_hi = data32[(p >> 2) + 2]; }
                     }
                     cand[g] = m;
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
                 if (nxt < 0) break;
                 p = ss + nxt;
                 const int c = (int)table[enc_hash(smem_read4(data32, p))];
-                int len = 4;
+                int len = (c & 3) ? 0 : 4;                    // pass 1 compared all four bytes only for aligned candidates
                 const int maxlen = match_limit - p;
                 while (len < maxlen) {
                     const uint32_t x = smem_read4(data32, p + len) ^ smem_read4(data32, c + len);
@@ -375,6 +379,7 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
                     len += 4;
                 }
                 len = min(len, maxlen);
+                if (len < 4) { p++; continue; }                // the filter let a partial match through
                 int st = p, m = c;
                 while (st > anchor && m > 0 && data[st - 1] == data[m - 1]) { st--; m--; len++; }
                 if (len >= P.min_match) {
