@@ -564,8 +564,16 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             }
             const uint32_t *tm = (const uint32_t *)ws.tokmap.p, *co = (const uint32_t *)ws.chunkop.p;
             const int32_t *rs = (const int32_t *)ws.result.p;
-#define D2_LAUNCH(WW) KL("lz4_copy_kernel", st, lz4_copy_kernel<WW><<<nb, WW * 32, 0, st>>>(desc, tm, co, rs))
-            if (w == 1) D2_LAUNCH(1); else if (w == 2) D2_LAUNCH(2); else if (w == 4) D2_LAUNCH(4); else D2_LAUNCH(8);
+            static int prewait = -1;
+            if (prewait < 0) { const char *e = getenv("FOURMC_D2_PREWAIT"); prewait = e ? atoi(e) : 0; }
+#define D2_LAUNCH(WW) KL("lz4_copy_kernel", st, lz4_copy_kernel<WW><<<nb, WW * 32, 0, st>>>(desc, tm, co, rs, prewait))
+            static int d2_var = -1;
+            if (d2_var < 0) { const char *e = getenv("FOURMC_D2_VAR"); d2_var = e ? atoi(e) : 4; }
+#define D2_VAR(VV) KL("lz4_copy_kernel", st, (lz4_copy_kernel<1, VV><<<nb, 32, 0, st>>>(desc, tm, co, rs, prewait)))
+            if (w == 1 && d2_var == 8) D2_VAR(8);
+            else if (w == 1 && d2_var == 1) D2_VAR(0);
+#undef D2_VAR
+            else if (w == 1) D2_LAUNCH(1); else if (w == 2) D2_LAUNCH(2); else if (w == 4) D2_LAUNCH(4); else D2_LAUNCH(8);
 #undef D2_LAUNCH
         }
     }

@@ -652,13 +652,17 @@ __device__ __forceinline__ void smem_copy_seq(uint8_t *dst, const uint8_t *src, 
 }
 
 constexpr int LZ4_SPAN = 2048;            // output bytes a warp assembles in shared memory at once
-constexpr int LZ4_SCR = 80;               // scratch bytes per lane (64 used; 80 keeps 128-bit stores conflict-free)
+constexpr int LZ4_SCR = 80;               // scratch bytes per lane (80 keeps 128-bit stores conflict-free)
+constexpr int LZ4_MAC_CHUNKS = 8;         // 128-byte chunks per D2 work item when a warp has a block to itself: 1 KiB,
+                                          // 32 tokmap words, one per lane
+constexpr int LZ4_MAC_TOK = 352;          // > ceil(1024 / 3): a sequence is at least 3 bytes
+constexpr int LZ4_WMATCH = 32;            // and matches up to this long (three aligned 16-byte loads cover them)
 
 // Shared memory of one copy warp / of the W warps that share a block.
 struct CopyWarpSmem {
     __align__(16) uint8_t span[LZ4_SPAN + 32];
-    __align__(16) uint8_t scr[32 * LZ4_SCR];      // per lane: 4 aligned 16-byte chunks of a match source
-    uint8_t tokpos[64];
+    __align__(16) uint8_t scr[32 * LZ4_SCR + 16]; // per lane: 16 bytes of slack + the aligned 16-byte chunks of a match source
+    uint16_t tokpos[LZ4_MAC_TOK];                 // token positions of the work item, in stream order
 };
 template <int W>
 struct CopyBlockSmem {
@@ -667,20 +671,51 @@ struct CopyBlockSmem {
 };
 
 // The copy of one block by W warps (`warp` = 0 .. W-1 within the block).
-template <int W>
+//
+// Work item = C 128-byte chunks of the compressed stream (4 C tokmap words, one per lane): its tokens are listed in
+// shared memory and taken 32 at a time, one sequence per lane.  C = 8 when the warp has the block to itself: full
+// batches whatever the sequences' sizes (a 128-byte chunk of the log text holds 20), a span of ~420 B.  C = 1 when W
+// warps share a block: an item's matches mostly point a few KiB back, i.e. into the items of the sibling warps, so
+// the window in flight (W items) must stay small (r02n: 1 KiB items with 8 warps, 8.4 -> 19 ms for 64 blocks).
+// A batch's output span is assembled in shared memory and flushed with 128-bit stores.
+//
+// Assembly.  99 % of the sequences are a literal run of at most LZ4_WLIT bytes and a match of at most LZ4_WMATCH bytes
+// whose source lies wholly before the span.  Such a lane builds its sequence's bytes as aligned 32-bit WORDS of the
+// span: literal words from aligned words of the stream, match words from the aligned 16-byte chunks of the source
+// (HBM / L2 -> registers -> the lane's scratch slot), both through a funnel shift, bytes outside the sequence zeroed.
+// Only a lane's first and last word can be shared with a neighbour (a sequence is at least 4 bytes): the LEFT lane
+// stores the shared word, OR-ing in the right lane's half that it gets by shuffle.  No byte stores, no read-modify-write.
+// Everything else is patched in afterwards with byte stores, which disturb nobody: long literal runs (whole warp per
+// run), and "slow" matches -- a source inside the span (0.7 % on text: resolved in rounds, lowest destination first),
+// offset 0 (zeros, lz4.c:2300-2303), long matches, and (W > 1) a source the sibling warps have not delivered yet.
+// A lane with a slow match takes no part in the word stage at all.
+// V: experiment switches (bit 0: tokens fetched one batch ahead; bit 1: match loads issued before the literal
+// words; bits 2-3: literal words 0 = three unrolled (runs up to 8 bytes), 1 = a loop (up to 64), 2 = five unrolled (up to 16))
+template <int W, int C, int V>
 __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32_t *tokmap, const uint32_t *chunk_op,
-                                               const int warp, const int lane, CopyBlockSmem<W> *bs, CopyWarpSmem *ws)
+                                               const int warp, const int lane, CopyBlockSmem<W> *bs, CopyWarpSmem *ws,
+                                               const int prewait)
 {
     const uint8_t *__restrict__ src = bd.src;
     uint8_t *out = bd.dst;
     const int csize = (int)bd.csize;
     const int dq = (int)((uintptr_t)bd.src & 15);     // D1 records tokens at aligned positions ip + dq
     const int nchunks = (dq + csize + LZ4_CHUNK - 1) / LZ4_CHUNK;
-    const uint4 *maps = (const uint4 *)(tokmap + (size_t)bd.chunk_base * LZ4_CHUNK_WORDS);
+    const int nmac = (nchunks + C - 1) / C;
+    const int nwords = nchunks * LZ4_CHUNK_WORDS;
+    const uint32_t *maps = tokmap + (size_t)bd.chunk_base * LZ4_CHUNK_WORDS;
     const uint32_t *cops = chunk_op + bd.chunk_base;
+    // literal words are fetched as the aligned words around their bytes: never outside the payload's own words
+    const uint32_t *src_w_lo = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
+    const int src_w_last = (int)((((uintptr_t)(src + (csize > 0 ? csize - 1 : 0)) & ~(uintptr_t)3) - (uintptr_t)src_w_lo) >> 2);
+    constexpr bool PF = (V & 1) != 0, EARLY = (V & 2) != 0;
+    constexpr int LITM = (V >> 2) & 3;
+    constexpr int LZ4_WLIT = LITM == 1 ? 64 : LITM == 2 ? 16 : 8;   // literal runs up to this long travel as words with their sequence
+    constexpr int NLW = (3 + LZ4_WLIT + 3) / 4;                     // words such a run can touch
     volatile int *owed = bs->owed;
     uint8_t *span = ws->span;
-    uint8_t *s_tokpos_w = ws->tokpos;
+    uint32_t *span32 = (uint32_t *)ws->span;
+    uint16_t *s_tokpos_w = ws->tokpos;
     uint8_t *s_scr_w = ws->scr;
 
     // lowest output position any warp of this block still owes
@@ -697,10 +732,9 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
         if (lane == 0) owed[warp] = pos;
     };
 
-    // Chunks are taken one AHEAD: while chunk k is copied, the token bits and the output position of the chunk
-    // this warp takes next are already on their way, and the two lines of compressed bytes it will read are
-    // being pulled into L1 -- a warp's chunks are a dependent chain (bits -> tokens -> offsets -> match bytes),
-    // so every load taken off that chain shortens the block's time.
+    // Work items are taken one AHEAD: while item k is copied, the token bits and the output position of the item
+    // this warp takes next are already on their way, and the lines of compressed bytes it will read are being
+    // pulled into L1.
     int kseq = 0;
     auto take = [&]() -> int {
         int t = 0;
@@ -711,42 +745,48 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
         }
         return t;
     };
-    uint4 m_n = make_uint4(0u, 0u, 0u, 0u);
-    int op_n = 0;
+    uint32_t w_n = 0, co_n = 0;
     auto fetch = [&](int kk) {
-        if (kk >= nchunks) return;
-        m_n = maps[kk]; op_n = (int)cops[kk];
-        const int at = kk * LZ4_CHUNK - dq + lane * 128;
-        if (lane < 2 && at >= 0 && at < csize) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + at));
+        if (kk >= nmac) return;
+        const int wi = kk * (C * LZ4_CHUNK_WORDS) + lane;
+        w_n = (lane < C * LZ4_CHUNK_WORDS && wi < nwords) ? maps[wi] : 0u;
+        const int ci = kk * C + (lane & (C - 1));
+        co_n = ci < nchunks ? cops[ci] : 0u;
+        const int at = max(kk * (C * LZ4_CHUNK) - dq + lane * 128, 0);
+        if (lane < C + 1 && at < csize) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + at));
     };
     int kn = take();
     fetch(kn);
     for (;;) {
         const int k = kn;
-        if (k >= nchunks) break;
-        const uint4 m = m_n;
-        int op0 = op_n;
+        if (k >= nmac) break;
+        uint32_t word = w_n;
+        const uint32_t co = co_n;
         kn = take();
         fetch(kn);
-        const int c0 = __popc(m.x), c1 = c0 + __popc(m.y), c2 = c1 + __popc(m.z), ntok = c2 + __popc(m.w);
+        const int cnt = __popc(word);
+        const int incl_c = warp_incl_scan_add(cnt);
+        const int ntok = min(__shfl_sync(FM_FULL, incl_c, 31), LZ4_MAC_TOK);
         if (ntok == 0) continue;
-
-        // lane r takes the r-th token of the chunk: scatter positions by rank
-        {
-            const uint32_t lt = (1u << lane) - 1u;
-            if ((m.x >> lane) & 1u) s_tokpos_w[__popc(m.x & lt)] = (uint8_t)lane;
-            if ((m.y >> lane) & 1u) s_tokpos_w[c0 + __popc(m.y & lt)] = (uint8_t)(32 + lane);
-            if ((m.z >> lane) & 1u) s_tokpos_w[c1 + __popc(m.z & lt)] = (uint8_t)(64 + lane);
-            if ((m.w >> lane) & 1u) s_tokpos_w[c2 + __popc(m.w & lt)] = (uint8_t)(96 + lane);
-        }
+        // output position of the item's first sequence: D1 left it with the first 128-byte chunk that holds a token
+        int op0 = (int)__shfl_sync(FM_FULL, co, (__ffs(__ballot_sync(FM_FULL, cnt > 0)) - 1) >> 2);
+        for (int base = incl_c - cnt; word; word &= word - 1, base++)
+            if (base < LZ4_MAC_TOK) s_tokpos_w[base] = (uint16_t)(lane * 32 + __ffs(word) - 1);
         __syncwarp();
+        const int ip_base = k * (C * LZ4_CHUNK) - dq;
+        // tokens are fetched one batch ahead
+        int ip_nx = 0;
+        unsigned tok_nx = 0;
+        if (PF && lane < ntok) { ip_nx = ip_base + (int)s_tokpos_w[lane]; tok_nx = src[ip_nx]; }
 
         for (int batch = 0; batch < ntok; batch += 32) {
             const bool active = batch + lane < ntok;
             int lit = 0, ml = 0, off = 0, lit_src = 0;
+            int ip = ip_nx + 1;
+            unsigned tok = tok_nx;
+            if (PF) { if (batch + 32 + lane < ntok) { ip_nx = ip_base + (int)s_tokpos_w[batch + 32 + lane]; tok_nx = src[ip_nx]; } }
+            else if (active) { ip = ip_base + (int)s_tokpos_w[batch + lane]; tok = src[ip++]; }
             if (active) {
-                int ip = k * LZ4_CHUNK + (int)s_tokpos_w[batch + lane] - dq;
-                const unsigned tok = src[ip++];
                 lit = (int)(tok >> 4);
                 if (lit == 15) { unsigned s; do { s = src[ip++]; lit += (int)s; } while (s == 255); }
                 lit_src = ip;
@@ -770,64 +810,207 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
                 const int shift = (int)((uintptr_t)(out + op0) & 15);   // equal 16-byte phases in smem and HBM
                 uint8_t *sp = span + shift - op0;     // sp[x] holds output byte x
                 publish(op0);                         // nothing below op0 is owed by this warp
-                // literals
-                if (active && lit < LZ4_LONG) copy_batched(sp + my_op, src + lit_src, lit);
-                for (unsigned lm = __ballot_sync(FM_FULL, active && lit >= LZ4_LONG); lm; lm &= lm - 1) {
+
+                // which bytes of my sequence travel as words: [rs, re)
+                // (W > 1) a source the sibling warps still owe makes a slow match: it waits there, alone -- after a short
+                // wait here, for all: a source that arrives in time saves its lane the slow way
+                if (W > 1 && prewait > 0) {
+                    const int need = warp_max((ml > 0 && off != 0 && mstart + ml <= op0 && ml <= LZ4_WMATCH) ? mstart + ml : 0);
+                    for (int spin = 0; spin < prewait && high_water() < need; spin++) __nanosleep(40);
+                }
+                const int hwm0 = high_water();
+                if (W > 1) __threadfence_block();
+                const bool fastm = ml > 0 && off != 0 && mstart + ml <= min(op0, hwm0) && ml <= LZ4_WMATCH;
+                const bool slowm = ml > 0 && !fastm;
+                // literal words are the aligned words of the stream around the run: all of them inside the payload's own words
+                const uint32_t la = (uint32_t)(shift + (my_op - op0));
+                const int dd = (int)(la & 3u);
+                const int nwl = (dd + lit + 3) >> 2;
+                const uintptr_t sb = (uintptr_t)(src + lit_src) - (uintptr_t)dd;      // the stream byte under byte 0 of word 0
+                const int wo = (int)(((intptr_t)(sb & ~(uintptr_t)3) - (intptr_t)(uintptr_t)src_w_lo) >> 2);
+                const bool lit_words = lit <= LZ4_WLIT && wo >= 0 && wo + nwl <= src_w_last;
+                int rs = my_op, re = my_op + outlen;
+                if (slowm) re = rs;
+                else if (!lit_words) rs = d;
+                if (re - rs < 4) { rs = my_op; re = my_op; }          // a word must not be shared by three lanes
+                const bool in = re > rs;
+                const bool lit_in = in && rs == my_op && lit > 0;
+                const bool m_in = in && ml > 0;
+                const bool lit_later = lit > 0 && !lit_in;
+
+                // is my first word the left neighbour's last word?  (the same test, seen from the other side, below)
+                const int p_re = __shfl_up_sync(FM_FULL, in ? re : -1, 1);
+                const bool head_skip = in && lane > 0 && p_re == rs && ((shift + rs - op0) & 3) != 0;
+                // match sources: the aligned 16-byte chunks around them
+                const int so = (int)((uintptr_t)(out + mstart) & 15);
+                const int nch = (so + ml + 15) >> 4;                  // 1..3 when m_in
+                uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
+                if (EARLY && m_in) {
+                    const uint4 *gb = (const uint4 *)(out + mstart - so);
+                    q0 = ldg_v4(gb);
+                    if (nch > 1) q1 = ldg_v4(gb + 1);
+                    if (nch > 2) q2 = ldg_v4(gb + 2);
+                }
+                // literal words: aligned words of the stream through a funnel shift, bytes outside the run zeroed
+                uint32_t l0 = 0, llast = 0;
+                const uint32_t lwi = la >> 2;
+                if (lit_in) {
+                    const int nb = dd + lit;
+                    const int sh = (int)(sb & 3) * 8;
+                    const uint32_t *sw = src_w_lo + wo;
+                    const uint32_t tmask = 0xffffffffu >> (8 * (4 * nwl - nb));
+                    if (LITM == 1) {
+                        // word j is built, word j - 1 stored
+                        uint32_t lo = sw[1];
+                        uint32_t cur = __funnelshift_r(sw[0], lo, sh) & (0xffffffffu << (8 * dd));
+                        if (nwl == 1) cur &= tmask;
+                        l0 = cur;
+                        for (int j = 1; j < nwl; j++) {
+                            const uint32_t hi = sw[j + 1];
+                            uint32_t v = __funnelshift_r(lo, hi, sh);
+                            lo = hi;
+                            if (j == nwl - 1) v &= tmask;
+                            if (!(j == 1 && head_skip)) span32[lwi + j - 1] = cur;
+                            cur = v;
+                        }
+                        llast = cur;
+                    } else {
+                        // scalars, not arrays: the compiler turns "if (i == nwl - 1) w[i] ..." into a local-memory array
+                        auto tm = [&](int x) -> uint32_t { return __funnelshift_rc(0xffffffffu, 0u, max(32 - 8 * x, 0)); };  // the low x bytes (x <= 0: none)
+                        const uint32_t a0 = sw[0], a1 = sw[1];
+                        const uint32_t a2 = nwl >= 2 ? sw[2] : 0u, a3 = nwl >= 3 ? sw[3] : 0u;
+                        const uint32_t w0 = __funnelshift_r(a0, a1, sh) & (0xffffffffu << (8 * dd)) & tm(nb);
+                        const uint32_t w1 = __funnelshift_r(a1, a2, sh) & tm(nb - 4);
+                        const uint32_t w2 = __funnelshift_r(a2, a3, sh) & tm(nb - 8);
+                        l0 = w0;
+                        // all but the last word now: that one may be shared with my match, or be my last word
+                        if (nwl > 1 && !head_skip) span32[lwi] = w0;
+                        if (nwl > 2) span32[lwi + 1] = w1;
+                        llast = nwl <= 1 ? w0 : nwl == 2 ? w1 : w2;
+                        if constexpr (NLW > 3) {
+                            const uint32_t a4 = nwl >= 4 ? sw[4] : 0u, a5 = nwl >= 5 ? sw[5] : 0u;
+                            const uint32_t w3 = __funnelshift_r(a3, a4, sh) & tm(nb - 12);
+                            const uint32_t w4 = __funnelshift_r(a4, a5, sh) & tm(nb - 16);
+                            if (nwl > 3) span32[lwi + 2] = w2;
+                            if (nwl > 4) span32[lwi + 3] = w3;
+                            if (nwl == 4) llast = w3;
+                            if (nwl >= 5) llast = w4;
+                        }
+                    }
+                }
+                // first match word
+                uint32_t mcur = 0, mlo = 0, mwi = 0, m_tmask = 0xffffffffu;
+                const uint32_t *msw = (const uint32_t *)s_scr_w;
+                int nwm = 0, msh = 0;
+                if (m_in) {
+                    if (!EARLY) {
+                        const uint4 *gb = (const uint4 *)(out + mstart - so);
+                        q0 = ldg_v4(gb);
+                        if (nch > 1) q1 = ldg_v4(gb + 1);
+                        if (nch > 2) q2 = ldg_v4(gb + 2);
+                    }
+                    uint4 *scr = (uint4 *)(s_scr_w + lane * LZ4_SCR + 16);
+                    scr[0] = q0; if (nch > 1) scr[1] = q1; if (nch > 2) scr[2] = q2;
+                    const uint32_t ma = (uint32_t)(shift + (d - op0));
+                    const int ddm = (int)(ma & 3u);
+                    const int nbm = ddm + ml;
+                    nwm = (nbm + 3) >> 2;
+                    const uint32_t sbo = (uint32_t)(lane * LZ4_SCR + 16 + so - ddm);  // scratch byte under byte 0 of word 0
+                    msh = (int)(sbo & 3u) * 8;
+                    msw = (const uint32_t *)(s_scr_w + (sbo & ~3u));
+                    const uint32_t b0 = msw[0];
+                    mlo = msw[1];
+                    mcur = __funnelshift_r(b0, mlo, msh) & (0xffffffffu << (8 * ddm));
+                    m_tmask = 0xffffffffu >> (8 * (4 * nwm - nbm));
+                    if (nwm == 1) mcur &= m_tmask;
+                    mwi = ma >> 2;
+                }
+                // the word where my literals end and my match begins holds both
+                const bool share = lit_in && m_in && mwi == lwi + (uint32_t)nwl - 1u;
+                if (share) mcur |= llast;
+                else if (lit_in && m_in && !(nwl == 1 && head_skip)) span32[lwi + nwl - 1] = llast;
+                const bool head_is_m = m_in && (!lit_in || (share && nwl == 1));
+                const uint32_t hv = head_is_m ? mcur : l0;            // my first word, complete
+                // match words: word j is built, word j - 1 stored
+                for (int j = 1; j < nwm; j++) {
+                    const uint32_t hi = msw[j + 1];
+                    uint32_t v = __funnelshift_r(mlo, hi, msh);
+                    mlo = hi;
+                    if (j == nwm - 1) v &= m_tmask;
+                    if (!(j == 1 && head_is_m && head_skip)) span32[mwi + j - 1] = mcur;
+                    mcur = v;
+                }
+                // my last word, with the right neighbour's first word folded in when they are the same word
+                {
+                    const uint32_t n_hv = __shfl_down_sync(FM_FULL, hv, 1);
+                    const int n_rs = __shfl_down_sync(FM_FULL, in ? rs : -1, 1);
+                    const bool adj = lane < 31 && n_rs == re && ((shift + re - op0) & 3) != 0;
+                    if (in) {
+                        const uint32_t tv = m_in ? mcur : llast;
+                        const uint32_t twi = m_in ? mwi + (uint32_t)nwm - 1u : lwi + (uint32_t)nwl - 1u;
+                        span32[twi] = tv | (adj ? n_hv : 0u);
+                    }
+                }
+                __syncwarp();
+                // ---- patches, all with byte stores ----
+                if (lit_later && lit <= LZ4_WLIT)                  // beside a slow match, or a closing run under 4 bytes
+                    copy_batched(sp + my_op, src + lit_src, lit);
+                for (unsigned lm = __ballot_sync(FM_FULL, lit > LZ4_WLIT); lm; lm &= lm - 1) {
                     const int l = __ffs(lm) - 1;
                     const int n = __shfl_sync(FM_FULL, lit, l), sp0 = __shfl_sync(FM_FULL, my_op, l);
                     const int ls = __shfl_sync(FM_FULL, lit_src, l);
                     for (int i = lane; i < n; i += 32) sp[sp0 + i] = src[ls + i];
                 }
-                // matches.  Bytes from before the span come from HBM once the block-wide mark has
-                // passed them; bytes inside the span come from shared memory once every earlier
-                // match of this warp that could overlap them is done (lowest destination first).
-                bool pending = ml > 0;
-                if (pending && off == 0) {            // lz4.c:2300-2303: offset 0 yields zeros
-                    for (int i = 0; i < ml; i++) sp[d + i] = 0;
-                    pending = false;
-                }
-                const int ext = (pending && mstart < op0) ? min(ml, op0 - mstart) : 0;
-                const int need_ext = ext ? mstart + ext : 0;
-                const int need_in = (ml > ext) ? min(mstart + ml, d) : 0;
-                __syncwarp();
-                int idle = 0;
-                for (;;) {
-                    const int low = warp_min(pending ? d : 0x7fffffff);
-                    if (low == 0x7fffffff) break;
-                    const int hwm = high_water();
-                    if (W > 1) __threadfence_block();
-                    const bool go = pending && need_ext <= hwm && need_in <= low;
-                    if (go) {
-                        if (ext > 0 && ext < LZ4_LONG) {
-                            // the source is somewhere in HBM/L2: fetch it with (at most four) aligned
-                            // 128-bit loads instead of one load per byte -- every load of a scattered
-                            // address costs the L1 data pipe a wavefront per lane
-                            const uint8_t *gs = out + mstart;
-                            const int so = (int)((uintptr_t)gs & 15);
-                            const uint4 *gb = (const uint4 *)(gs - so);
-                            const int nch = (so + ext + 15) >> 4;
-                            uint4 *scr = (uint4 *)(s_scr_w + lane * LZ4_SCR);
-                            const uint4 z = make_uint4(0, 0, 0, 0);
-                            const uint4 q0 = ldg_v4(gb), q1 = nch > 1 ? ldg_v4(gb + 1) : z;
-                            const uint4 q2 = nch > 2 ? ldg_v4(gb + 2) : z, q3 = nch > 3 ? ldg_v4(gb + 3) : z;
-                            scr[0] = q0; if (nch > 1) scr[1] = q1; if (nch > 2) scr[2] = q2; if (nch > 3) scr[3] = q3;
-                            copy_batched(sp + d, (const uint8_t *)scr + so, ext);
-                        }
-                        if (ml > ext && ext < LZ4_LONG) smem_copy_seq(sp + d + ext, sp + mstart + ext, ml - ext);
+                if (__any_sync(FM_FULL, slowm)) {
+                    // Bytes from before the span come from HBM once the block-wide mark has passed them; bytes inside
+                    // the span come from shared memory once every earlier slow match that could overlap them is done
+                    // (lowest destination first; everything that is not a slow match is complete by now).
+                    bool pending = slowm;
+                    if (pending && off == 0) {            // lz4.c:2300-2303: offset 0 yields zeros
+                        for (int i = 0; i < ml; i++) sp[d + i] = 0;
+                        pending = false;
                     }
-                    // long reads from HBM: the whole warp per match, then its in-span remainder
-                    for (unsigned lm = __ballot_sync(FM_FULL, go && ext >= LZ4_LONG); lm; lm &= lm - 1) {
-                        const int l = __ffs(lm) - 1;
-                        const int n = __shfl_sync(FM_FULL, ext, l), dd = __shfl_sync(FM_FULL, d, l);
-                        const int ms = __shfl_sync(FM_FULL, mstart, l), mm = __shfl_sync(FM_FULL, ml, l);
-                        for (int i = lane; i < n; i += 32) sp[dd + i] = out[ms + i];
-                        __syncwarp();
-                        if (lane == l && mm > n) smem_copy_seq(sp + dd + n, sp + ms + n, mm - n);
-                    }
-                    const bool any = __any_sync(FM_FULL, go);
-                    if (go) pending = false;
+                    const int ext = (pending && mstart < op0) ? min(ml, op0 - mstart) : 0;
+                    const int need_ext = ext ? mstart + ext : 0;
+                    const int need_in = (ml > ext) ? min(mstart + ml, d) : 0;
                     __syncwarp();
-                    if (!any) { if (++idle > 2) __nanosleep(idle > 16 ? 256 : 32); } else idle = 0;
+                    int idle = 0;
+                    for (;;) {
+                        const int low = warp_min(pending ? d : 0x7fffffff);
+                        if (low == 0x7fffffff) break;
+                        const int hwm = high_water();
+                        if (W > 1) __threadfence_block();
+                        const bool go = pending && need_ext <= hwm && need_in <= low;
+                        if (go) {
+                            if (ext > 0 && ext < LZ4_LONG) {
+                                const uint8_t *gs = out + mstart;
+                                const int so2 = (int)((uintptr_t)gs & 15);
+                                const uint4 *gb = (const uint4 *)(gs - so2);
+                                const int nch = (so2 + ext + 15) >> 4;
+                                uint4 *scr = (uint4 *)(s_scr_w + lane * LZ4_SCR);
+                                const uint4 z = make_uint4(0, 0, 0, 0);
+                                const uint4 q0 = ldg_v4(gb), q1 = nch > 1 ? ldg_v4(gb + 1) : z;
+                                const uint4 q2 = nch > 2 ? ldg_v4(gb + 2) : z, q3 = nch > 3 ? ldg_v4(gb + 3) : z;
+                                scr[0] = q0; if (nch > 1) scr[1] = q1; if (nch > 2) scr[2] = q2; if (nch > 3) scr[3] = q3;
+                                const uint8_t *sc = (const uint8_t *)scr + so2;
+                                for (int i = 0; i < ext; i++) sp[d + i] = sc[i];
+                            }
+                            if (ml > ext && ext < LZ4_LONG) smem_copy_seq(sp + d + ext, sp + mstart + ext, ml - ext);
+                        }
+                        // long reads from HBM: the whole warp per match, then its in-span remainder
+                        for (unsigned lm = __ballot_sync(FM_FULL, go && ext >= LZ4_LONG); lm; lm &= lm - 1) {
+                            const int l = __ffs(lm) - 1;
+                            const int n = __shfl_sync(FM_FULL, ext, l), dd = __shfl_sync(FM_FULL, d, l);
+                            const int ms = __shfl_sync(FM_FULL, mstart, l), mm = __shfl_sync(FM_FULL, ml, l);
+                            for (int i = lane; i < n; i += 32) sp[dd + i] = out[ms + i];
+                            __syncwarp();
+                            if (lane == l && mm > n) smem_copy_seq(sp + dd + n, sp + ms + n, mm - n);
+                        }
+                        const bool any = __any_sync(FM_FULL, go);
+                        if (go) pending = false;
+                        __syncwarp();
+                        if (!any) { if (++idle > 2) __nanosleep(idle > 16 ? 256 : 32); } else idle = 0;
+                    }
                 }
                 __syncwarp();
                 // flush
@@ -882,7 +1065,7 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
                 if (!any) { if (++idle > 2) __nanosleep(idle > 16 ? 256 : 32); } else idle = 0;
             }
         }
-        __syncwarp();
+        __syncwarp();                                 // the token list is rewritten by the next work item
     }
     // a finished warp must not hold the mark down
     publish(0x7fffffff);
@@ -893,10 +1076,10 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
 // each (and then hardly ever wait on one another), few blocks need many.  More than 8 only wait for one another: a
 // chunk's matches mostly point into the last few KiB, i.e. into the chunks the sibling warps still work on
 // (r02i, one block: 8 warps 8.5 ms, 32 warps 12.5 ms).
-template <int W>
-__global__ void __launch_bounds__(W * 32)
+template <int W, int V = 4>
+__global__ void __launch_bounds__(W * 32, W == 1 ? ((V & 16) ? 32 : 28) : 1)
 lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t *chunk_op,
-                const int32_t *result)
+                const int32_t *result, const int prewait)
 {
     __shared__ CopyBlockSmem<W> s_block;
     __shared__ CopyWarpSmem s_warp[W];
@@ -905,7 +1088,7 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
     if (threadIdx.x < W) s_block.owed[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_block.ticket = 0;
     if (W > 1) __syncthreads();
-    lz4_copy_block<W>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, &s_block, &s_warp[threadIdx.x >> 5]);
+    lz4_copy_block<W, (W == 1 ? LZ4_MAC_CHUNKS : 1), V>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, &s_block, &s_warp[threadIdx.x >> 5], prewait);
 }
 
 // ---- D0 ------------------------------------------------------------------------------------
