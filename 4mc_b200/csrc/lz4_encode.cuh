@@ -336,24 +336,46 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
             // position with the same four bytes?  One bit per position (uniform work for all lanes).
             unsigned long long cand[3] = {0ull, 0ull, 0ull};
             {
-                const int stop = min(se, mf_limit + 1);
-                uint32_t w_lo = data32[ss >> 2], w_hi = data32[(ss >> 2) + 1];     // ss is word aligned
+                // One slice word per step = four positions with compile-time byte shifts (17 instructions per position
+                // instead of 37 for the position-by-position loop, r02 SASS); positions at or after `stop` are
+                // masked off at the end (their lookups read table entries and region bytes that exist).
+                const int stop_rel = min(se, mf_limit + 1) - ss;
+                const uint32_t *sw = data32 + (ss >> 2);                           // ss is word aligned
+                uint32_t w_lo = sw[0];
+                uint32_t half[5] = {0u, 0u, 0u, 0u, 0u};                           // 8 words = 32 positions each
+                auto probe = [&](const uint32_t v, const int p) -> bool {
+                    const int c = (int)table[enc_hash(v)];
+                    // filter on the ONE word that holds the candidate's first byte (4 - (c & 3) of the four
+                    // bytes): half the scattered loads of a full compare; pass 2 checks the rest
+                    const uint32_t cw = data32[c >> 2];
+                    const int cs = (c & 3) * 8;
+                    return c < p && ((((cw >> cs) ^ v) << cs) == 0);
+                };
+#pragma unroll
+                for (int h = 0; h < 5; h++) {
+                    const int nw = h < 4 ? 8 : 1;                                  // 33 words per slice
+                    uint32_t m = 0;
+                    for (int j = 0; j < nw; j++) {
+                        const int wi = h * 8 + j;
+                        const uint32_t w_hi = sw[wi + 1];
+                        const int p = ss + 4 * wi;
+                        uint32_t nib = 0;
+                        if (probe(w_lo, p)) nib |= 1u;
+                        if (probe(__funnelshift_r(w_lo, w_hi, 8), p + 1)) nib |= 2u;
+                        if (probe(__funnelshift_r(w_lo, w_hi, 16), p + 2)) nib |= 4u;
+                        if (probe(__funnelshift_r(w_lo, w_hi, 24), p + 3)) nib |= 8u;
+                        m |= nib << (4 * j);
+                        w_lo = w_hi;
+                    }
+                    half[h] = m;
+                }
+                cand[0] = (unsigned long long)half[0] | ((unsigned long long)half[1] << 32);
+                cand[1] = (unsigned long long)half[2] | ((unsigned long long)half[3] << 32);
+                cand[2] = (unsigned long long)half[4];
 #pragma unroll
                 for (int g = 0; g < 3; g++) {
-                    unsigned long long m = 0;
-                    const int p0 = ss + g * 64, cnt = min(64, stop - p0);
-                    for (int b = 0; b < cnt; b++) {
-                        const int p = p0 + b;
-                        const uint32_t v = __funnelshift_r(w_lo, w_hi, (p & 3) * 8);
-                        const int c = (int)table[enc_hash(v)];
-                        // filter on the ONE word that holds the candidate's first byte (4 - (c & 3) of the four
-                        // bytes): half the scattered loads of a full compare; pass 2 checks the rest
-                        const uint32_t cw = data32[c >> 2];
-                        const int cs = (c & 3) * 8;
-                        if (c < p && ((((cw >> cs) ^ v) << cs) == 0)) m |= 1ull << b;
-                        if ((p & 3) == 3) { w_lo = w_hi; w_hi = data32[(p >> 2) + 2]; }
-                    }
-                    cand[g] = m;
+                    const int k = stop_rel - g * 64;                               // positions of this group before `stop`
+                    if (k <= 0) cand[g] = 0ull; else if (k < 64) cand[g] &= (1ull << k) - 1ull;
                 }
             }
             // pass 2 -- the greedy walk only visits positions whose bit is set
