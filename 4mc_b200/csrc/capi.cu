@@ -470,16 +470,26 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
         CK(cudaMemsetAsync(ws.tokmap.p, 0, (max_chunks + 1) * LZ4_CHUNK_WORDS * 4, st));
         const BlockDesc *desc = desc_all;
         uint8_t *status = status_all;
+        // The checksum pass runs on a side stream beside the decode.  Its launch comes AFTER the parse kernel's
+        // (verify_order 1) or after the copy kernel's (2): submitted first (0, round 1), its CTAs -- 16 KiB of shared
+        // memory each, seven per SM -- took the room of half the parse kernel's CTAs for as long as they ran.
+        static int verify_order = -1;
+        if (verify_order < 0) { const char *e = getenv("FOURMC_VERIFY_ORDER"); verify_order = e ? atoi(e) : 1; }
         if (check_xxh) {
             int rs;
             if ((rs = ensure_side(ctx, ws))) return rs;
             CK(cudaEventRecord(ws.fork, st));
             CK(cudaStreamWaitEvent(ws.side, ws.fork, 0));
+        }
+        auto launch_verify = [&]() -> int {
+            if (!check_xxh || verify_forked) return FOURMC_OK;
             KL("xxh_verify_kernel", ws.side, xxh_verify_kernel<<<(nb + VERIFY_WARPS - 1) / VERIFY_WARPS, VERIFY_WARPS * 32, 0, ws.side>>>(
                 desc, xxh_all, nb, status));
             CK(cudaEventRecord(ws.join, ws.side));
             verify_forked = true;
-        }
+            return FOURMC_OK;
+        };
+        if (verify_order == 0 || codec == CODEC_ZSTD) { if ((r = launch_verify())) return r; }
         if (!ctx->d1_attr_set) {
             CK(cudaFuncSetAttribute(lz4_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D1_SMEM));
             ctx->d1_attr_set = true;
@@ -549,6 +559,7 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
                 KL("lz4_parse_kernel", st, lz4_parse_kernel<<<(nb + D1_WARPS - 1) / D1_WARPS, D1_WARPS * 32, D1_SMEM, st>>>(desc, nb, (uint32_t *)ws.tokmap.p,
                                                                (uint32_t *)ws.chunkop.p, (int32_t *)ws.result.p));
         }
+        if (verify_order == 1) { if ((r = launch_verify())) return r; }
         for (uint32_t b0 = 0; b0 < nb; b0 += 32768) {
             const uint32_t cnt = std::min<uint32_t>(32768, nb - b0);
             KL("lz4_stored_kernel", st, lz4_stored_kernel<<<dim3(32, cnt), 256, 0, st>>>(desc + b0, cnt));
@@ -564,18 +575,11 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             }
             const uint32_t *tm = (const uint32_t *)ws.tokmap.p, *co = (const uint32_t *)ws.chunkop.p;
             const int32_t *rs = (const int32_t *)ws.result.p;
-            static int prewait = -1;
-            if (prewait < 0) { const char *e = getenv("FOURMC_D2_PREWAIT"); prewait = e ? atoi(e) : 0; }
-#define D2_LAUNCH(WW) KL("lz4_copy_kernel", st, lz4_copy_kernel<WW><<<nb, WW * 32, 0, st>>>(desc, tm, co, rs, prewait))
-            static int d2_var = -1;
-            if (d2_var < 0) { const char *e = getenv("FOURMC_D2_VAR"); d2_var = e ? atoi(e) : 4; }
-#define D2_VAR(VV) KL("lz4_copy_kernel", st, (lz4_copy_kernel<1, VV><<<nb, 32, 0, st>>>(desc, tm, co, rs, prewait)))
-            if (w == 1 && d2_var == 8) D2_VAR(8);
-            else if (w == 1 && d2_var == 1) D2_VAR(0);
-#undef D2_VAR
-            else if (w == 1) D2_LAUNCH(1); else if (w == 2) D2_LAUNCH(2); else if (w == 4) D2_LAUNCH(4); else D2_LAUNCH(8);
+#define D2_LAUNCH(WW) KL("lz4_copy_kernel", st, lz4_copy_kernel<WW><<<nb, WW * 32, 0, st>>>(desc, tm, co, rs))
+            if (w == 1) D2_LAUNCH(1); else if (w == 2) D2_LAUNCH(2); else if (w == 4) D2_LAUNCH(4); else D2_LAUNCH(8);
 #undef D2_LAUNCH
         }
+        if ((r = launch_verify())) return r;          // verify_order 2, and whatever has not launched it yet
     }
     if (verify_forked) CK(cudaStreamWaitEvent(st, ws.join, 0));
     if ((r = ensure(ctx, ws.final_, 16))) return r;

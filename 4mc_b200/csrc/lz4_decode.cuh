@@ -7,17 +7,20 @@
 //                           chunk_op u32 per 128 compressed bytes: output position of the first
 //                                    sequence whose token lies in that 128-byte chunk
 //                         (0.16 bytes of scratch per compressed byte).
-//  D2  lz4_copy_kernel    one CTA per block.  Warps take 128-byte chunks of the compressed
-//                         stream in order (a shared ticket), turn the chunk's <= 43 token bits
-//                         into one sequence per lane and prefix-sum the output lengths.  The
-//                         chunk's output span (~250 B on text) is assembled in shared memory --
-//                         literals from the stream, match bytes from HBM when the source precedes
-//                         the span, from the span itself otherwise (resolved in rounds, lowest
-//                         destination first) -- and flushed with 128-bit stores.  A source in HBM
-//                         may belong to a chunk another warp is still working on, so warps publish
-//                         the lowest output position they still owe (`owed[w]`) and wait until the
-//                         minimum over all warps has passed the bytes they need.  Spans over 2 KiB
-//                         (long runs) are copied in place instead, by the whole warp.
+//  D2  lz4_copy_kernel    one CTA per block.  A warp takes 1 KiB of the compressed stream at a time
+//                         (128 B when several warps share a block), lists its tokens and takes them 32
+//                         at a time, one sequence per lane; output positions by prefix sum.  The batch's
+//                         output span (~420 B on text) is assembled in shared memory as aligned 32-bit
+//                         WORDS -- literal words from aligned words of the stream, match words from the
+//                         aligned 16-byte chunks around the source in HBM / L2, both through a funnel
+//                         shift; a word shared by two neighbouring sequences is stored once, by the left
+//                         lane, with the right lane's half OR-ed in (shuffle) -- and flushed with 128-bit
+//                         stores.  The rare rest is patched in with byte stores: sources inside the span
+//                         (resolved in rounds, lowest destination first), offset 0, long runs.  A source
+//                         may belong to a work item another warp is still copying, so warps publish the
+//                         lowest output position they still owe (`owed[w]`) and a match waits until the
+//                         minimum over all warps has passed the bytes it needs.  Spans over 2 KiB (long
+//                         runs) are copied in place instead, by the whole warp.
 //  D0  lz4_stored_kernel  csize == usize blocks are raw copies (native/4mc.c:635-642).
 #pragma once
 
@@ -656,6 +659,7 @@ constexpr int LZ4_SCR = 80;               // scratch bytes per lane (80 keeps 12
 constexpr int LZ4_MAC_CHUNKS = 8;         // 128-byte chunks per D2 work item when a warp has a block to itself: 1 KiB,
                                           // 32 tokmap words, one per lane
 constexpr int LZ4_MAC_TOK = 352;          // > ceil(1024 / 3): a sequence is at least 3 bytes
+constexpr int LZ4_WLIT = 64;              // literal runs up to this long travel as words with their sequence
 constexpr int LZ4_WMATCH = 32;            // and matches up to this long (three aligned 16-byte loads cover them)
 
 // Shared memory of one copy warp / of the W warps that share a block.
@@ -689,12 +693,9 @@ struct CopyBlockSmem {
 // run), and "slow" matches -- a source inside the span (0.7 % on text: resolved in rounds, lowest destination first),
 // offset 0 (zeros, lz4.c:2300-2303), long matches, and (W > 1) a source the sibling warps have not delivered yet.
 // A lane with a slow match takes no part in the word stage at all.
-// V: experiment switches (bit 0: tokens fetched one batch ahead; bit 1: match loads issued before the literal
-// words; bits 2-3: literal words 0 = three unrolled (runs up to 8 bytes), 1 = a loop (up to 64), 2 = five unrolled (up to 16))
-template <int W, int C, int V>
+template <int W, int C>
 __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32_t *tokmap, const uint32_t *chunk_op,
-                                               const int warp, const int lane, CopyBlockSmem<W> *bs, CopyWarpSmem *ws,
-                                               const int prewait)
+                                               const int warp, const int lane, CopyBlockSmem<W> *bs, CopyWarpSmem *ws)
 {
     const uint8_t *__restrict__ src = bd.src;
     uint8_t *out = bd.dst;
@@ -708,10 +709,6 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
     // literal words are fetched as the aligned words around their bytes: never outside the payload's own words
     const uint32_t *src_w_lo = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
     const int src_w_last = (int)((((uintptr_t)(src + (csize > 0 ? csize - 1 : 0)) & ~(uintptr_t)3) - (uintptr_t)src_w_lo) >> 2);
-    constexpr bool PF = (V & 1) != 0, EARLY = (V & 2) != 0;
-    constexpr int LITM = (V >> 2) & 3;
-    constexpr int LZ4_WLIT = LITM == 1 ? 64 : LITM == 2 ? 16 : 8;   // literal runs up to this long travel as words with their sequence
-    constexpr int NLW = (3 + LZ4_WLIT + 3) / 4;                     // words such a run can touch
     volatile int *owed = bs->owed;
     uint8_t *span = ws->span;
     uint32_t *span32 = (uint32_t *)ws->span;
@@ -774,19 +771,13 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
             if (base < LZ4_MAC_TOK) s_tokpos_w[base] = (uint16_t)(lane * 32 + __ffs(word) - 1);
         __syncwarp();
         const int ip_base = k * (C * LZ4_CHUNK) - dq;
-        // tokens are fetched one batch ahead
-        int ip_nx = 0;
-        unsigned tok_nx = 0;
-        if (PF && lane < ntok) { ip_nx = ip_base + (int)s_tokpos_w[lane]; tok_nx = src[ip_nx]; }
 
         for (int batch = 0; batch < ntok; batch += 32) {
             const bool active = batch + lane < ntok;
             int lit = 0, ml = 0, off = 0, lit_src = 0;
-            int ip = ip_nx + 1;
-            unsigned tok = tok_nx;
-            if (PF) { if (batch + 32 + lane < ntok) { ip_nx = ip_base + (int)s_tokpos_w[batch + 32 + lane]; tok_nx = src[ip_nx]; } }
-            else if (active) { ip = ip_base + (int)s_tokpos_w[batch + lane]; tok = src[ip++]; }
             if (active) {
+                int ip = ip_base + (int)s_tokpos_w[batch + lane];
+                const unsigned tok = src[ip++];
                 lit = (int)(tok >> 4);
                 if (lit == 15) { unsigned s; do { s = src[ip++]; lit += (int)s; } while (s == 255); }
                 lit_src = ip;
@@ -812,12 +803,8 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
                 publish(op0);                         // nothing below op0 is owed by this warp
 
                 // which bytes of my sequence travel as words: [rs, re)
-                // (W > 1) a source the sibling warps still owe makes a slow match: it waits there, alone -- after a short
-                // wait here, for all: a source that arrives in time saves its lane the slow way
-                if (W > 1 && prewait > 0) {
-                    const int need = warp_max((ml > 0 && off != 0 && mstart + ml <= op0 && ml <= LZ4_WMATCH) ? mstart + ml : 0);
-                    for (int spin = 0; spin < prewait && high_water() < need; spin++) __nanosleep(40);
-                }
+                // (W > 1) a source the sibling warps still owe makes a slow match: it waits there, alone (a short wait
+                // here, for all lanes, in the hope of saving that lane the slow way: r02p, 0 / 8 / 32 polls: 9.8 / 10.1 / 10.6 ms)
                 const int hwm0 = high_water();
                 if (W > 1) __threadfence_block();
                 const bool fastm = ml > 0 && off != 0 && mstart + ml <= min(op0, hwm0) && ml <= LZ4_WMATCH;
@@ -844,13 +831,6 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
                 // match sources: the aligned 16-byte chunks around them
                 const int so = (int)((uintptr_t)(out + mstart) & 15);
                 const int nch = (so + ml + 15) >> 4;                  // 1..3 when m_in
-                uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
-                if (EARLY && m_in) {
-                    const uint4 *gb = (const uint4 *)(out + mstart - so);
-                    q0 = ldg_v4(gb);
-                    if (nch > 1) q1 = ldg_v4(gb + 1);
-                    if (nch > 2) q2 = ldg_v4(gb + 2);
-                }
                 // literal words: aligned words of the stream through a funnel shift, bytes outside the run zeroed
                 uint32_t l0 = 0, llast = 0;
                 const uint32_t lwi = la >> 2;
@@ -859,56 +839,29 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
                     const int sh = (int)(sb & 3) * 8;
                     const uint32_t *sw = src_w_lo + wo;
                     const uint32_t tmask = 0xffffffffu >> (8 * (4 * nwl - nb));
-                    if (LITM == 1) {
-                        // word j is built, word j - 1 stored
-                        uint32_t lo = sw[1];
-                        uint32_t cur = __funnelshift_r(sw[0], lo, sh) & (0xffffffffu << (8 * dd));
-                        if (nwl == 1) cur &= tmask;
-                        l0 = cur;
-                        for (int j = 1; j < nwl; j++) {
-                            const uint32_t hi = sw[j + 1];
-                            uint32_t v = __funnelshift_r(lo, hi, sh);
-                            lo = hi;
-                            if (j == nwl - 1) v &= tmask;
-                            if (!(j == 1 && head_skip)) span32[lwi + j - 1] = cur;
-                            cur = v;
-                        }
-                        llast = cur;
-                    } else {
-                        // scalars, not arrays: the compiler turns "if (i == nwl - 1) w[i] ..." into a local-memory array
-                        auto tm = [&](int x) -> uint32_t { return __funnelshift_rc(0xffffffffu, 0u, max(32 - 8 * x, 0)); };  // the low x bytes (x <= 0: none)
-                        const uint32_t a0 = sw[0], a1 = sw[1];
-                        const uint32_t a2 = nwl >= 2 ? sw[2] : 0u, a3 = nwl >= 3 ? sw[3] : 0u;
-                        const uint32_t w0 = __funnelshift_r(a0, a1, sh) & (0xffffffffu << (8 * dd)) & tm(nb);
-                        const uint32_t w1 = __funnelshift_r(a1, a2, sh) & tm(nb - 4);
-                        const uint32_t w2 = __funnelshift_r(a2, a3, sh) & tm(nb - 8);
-                        l0 = w0;
-                        // all but the last word now: that one may be shared with my match, or be my last word
-                        if (nwl > 1 && !head_skip) span32[lwi] = w0;
-                        if (nwl > 2) span32[lwi + 1] = w1;
-                        llast = nwl <= 1 ? w0 : nwl == 2 ? w1 : w2;
-                        if constexpr (NLW > 3) {
-                            const uint32_t a4 = nwl >= 4 ? sw[4] : 0u, a5 = nwl >= 5 ? sw[5] : 0u;
-                            const uint32_t w3 = __funnelshift_r(a3, a4, sh) & tm(nb - 12);
-                            const uint32_t w4 = __funnelshift_r(a4, a5, sh) & tm(nb - 16);
-                            if (nwl > 3) span32[lwi + 2] = w2;
-                            if (nwl > 4) span32[lwi + 3] = w3;
-                            if (nwl == 4) llast = w3;
-                            if (nwl >= 5) llast = w4;
-                        }
+                    // word j is built, word j - 1 stored
+                    uint32_t lo = sw[1];
+                    uint32_t cur = __funnelshift_r(sw[0], lo, sh) & (0xffffffffu << (8 * dd));
+                    if (nwl == 1) cur &= tmask;
+                    l0 = cur;
+                    for (int j = 1; j < nwl; j++) {
+                        const uint32_t hi = sw[j + 1];
+                        uint32_t v = __funnelshift_r(lo, hi, sh);
+                        lo = hi;
+                        if (j == nwl - 1) v &= tmask;
+                        if (!(j == 1 && head_skip)) span32[lwi + j - 1] = cur;
+                        cur = v;
                     }
+                    llast = cur;
                 }
                 // first match word
                 uint32_t mcur = 0, mlo = 0, mwi = 0, m_tmask = 0xffffffffu;
                 const uint32_t *msw = (const uint32_t *)s_scr_w;
                 int nwm = 0, msh = 0;
                 if (m_in) {
-                    if (!EARLY) {
-                        const uint4 *gb = (const uint4 *)(out + mstart - so);
-                        q0 = ldg_v4(gb);
-                        if (nch > 1) q1 = ldg_v4(gb + 1);
-                        if (nch > 2) q2 = ldg_v4(gb + 2);
-                    }
+                    const uint4 *gb = (const uint4 *)(out + mstart - so);
+                    const uint4 z = make_uint4(0, 0, 0, 0);
+                    const uint4 q0 = ldg_v4(gb), q1 = nch > 1 ? ldg_v4(gb + 1) : z, q2 = nch > 2 ? ldg_v4(gb + 2) : z;
                     uint4 *scr = (uint4 *)(s_scr_w + lane * LZ4_SCR + 16);
                     scr[0] = q0; if (nch > 1) scr[1] = q1; if (nch > 2) scr[2] = q2;
                     const uint32_t ma = (uint32_t)(shift + (d - op0));
@@ -1076,10 +1029,12 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
 // each (and then hardly ever wait on one another), few blocks need many.  More than 8 only wait for one another: a
 // chunk's matches mostly point into the last few KiB, i.e. into the chunks the sibling warps still work on
 // (r02i, one block: 8 warps 8.5 ms, 32 warps 12.5 ms).
-template <int W, int V = 4>
-__global__ void __launch_bounds__(W * 32, W == 1 ? ((V & 16) ? 32 : 28) : 1)
+// A warp alone with its block: 28 CTAs per SM at 72 registers (r02q: forced down to 64 registers for 32 CTAs per SM,
+// 42 -> 47 ms per 16 GiB).
+template <int W>
+__global__ void __launch_bounds__(W * 32, W == 1 ? 28 : 1)
 lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t *chunk_op,
-                const int32_t *result, const int prewait)
+                const int32_t *result)
 {
     __shared__ CopyBlockSmem<W> s_block;
     __shared__ CopyWarpSmem s_warp[W];
@@ -1088,7 +1043,7 @@ lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t 
     if (threadIdx.x < W) s_block.owed[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_block.ticket = 0;
     if (W > 1) __syncthreads();
-    lz4_copy_block<W, (W == 1 ? LZ4_MAC_CHUNKS : 1), V>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, &s_block, &s_warp[threadIdx.x >> 5], prewait);
+    lz4_copy_block<W, (W == 1 ? LZ4_MAC_CHUNKS : 1)>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, &s_block, &s_warp[threadIdx.x >> 5]);
 }
 
 // ---- D0 ------------------------------------------------------------------------------------

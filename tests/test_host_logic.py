@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import random
 import re
+import sys
 
 import pytest
 
@@ -196,3 +197,33 @@ def test_warp_parallel_parse_equals_serial_walk(d1, ora, pkg):
             m = bytes(m)
             a, b = _d1_both(d1, m, rng.choice([len(src), len(src) + 64, 4 << 20]), rng.choice([0, 3, 12]))
             assert a == b, (len(src), k, a[0], b[0])
+
+
+def test_d2_word_assembly_rules(ora):
+    """The word stage of lz4_copy_kernel (which bytes travel as aligned words of the span, who stores a word two
+    sequences share, what is patched in with byte stores), restated lane by lane in tools/d2_words_emul.py, on the
+    sequences of a reference-written block and on adversarial batches; the GPU suite checks the kernel itself."""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import d2_words_emul as E
+    rnd = random.Random(7)
+    stream = golden_bytes("logtext_128k.l1.4mc")
+    text = golden_bytes("logtext_128k.bin")
+    usize, csize = int.from_bytes(stream[12:16], "big"), int.from_bytes(stream[16:20], "big")
+    block = stream[24:24 + csize]
+    assert ora.lz4_decompress(block, usize) == (usize, text[:usize])
+    seqs = E.parse_lz4_block(block)
+    assert sum(s[1] + s[2] for s in seqs) == usize
+    for s0 in range(0, len(seqs), 32):
+        grp = [(lit, ml, off, op, text[op:op + lit]) for _, lit, ml, off, op in seqs[s0:s0 + 32]]
+        if sum(g[0] + g[1] for g in grp) > E.SPAN:
+            continue
+        for dstbase in (0, 5):
+            got, op0, total = E.run_batch(grp, text, dstbase, rnd)
+            assert got == text[op0:op0 + total], (s0, dstbase)
+    for _ in range(1500):
+        grp, out = E.adversarial_case(rnd)
+        if sum(g[0] + g[1] for g in grp) > E.SPAN:
+            continue
+        got, op0, total = E.run_batch(grp, out, rnd.randrange(16), rnd)
+        assert got == out[op0:op0 + total]
