@@ -565,18 +565,25 @@ int dec_blocks(fourmc_ctx *ctx, cudaStream_t st, DecWs &ws, uint32_t nb, size_t 
             KL("lz4_stored_kernel", st, lz4_stored_kernel<<<dim3(32, cnt), 256, 0, st>>>(desc + b0, cnt));
         }
         if (codec == CODEC_LZ4) {
-            // warps per block: enough to fill the chip when blocks are few, few when blocks are many
-            static int forced = -1;
+            // warps per block.  Many blocks: one warp each, the word-stage kernel with 1 KiB items (full batches; a
+            // lone warp needs ~25 ms for its block however few blocks there are).  Fewer: four warps share a block,
+            // same kernel with 128-byte items.  Few: eight warps, the byte-granular kernel, which delivers a single
+            // item soonest.  D2 ms at 2048 / 1024 / 512 / 256 / 64 / 1 blocks (r02v, r02w): one warp 29.8 / 26.1 / 25.2 /
+            // 24.8 / - / 21; four 44.5 / 28.2 / 14.5 / 13.2 / 14.4 / -; eight, byte-granular - / - / 17.9 / 9.0 / 8.1 / 7.7
+            static int forced = -1, forced_bytes = -1;
             if (forced < 0) { const char *e = getenv("FOURMC_D2_WARPS"); forced = e ? atoi(e) : 0; }
+            if (forced_bytes < 0) { const char *e = getenv("FOURMC_D2_BYTES"); forced_bytes = e ? (atoi(e) ? 1 : 0) : 2; }
+            const uint32_t sm = (uint32_t)ctx->sm_count;
             int w = forced;
-            if (w != 1 && w != 2 && w != 4 && w != 8) {
-                const uint32_t want = (uint32_t)ctx->sm_count * 24;        // resident warps to aim for (measured, profiles/)
-                w = nb * 1 >= want ? 1 : nb * 2 >= want ? 2 : nb * 4 >= want ? 4 : 8;
-            }
+            if (w != 1 && w != 2 && w != 4 && w != 8) w = nb >= sm * 6 ? 1 : nb * 10 >= sm * 26 ? 4 : 8;
+            const bool bytes = w > 1 && (forced_bytes == 2 ? w == 8 : forced_bytes == 1);
             const uint32_t *tm = (const uint32_t *)ws.tokmap.p, *co = (const uint32_t *)ws.chunkop.p;
             const int32_t *rs = (const int32_t *)ws.result.p;
-#define D2_LAUNCH(WW) KL("lz4_copy_kernel", st, lz4_copy_kernel<WW><<<nb, WW * 32, 0, st>>>(desc, tm, co, rs))
-            if (w == 1) D2_LAUNCH(1); else if (w == 2) D2_LAUNCH(2); else if (w == 4) D2_LAUNCH(4); else D2_LAUNCH(8);
+#define D2_LAUNCH(WW, BB) KL("lz4_copy_kernel", st, (lz4_copy_kernel<WW, BB><<<nb, WW * 32, 0, st>>>(desc, tm, co, rs)))
+            if (w == 1) D2_LAUNCH(1, false);
+            else if (w == 2) { if (bytes) D2_LAUNCH(2, true); else D2_LAUNCH(2, false); }
+            else if (w == 4) { if (bytes) D2_LAUNCH(4, true); else D2_LAUNCH(4, false); }
+            else { if (bytes) D2_LAUNCH(8, true); else D2_LAUNCH(8, false); }
 #undef D2_LAUNCH
         }
         if ((r = launch_verify())) return r;          // verify_order 2, and whatever has not launched it yet

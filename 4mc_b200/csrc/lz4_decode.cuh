@@ -1024,6 +1024,245 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
     publish(0x7fffffff);
 }
 
+// ---- D2 when W warps SHARE a block (few blocks: the per-block calls, the slices of the host pipeline, a rank's
+// share of a stream on many GPUs).  This is the round-1 design, kept for exactly this case: work items of ONE
+// 128-byte chunk (~20 sequences), every match waiting on its own for the block-wide mark, byte-granular assembly.
+// A block's matches mostly point a few KiB back -- into the items the sibling warps are still copying -- so what
+// counts here is how soon a single item is delivered, not how few instructions it costs: the word-stage kernel
+// above with its full batches is 1.7x faster when a warp has a block to itself and 1.1-1.4x SLOWER than this one
+// when warps share a block (r02v: 1024 blocks, 4 warps each: 28.2 ms against 19.6 ms; 256 blocks, 8 warps: 10.9
+// against 9.5).
+
+// Shared memory of one copy warp / of the W warps that share a block.
+struct SharedCopyWarpSmem {
+    __align__(16) uint8_t span[LZ4_SPAN + 32];
+    __align__(16) uint8_t scr[32 * LZ4_SCR];      // per lane: 4 aligned 16-byte chunks of a match source
+    uint8_t tokpos[64];
+};
+
+// The copy of one block by W warps (`warp` = 0 .. W-1 within the block).
+template <int W>
+__device__ __forceinline__ void lz4_copy_block_shared(const BlockDesc &bd, const uint32_t *tokmap, const uint32_t *chunk_op,
+                                               const int warp, const int lane, CopyBlockSmem<W> *bs, SharedCopyWarpSmem *ws)
+{
+    const uint8_t *__restrict__ src = bd.src;
+    uint8_t *out = bd.dst;
+    const int csize = (int)bd.csize;
+    const int dq = (int)((uintptr_t)bd.src & 15);     // D1 records tokens at aligned positions ip + dq
+    const int nchunks = (dq + csize + LZ4_CHUNK - 1) / LZ4_CHUNK;
+    const uint4 *maps = (const uint4 *)(tokmap + (size_t)bd.chunk_base * LZ4_CHUNK_WORDS);
+    const uint32_t *cops = chunk_op + bd.chunk_base;
+    volatile int *owed = bs->owed;
+    uint8_t *span = ws->span;
+    uint8_t *s_tokpos_w = ws->tokpos;
+    uint8_t *s_scr_w = ws->scr;
+
+    // lowest output position any warp of this block still owes
+    auto high_water = [&]() -> int {
+        if (W == 1) return 0x7fffffff;
+        int v = lane < W ? owed[lane] : 0x7fffffff;
+#pragma unroll
+        for (int s = W / 2; s > 0; s >>= 1) v = min(v, __shfl_xor_sync(FM_FULL, v, s));
+        return __shfl_sync(FM_FULL, v, 0);
+    };
+    auto publish = [&](int pos) {
+        if (W == 1) return;
+        __threadfence_block();                        // our finished bytes before the new mark
+        if (lane == 0) owed[warp] = pos;
+    };
+
+    // Chunks are taken one AHEAD: while chunk k is copied, the token bits and the output position of the chunk
+    // this warp takes next are already on their way, and the two lines of compressed bytes it will read are
+    // being pulled into L1 -- a warp's chunks are a dependent chain (bits -> tokens -> offsets -> match bytes),
+    // so every load taken off that chain shortens the block's time.
+    int kseq = 0;
+    auto take = [&]() -> int {
+        int t = 0;
+        if (W == 1) t = kseq++;
+        else {
+            if (lane == 0) t = atomicAdd(&bs->ticket, 1);
+            t = __shfl_sync(FM_FULL, t, 0);
+        }
+        return t;
+    };
+    uint4 m_n = make_uint4(0u, 0u, 0u, 0u);
+    int op_n = 0;
+    auto fetch = [&](int kk) {
+        if (kk >= nchunks) return;
+        m_n = maps[kk]; op_n = (int)cops[kk];
+        const int at = kk * LZ4_CHUNK - dq + lane * 128;
+        if (lane < 2 && at >= 0 && at < csize) asm volatile("prefetch.global.L1 [%0];" ::"l"(src + at));
+    };
+    int kn = take();
+    fetch(kn);
+    for (;;) {
+        const int k = kn;
+        if (k >= nchunks) break;
+        const uint4 m = m_n;
+        int op0 = op_n;
+        kn = take();
+        fetch(kn);
+        const int c0 = __popc(m.x), c1 = c0 + __popc(m.y), c2 = c1 + __popc(m.z), ntok = c2 + __popc(m.w);
+        if (ntok == 0) continue;
+
+        // lane r takes the r-th token of the chunk: scatter positions by rank
+        {
+            const uint32_t lt = (1u << lane) - 1u;
+            if ((m.x >> lane) & 1u) s_tokpos_w[__popc(m.x & lt)] = (uint8_t)lane;
+            if ((m.y >> lane) & 1u) s_tokpos_w[c0 + __popc(m.y & lt)] = (uint8_t)(32 + lane);
+            if ((m.z >> lane) & 1u) s_tokpos_w[c1 + __popc(m.z & lt)] = (uint8_t)(64 + lane);
+            if ((m.w >> lane) & 1u) s_tokpos_w[c2 + __popc(m.w & lt)] = (uint8_t)(96 + lane);
+        }
+        __syncwarp();
+
+        for (int batch = 0; batch < ntok; batch += 32) {
+            const bool active = batch + lane < ntok;
+            int lit = 0, ml = 0, off = 0, lit_src = 0;
+            if (active) {
+                int ip = k * LZ4_CHUNK + (int)s_tokpos_w[batch + lane] - dq;
+                const unsigned tok = src[ip++];
+                lit = (int)(tok >> 4);
+                if (lit == 15) { unsigned s; do { s = src[ip++]; lit += (int)s; } while (s == 255); }
+                lit_src = ip;
+                ip += lit;
+                if (ip != csize) {                    // not the closing literal run
+                    off = (int)src[ip] | ((int)src[ip + 1] << 8); ip += 2;
+                    ml = (int)(tok & 15);
+                    if (ml == 15) { unsigned s; do { s = src[ip++]; ml += (int)s; } while (s == 255); }
+                    ml += 4;
+                }
+            }
+            const int outlen = lit + ml;
+            const int incl = warp_incl_scan_add(outlen);
+            const int my_op = op0 + incl - outlen;
+            const int total = __shfl_sync(FM_FULL, incl, 31);
+            const int d = my_op + lit;                // where my match starts
+            const int mstart = d - off;
+
+            if (total <= LZ4_SPAN) {
+                // ---------- path A: assemble [op0, op0 + total) in shared memory, flush once ----------
+                const int shift = (int)((uintptr_t)(out + op0) & 15);   // equal 16-byte phases in smem and HBM
+                uint8_t *sp = span + shift - op0;     // sp[x] holds output byte x
+                publish(op0);                         // nothing below op0 is owed by this warp
+                // literals
+                if (active && lit < LZ4_LONG) copy_batched(sp + my_op, src + lit_src, lit);
+                for (unsigned lm = __ballot_sync(FM_FULL, active && lit >= LZ4_LONG); lm; lm &= lm - 1) {
+                    const int l = __ffs(lm) - 1;
+                    const int n = __shfl_sync(FM_FULL, lit, l), sp0 = __shfl_sync(FM_FULL, my_op, l);
+                    const int ls = __shfl_sync(FM_FULL, lit_src, l);
+                    for (int i = lane; i < n; i += 32) sp[sp0 + i] = src[ls + i];
+                }
+                // matches.  Bytes from before the span come from HBM once the block-wide mark has
+                // passed them; bytes inside the span come from shared memory once every earlier
+                // match of this warp that could overlap them is done (lowest destination first).
+                bool pending = ml > 0;
+                if (pending && off == 0) {            // lz4.c:2300-2303: offset 0 yields zeros
+                    for (int i = 0; i < ml; i++) sp[d + i] = 0;
+                    pending = false;
+                }
+                const int ext = (pending && mstart < op0) ? min(ml, op0 - mstart) : 0;
+                const int need_ext = ext ? mstart + ext : 0;
+                const int need_in = (ml > ext) ? min(mstart + ml, d) : 0;
+                __syncwarp();
+                int idle = 0;
+                for (;;) {
+                    const int low = warp_min(pending ? d : 0x7fffffff);
+                    if (low == 0x7fffffff) break;
+                    const int hwm = high_water();
+                    if (W > 1) __threadfence_block();
+                    const bool go = pending && need_ext <= hwm && need_in <= low;
+                    if (go) {
+                        if (ext > 0 && ext < LZ4_LONG) {
+                            // the source is somewhere in HBM/L2: fetch it with (at most four) aligned
+                            // 128-bit loads instead of one load per byte -- every load of a scattered
+                            // address costs the L1 data pipe a wavefront per lane
+                            const uint8_t *gs = out + mstart;
+                            const int so = (int)((uintptr_t)gs & 15);
+                            const uint4 *gb = (const uint4 *)(gs - so);
+                            const int nch = (so + ext + 15) >> 4;
+                            uint4 *scr = (uint4 *)(s_scr_w + lane * LZ4_SCR);
+                            const uint4 z = make_uint4(0, 0, 0, 0);
+                            const uint4 q0 = ldg_v4(gb), q1 = nch > 1 ? ldg_v4(gb + 1) : z;
+                            const uint4 q2 = nch > 2 ? ldg_v4(gb + 2) : z, q3 = nch > 3 ? ldg_v4(gb + 3) : z;
+                            scr[0] = q0; if (nch > 1) scr[1] = q1; if (nch > 2) scr[2] = q2; if (nch > 3) scr[3] = q3;
+                            copy_batched(sp + d, (const uint8_t *)scr + so, ext);
+                        }
+                        if (ml > ext && ext < LZ4_LONG) smem_copy_seq(sp + d + ext, sp + mstart + ext, ml - ext);
+                    }
+                    // long reads from HBM: the whole warp per match, then its in-span remainder
+                    for (unsigned lm = __ballot_sync(FM_FULL, go && ext >= LZ4_LONG); lm; lm &= lm - 1) {
+                        const int l = __ffs(lm) - 1;
+                        const int n = __shfl_sync(FM_FULL, ext, l), dd = __shfl_sync(FM_FULL, d, l);
+                        const int ms = __shfl_sync(FM_FULL, mstart, l), mm = __shfl_sync(FM_FULL, ml, l);
+                        for (int i = lane; i < n; i += 32) sp[dd + i] = out[ms + i];
+                        __syncwarp();
+                        if (lane == l && mm > n) smem_copy_seq(sp + dd + n, sp + ms + n, mm - n);
+                    }
+                    const bool any = __any_sync(FM_FULL, go);
+                    if (go) pending = false;
+                    __syncwarp();
+                    if (!any) { if (++idle > 2) __nanosleep(idle > 16 ? 256 : 32); } else idle = 0;
+                }
+                __syncwarp();
+                // flush
+                {
+                    const int head = min(total, (16 - shift) & 15);
+                    if (lane < head) out[op0 + lane] = span[shift + lane];
+                    const int body = (total - head) >> 4;
+                    const uint4 *sv = (const uint4 *)(span + shift + head);
+                    uint4 *dv = (uint4 *)(out + op0 + head);
+                    for (int i = lane; i < body; i += 32) dv[i] = sv[i];
+                    const int done = head + (body << 4);
+                    if (done + lane < total) out[op0 + done + lane] = span[shift + done + lane];
+                }
+                op0 += total;
+                __syncwarp();
+                publish(op0);
+                continue;
+            }
+
+            // ---------- path B: long sequences, copied in place ----------
+            op0 += total;
+            if (active && lit < LZ4_LONG) copy_batched(out + my_op, src + lit_src, lit);
+            for (unsigned long_m = __ballot_sync(FM_FULL, active && lit >= LZ4_LONG); long_m; long_m &= long_m - 1) {
+                const int l = __ffs(long_m) - 1;
+                warp_copy_bytes(out + __shfl_sync(FM_FULL, my_op, l), src + __shfl_sync(FM_FULL, lit_src, l),
+                                __shfl_sync(FM_FULL, lit, l));
+            }
+            bool pending = active && ml > 0;
+            const int need = (off == 0) ? 0 : min(mstart + ml, d);   // everything below this must exist
+            int idle = 0;
+            for (;;) {
+                const int wmin = warp_min(pending ? d : 0x7fffffff);
+                publish(wmin == 0x7fffffff ? op0 : wmin);
+                if (wmin == 0x7fffffff) break;
+                __syncwarp();
+                // alone in the block, everything below our own lowest pending match is complete
+                const int hwm = (W == 1) ? wmin : high_water();
+                __threadfence_block();
+                const bool go = pending && need <= hwm;
+                if (go && ml < LZ4_LONG) {
+                    if (off == 0) { for (int i = 0; i < ml; i++) out[d + i] = 0; }
+                    else { for (int i = 0; i < ml; i++) out[d + i] = out[mstart + i]; }
+                }
+                for (unsigned long_m = __ballot_sync(FM_FULL, go && ml >= LZ4_LONG); long_m; long_m &= long_m - 1) {
+                    const int l = __ffs(long_m) - 1;
+                    warp_copy_match(out, __shfl_sync(FM_FULL, d, l), __shfl_sync(FM_FULL, off, l),
+                                    __shfl_sync(FM_FULL, ml, l));
+                }
+                const bool any = __any_sync(FM_FULL, go);
+                if (go) pending = false;
+                __syncwarp();
+                if (!any) { if (++idle > 2) __nanosleep(idle > 16 ? 256 : 32); } else idle = 0;
+            }
+        }
+        __syncwarp();
+    }
+    // a finished warp must not hold the mark down
+    publish(0x7fffffff);
+}
+
+
 // D2 as a kernel of its own (D1 ran before it): one CTA of W warps per block.
 // W = warps per block (1, 2, 4 or 8): the host picks it from the batch size -- many blocks in flight need few warps
 // each (and then hardly ever wait on one another), few blocks need many.  More than 8 only wait for one another: a
@@ -1031,19 +1270,25 @@ __device__ __forceinline__ void lz4_copy_block(const BlockDesc &bd, const uint32
 // (r02i, one block: 8 warps 8.5 ms, 32 warps 12.5 ms).
 // A warp alone with its block: 28 CTAs per SM at 72 registers (r02q: forced down to 64 registers for 32 CTAs per SM,
 // 42 -> 47 ms per 16 GiB).
-template <int W>
+// BYTES = true: the byte-granular copy (items of one chunk, W > 1 only).
+template <int W, bool BYTES>
 __global__ void __launch_bounds__(W * 32, W == 1 ? 28 : 1)
 lz4_copy_kernel(const BlockDesc *blocks, const uint32_t *tokmap, const uint32_t *chunk_op,
                 const int32_t *result)
 {
     __shared__ CopyBlockSmem<W> s_block;
-    __shared__ CopyWarpSmem s_warp[W];
     const BlockDesc bd = blocks[blockIdx.x];
     if (bd.stored || result[blockIdx.x] < 0) return;
     if (threadIdx.x < W) s_block.owed[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_block.ticket = 0;
     if (W > 1) __syncthreads();
-    lz4_copy_block<W, (W == 1 ? LZ4_MAC_CHUNKS : 1)>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, &s_block, &s_warp[threadIdx.x >> 5]);
+    if constexpr (!BYTES) {
+        __shared__ CopyWarpSmem s_warp[W];
+        lz4_copy_block<W, (W == 1 ? LZ4_MAC_CHUNKS : 1)>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, &s_block, &s_warp[threadIdx.x >> 5]);
+    } else {
+        __shared__ SharedCopyWarpSmem s_warp[W];
+        lz4_copy_block_shared<W>(bd, tokmap, chunk_op, threadIdx.x >> 5, threadIdx.x & 31, &s_block, &s_warp[threadIdx.x >> 5]);
+    }
 }
 
 // ---- D0 ------------------------------------------------------------------------------------

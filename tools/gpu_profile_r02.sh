@@ -17,6 +17,7 @@ tools/ncu_cap.sh ${TAG}_lz4_region_kernel lz4_region_kernel 1 python tools/quick
 tools/ncu_cap.sh ${TAG}_lz4_parse_kernel 'lz4_parse_kernel' 1 python tools/quick_decode.py 16 1
 tools/ncu_cap.sh ${TAG}_lz4_parse_wide_kernel lz4_parse_wide 1 python tools/quick_decode.py 0.5 1
 tools/ncu_cap.sh ${TAG}_zstd_frames_lane_kernel zstd_frames_lane 1 python tools/quick_decode.py 4 1 4mz
+timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > gpurun_out/${TAG}_pytest_gpu.txt
 timeout 300 python tools/latency_per_block.py > gpurun_out/${TAG}_latency.txt 2>&1
 FOURMC_CLI_TIMING=1 timeout 900 python tools/cli_file_timing.py 4 > gpurun_out/${TAG}_cli_t2.txt 2>&1
 for f in gpurun_out/${TAG}_bench.json gpurun_out/${TAG}_bench_reference.json gpurun_out/${TAG}_bench_c2.json gpurun_out/${TAG}_bench_c3.json gpurun_out/${TAG}_bench_c4.json; do cut -c1-260 $f; done

@@ -10,7 +10,8 @@ import shutil
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-TAG = "r02"
+import sys
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
 for f in glob.glob(os.path.join(G, TAG + "_*")):
     b = os.path.basename(f)
     if b.endswith((".json", ".txt", "_launches.csv")) and os.path.getsize(f) > 0:
