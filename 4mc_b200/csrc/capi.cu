@@ -37,6 +37,7 @@ struct DevBuf {
 struct EncWs {
     DevBuf scratch, meta, plan, lens, off, misc;   // misc: [0] work counter (u32), [8] span (u64), [16] total (u64), [24] carry (u64)
     DevBuf zout, zrout;                            // 4mz: entropy-stage output slots and their sizes
+    DevBuf chain;                                  // levels 2..4: chain links of the blocks in flight (2 bytes per input byte)
 };
 
 struct DecWs {
@@ -74,7 +75,7 @@ struct fourmc_ctx {
     size_t pinned_cap = 0;
     void *pin_up[2] = {nullptr, nullptr};   // pinned bounce buffers for uploads from pageable host memory (upload_pieces), per staging slot
     size_t pin_up_cap[2] = {0, 0};
-    bool region_attr_set = false, d1_attr_set = false, d1w_attr_set = false, zd_attr_set = false, gen_attr_set = false;   // per context = per device
+    bool region_attr_set = false, chain_attr_set = false, d1_attr_set = false, d1w_attr_set = false, zd_attr_set = false, gen_attr_set = false;   // per context = per device
     DevBuf ztables;                      // fmz::Tables (constant decode tables), uploaded once
     // optional per-kernel timing (fourmc_timing_enable): CUDA event pairs around every launch
     bool timing = false;
@@ -253,12 +254,14 @@ int level_min_match(int level)
 }
 
 // Levels as in native/4mc.c:243-253 (1 fast, 2 medium = LZ4 MC, 3 high = HC 4, 4 ultra = HC 8; the
-// 4mz twins :415-425): candidates tried per chain search; 0 selects the Fast parse.
+// 4mz twins :415-425): candidates tried per chain search; 0 selects the Fast parse.  32 / 64 candidates with the
+// cost-optimal parse reach the ratios of the reference's HC 4 / HC 8 (16 / 256 attempts, lz4hc.c:75-90 of its level
+// table) on the bench text: 2.67 / 2.69 against 2.66 / 2.69 (tools/hc_study.cpp).
 int level_chain_depth(int level)
 {
     const char *e = getenv("FOURMC_CHAIN_DEPTH");
     if (e) { int v = atoi(e); if (v >= 0 && v <= 4096) return v; }
-    return level <= 1 ? 0 : level == 2 ? 4 : level == 3 ? 16 : 64;
+    return level <= 1 ? 0 : level == 2 ? 4 : level == 3 ? 32 : 128;
 }
 
 enum { CODEC_LZ4 = 0, CODEC_ZSTD = 1 };
@@ -275,6 +278,36 @@ int ensure_ztables(fourmc_ctx *ctx)
 }
 
 // ---- encode --------------------------------------------------------------------------------
+
+// Levels 2..4: blocks of one launch of the region kernel share a chain-link buffer (2 bytes per input byte), so large
+// inputs are parsed in groups of blocks.
+uint32_t chain_group_blocks(uint32_t nb)
+{
+    const char *e = getenv("FOURMC_CHAIN_GROUP");  // read per call: the tests shrink it to exercise the loop over groups
+    int v = e ? atoi(e) : 256;
+    if (v < 1) v = 1;
+    if (v > 4096) v = 4096;
+    return std::min<uint32_t>(nb, (uint32_t)v);
+}
+
+// chain links of `gb` blocks starting at d_in (gn bytes), then nothing else: the caller launches the region kernel
+int launch_chain_links(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, const uint8_t *d_in, size_t gn, uint32_t gb, uint32_t block_bytes)
+{
+    if (!ctx->chain_attr_set) {
+        CK(cudaFuncSetAttribute(lz4_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_LINK_HASH_BYTES));
+        ctx->chain_attr_set = true;
+    }
+    // chunk size: enough warps to fill the GPU three times over when the group is small, little warm-up overhead when it is large
+    uint32_t chunk = 1u << 20;
+    const uint64_t want = 9ull * (uint64_t)ctx->sm_count;
+    while (chunk > (1u << 16) && (uint64_t)gb * ((block_bytes + chunk - 1) / chunk) < want) chunk >>= 1;
+    const uint32_t cpb = (block_bytes + chunk - 1) / chunk;
+    const uint32_t items = gb * cpb;
+    const uint32_t grid = std::min<uint32_t>(items, 3u * (uint32_t)ctx->sm_count);
+    KL("lz4_chain_kernel", st, lz4_chain_kernel<<<grid, 32, ENC_LINK_HASH_BYTES, st>>>(d_in, gn, block_bytes, chunk, cpb, items,
+                                                                                       (uint16_t *)ws.chain.p));
+    return FOURMC_OK;
+}
 
 // d_in[0..n) -> block records back to back at d_span (block b at d_span + off[b], off[0] = base).
 // raw_limit >= 0 selects the bare-block mode of the per-block API (single block, no header use).
@@ -321,8 +354,21 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     P.block_bytes = block_bytes;
     P.reproducible = ctx->repro_call;
     if (P.depth > 0) {
-        const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
-        KL("lz4_region_chain_kernel", st, lz4_region_kernel<false, true><<<grid, ENC_CHAIN_THREADS, ENC_SMEM_CHAIN, st>>>(P));
+        const uint32_t G = chain_group_blocks(nb);
+        if ((r = ensure(ctx, ws.chain, (size_t)G * block_bytes * 2))) return r;
+        for (uint32_t g0 = 0; g0 < nb; g0 += G) {
+            const uint32_t gb = std::min<uint32_t>(G, nb - g0);
+            const size_t goff = (size_t)g0 * block_bytes;
+            const size_t gn = std::min<size_t>(n - goff, (size_t)gb * block_bytes);
+            if (g0) CK(cudaMemsetAsync(ws.misc.p, 0, 4, st));
+            if ((r = launch_chain_links(ctx, st, ws, d_in + goff, gn, gb, block_bytes))) return r;
+            P.in = d_in + goff; P.n = gn; P.n_regions = gb * rpb;
+            P.scratch = (uint8_t *)ws.scratch.p + (size_t)g0 * rpb * slot_bytes;
+            P.meta = (RegionMeta *)ws.meta.p + (size_t)g0 * rpb;
+            P.chain = (const uint16_t *)ws.chain.p;
+            const uint32_t grid = std::min<uint32_t>(P.n_regions, (uint32_t)ctx->sm_count);
+            KL("lz4_region_chain_kernel", st, lz4_region_kernel<false, true><<<grid, ENC_CHAIN_THREADS, ENC_SMEM_CHAIN, st>>>(P));
+        }
     } else {
         const uint32_t grid = std::min<uint32_t>(nreg, 2u * (uint32_t)ctx->sm_count);
         KL("lz4_region_kernel", st, lz4_region_kernel<false, false><<<grid, ENC_THREADS, ENC_SMEM, st>>>(P));
@@ -379,6 +425,7 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
     if ((r = ensure(ctx, ws.plan, (size_t)nb * sizeof(BlockPlan)))) return r;
     if ((r = ensure(ctx, ws.lens, (size_t)nb * 4))) return r;
     if ((r = ensure(ctx, ws.off, (size_t)nb * 8))) return r;
+    if (depth > 0 && (r = ensure(ctx, ws.chain, (size_t)G * block_bytes * 2))) return r;
     if (!ctx->region_attr_set) {
         CK(cudaFuncSetAttribute(lz4_region_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
         CK(cudaFuncSetAttribute(lz4_region_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_SMEM));
@@ -406,6 +453,8 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
         P.block_bytes = block_bytes;
         P.reproducible = ctx->repro_call;
         if (P.depth > 0) {
+            if ((r = launch_chain_links(ctx, st, ws, d_in + goff, gn, gb, block_bytes))) return r;
+            P.chain = (const uint16_t *)ws.chain.p;
             const uint32_t grid = std::min<uint32_t>(nreg, (uint32_t)ctx->sm_count);
             KL("lz4_region_chain_kernel", st, lz4_region_kernel<true, true><<<grid, ENC_CHAIN_THREADS, ENC_SMEM_CHAIN, st>>>(P));
         } else {
@@ -701,7 +750,7 @@ void fourmc_ctx_destroy(fourmc_ctx *ctx)
     cudaDeviceSynchronize();
     for (int i = 0; i < FM_PIPE_MAX; i++) {
         EncWs &e = ctx->enc[i];
-        release(e.scratch); release(e.meta); release(e.plan); release(e.lens); release(e.off); release(e.misc); release(e.zout); release(e.zrout);
+        release(e.scratch); release(e.meta); release(e.plan); release(e.lens); release(e.off); release(e.misc); release(e.zout); release(e.zrout); release(e.chain);
         DecWs &d = ctx->dec[i];
         release(d.desc); release(d.xxh); release(d.status); release(d.tokmap); release(d.chunkop);
         release(d.result); release(d.info); release(d.tables); release(d.outsize); release(d.final_); release(d.zwork); release(d.zlane);

@@ -45,19 +45,28 @@ constexpr int ENC_MAXREC = ENC_SLICE / 4 + 1;    // inner records of one slice
 constexpr int ENC_PAD = 64;
 constexpr int ENC_STAGE = 48 * 1024;             // output staging: the (dead) hash table + 16 KiB
 constexpr size_t ENC_SMEM = ENC_REGION + ENC_PAD + ENC_STAGE;
-// chain parse (levels 2..4): u16 prev[65536] (previous position with the same hash) + u16 head[1 << 14]
-constexpr int ENC_STAGE_CHAIN = 2 * ENC_REGION + (2 << 14);
-// Chain parse geometry: the 64 KiB shared-memory window holds 32 KiB of LOOK-BACK (the block's previous
-// bytes, searchable but not parsed) + a 32 KiB region of new bytes, so every position sees at least 32 KiB
-// of history (log text, depth 16: ratio 2.29 without the look-back, 2.49 with it).  128 regions per block.
+// Chain parse (levels 2..4).  Geometry: the shared-memory window holds 64 KiB of LOOK-BACK (the block's previous
+// bytes, searchable but not parsed: LZ4's whole offset range, so every position sees the same sliding history the
+// reference's HC search sees, native/lz4/lz4hc.c:262-263) + a 32 KiB region of new bytes; 128 regions per block.
+// The chain links live in HBM (lz4_chain_kernel); shared memory holds the window and, per new position, the longest
+// match found (u16 offset + u8 length), which becomes the output staging area once the parse is done.
 constexpr int ENC_CHAIN_REGION = 32768;
-constexpr int ENC_CHAIN_LOOKBACK = ENC_REGION - ENC_CHAIN_REGION;
-constexpr int ENC_CHAIN_THREADS = 1024;          // the chain parse is latency bound per thread: twice the threads, half the slice
-constexpr int ENC_CHAIN_SLICE = 36;              // 1024 slices of 9 words cover the region
+constexpr int ENC_CHAIN_LOOKBACK = 65536;
+constexpr int ENC_CHAIN_WINDOW = ENC_CHAIN_LOOKBACK + ENC_CHAIN_REGION;
+constexpr int ENC_CHAIN_THREADS = 1024;          // the search is latency bound per thread (chain links come from L2)
+constexpr int ENC_CHAIN_SLICE = 64;              // positions per cost-optimal parse (one thread each, 512 per region)
+constexpr int ENC_CHAIN_MAXREC = ENC_CHAIN_SLICE / 4 + 1;
+constexpr int ENC_CHAIN_LENCAP = 255;            // match lengths are searched and stored up to here, longer ones are extended when taken
+constexpr int ENC_CHAIN_CREDIT = 6;              // parse cost model: 16 per output byte; a byte covered beyond the slice end is worth 6
+constexpr int ENC_CHAIN_SHORTER = 8;             // shorter lengths of a match tried by the parse
+constexpr int ENC_CHAIN_SWAPSCAN = 32;           // 4-byte windows of a new longest match inspected for a better chain
+constexpr int ENC_STAGE_CHAIN = 3 * ENC_CHAIN_REGION;
 constexpr int ENC_CHAIN_SLOT = ENC_CHAIN_REGION + 512;
 constexpr int ENC_MAX_REGIONS_PER_BLOCK = FOURMC_BLOCKSIZE / ENC_CHAIN_REGION;   // 128
 static_assert(ENC_CHAIN_THREADS * ENC_CHAIN_SLICE >= ENC_CHAIN_REGION, "chain slices must cover the region");
-constexpr size_t ENC_SMEM_CHAIN = ENC_REGION + ENC_PAD + ENC_STAGE_CHAIN;
+constexpr size_t ENC_SMEM_CHAIN = ENC_CHAIN_WINDOW + ENC_PAD + ENC_STAGE_CHAIN;
+// chain links: one warp per CHUNK of a block, 64 KiB of warm-up before it (links reach at most 65535 back)
+constexpr int ENC_LINK_HASH_BYTES = 4 << ENC_HASH_BITS;
 static_assert((sizeof(uint16_t) << ENC_HASH_BITS) <= ENC_STAGE, "the hash table lives inside the staging area");
 
 static_assert(ENC_THREADS * ENC_SLICE >= ENC_REGION, "slices must cover the region");
@@ -84,6 +93,7 @@ struct EncParams {
     uint32_t regions_per_block;
     uint32_t block_bytes;    // bytes per block: 0 = FOURMC_BLOCKSIZE (the containers); the raw codec streams cut smaller chunks
     int reproducible;        // ties between racing table stores are settled by position: the same bytes on every run
+    const uint16_t *chain;   // chain parse: per input byte of this launch, distance to the previous position with the same hash (0: none)
 };
 
 __device__ __forceinline__ uint32_t enc_hash(uint32_t v) { return (v * 2654435761u) >> (32 - ENC_HASH_BITS); }
@@ -133,6 +143,67 @@ __device__ __forceinline__ uint32_t enc_pack(int st_rel, int len, int off)
     return ((uint32_t)st_rel << 24) | ((uint32_t)len << 16) | (uint32_t)off;
 }
 
+// Chain links for levels 2..4: chain[p] = distance from position p of a block to the previous position of the
+// same block with the same 4-byte hash, 0 when there is none within 65535 (what the reference keeps in its
+// chainTable, native/lz4/lz4hc.c:120-141; here for every position of the block at once, 2 bytes per input byte).
+// A link never reaches further than 65535 back, so a block is cut into chunks that are linked independently:
+// one warp per chunk walks 64 KiB of warm-up and then its chunk in steps of 32 positions, a table of the last
+// position per hash in shared memory (64 KiB).  Inside a step equal hashes are linked lane to lane
+// (__match_any_sync) and the highest lane becomes the head, so the links are exact and the same on every run.
+__global__ void __launch_bounds__(32) lz4_chain_kernel(const uint8_t *in, uint64_t n, uint32_t block_bytes, uint32_t chunk,
+                                                       uint32_t chunks_per_block, uint32_t n_items, uint16_t *chain)
+{
+    extern __shared__ __align__(16) uint32_t link_head[];           // 1 << ENC_HASH_BITS
+    const int lane = threadIdx.x;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t blk = item / chunks_per_block, ci = item % chunks_per_block;
+        const uint64_t blk_off = (uint64_t)blk * block_bytes;
+        if (blk_off >= n) continue;
+        const int blk_len = (int)min((uint64_t)block_bytes, n - blk_off);
+        const int c0 = (int)(ci * chunk);
+        if (c0 >= blk_len) continue;
+        const int c1 = min(c0 + (int)chunk, blk_len);
+        const int w0 = max(c0 - 65536, 0);
+        const int last = blk_len - 4;                               // last position with four bytes
+        for (int i = lane; i < (1 << ENC_HASH_BITS); i += 32) link_head[i] = 0xffffffffu;
+        __syncwarp();
+        const uint8_t *b = in + blk_off;
+        const int mis = (int)((uintptr_t)b & 3);                    // bytes are fetched as aligned words
+        const uint32_t *bw = (const uint32_t *)(b - mis);
+        const int nwords = (mis + blk_len + 3) >> 2;
+        uint16_t *out = chain + blk_off;
+        auto fetch = [&](int base) -> uint32_t {                    // lane l: word l of the ten that hold the step's 32 + 3 bytes
+            const int w = ((base + mis) >> 2) + lane;
+            if (lane >= 10 || w >= nwords) return 0u;
+            const int first = (w << 2) - mis;                       // block position of the word's first byte
+            if (first >= 0 && first + 4 <= blk_len) return __ldg(bw + w);
+            uint32_t v = 0;                                         // a word that straddles the block's ends: only its own bytes
+            for (int j = 0; j < 4; j++) if (first + j >= 0 && first + j < blk_len) v |= (uint32_t)b[first + j] << (8 * j);
+            return v;
+        };
+        uint32_t wnext = fetch(w0);
+        for (int base = w0; base < c1; base += 32) {
+            const uint32_t wcur = wnext;
+            if (base + 32 < c1) wnext = fetch(base + 32);
+            const int p = base + lane;
+            const int bi = ((base + mis) & 3) + lane;               // byte index within the ten words
+            const uint32_t lo = __shfl_sync(FM_FULL, wcur, bi >> 2), hi = __shfl_sync(FM_FULL, wcur, (bi >> 2) + 1);
+            const bool live = p <= last;
+            const uint32_t h = live ? enc_hash(__funnelshift_r(lo, hi, (bi & 3) * 8)) : 0x10000u + (uint32_t)lane;
+            const uint32_t same = __match_any_sync(FM_FULL, h);
+            const uint32_t below = same & ((1u << lane) - 1u);
+            uint32_t q = 0xffffffffu;
+            if (below) q = (uint32_t)(base + 31 - __clz(below));
+            else if (live) q = link_head[h];
+            const uint32_t dist = (uint32_t)p - q;                  // q == 0xffffffff: p + 1, never a valid link below
+            if (p >= c0 && p < c1) out[p] = (q != 0xffffffffu && dist <= 65535u) ? (uint16_t)dist : (uint16_t)0;
+            __syncwarp();
+            if (live && (same >> lane) == 1u) link_head[h] = (uint32_t)p;
+            __syncwarp();
+        }
+    }
+}
+
 // ZSEQ = false: LZ4 sequences as bytes (4mc).  ZSEQ = true: the same parse, emitted as
 // (literal length, match length, offset) arrays plus the gathered literals for the zstd entropy
 // stage (zstd_encode.cuh): slot = u16 ll[n] | u16 ml[n] | u16 off[n] | literals, n rounded up to 8;
@@ -140,20 +211,27 @@ __device__ __forceinline__ uint32_t enc_pack(int st_rel, int len, int off)
 //
 // CHAIN = false: the Fast parse (level 1), first-occurrence table.  CHAIN = true: levels 2..4
 // (LZ4 MC and HC are hash-chain searches, native/lz4/lz4mc.c:518-579,
-// native/lz4/lz4hc.c:239-447).  Every position of the region is linked to the previous position
-// with the same 4-byte hash (u16 prev[], built in ascending rounds of 128 positions by four warps);
-// a search follows `depth` links and keeps the
-// longest match; with `lazy` a match is dropped when the next position has a longer one.  The
-// slices, the stitching and the emit stages are shared with the Fast parse.  One CTA per SM
-// (224 KiB of shared memory).
+// native/lz4/lz4hc.c:239-447).  The chain -- every position linked to the previous position with the same
+// 4-byte hash, at most 65535 back -- is built for the whole block beforehand (lz4_chain_kernel, HBM, read
+// through L1 / L2 here).  Per region:
+//   search  EVERY new position looks for its longest match: up to `depth` links, and, like the reference's
+//           search (lz4hc.c:321-343), a new longest match switches the walk to the chain of that one of its
+//           4-byte windows whose previous occurrence lies furthest back (a longer match must repeat every window)
+//   parse   one thread per 64-byte slice chooses, back to front, literal or match (at its full length or up to 8
+//           bytes shorter) at every position so that the encoded size of the slice is minimal (16 per byte; bytes
+//           a match covers beyond the slice are credited 6 each) -- a cost-optimal parse instead of the
+//           reference's lazy arbitration between overlapping matches (lz4hc.c:553-788)
+//   walk    every slice follows the choices from its own start; a max-scan tells every slice what earlier slices
+//           cover; it walks again from there.  What still overlaps is trimmed by the stitching shared with the Fast parse.
+// One CTA of 1024 threads per SM (192 KiB of shared memory).
 template <bool ZSEQ, bool CHAIN>
 __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN ? 1 : 2) lz4_region_kernel(EncParams P)
 {
     constexpr int NT = CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, NW = NT / 32;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *data = smem;                                          // ENC_REGION + ENC_PAD
+    uint8_t *data = smem;                                          // window + ENC_PAD
     uint32_t *data32 = (uint32_t *)smem;
-    uint16_t *table = (uint16_t *)(smem + ENC_REGION + ENC_PAD);
+    uint16_t *table = (uint16_t *)(smem + (CHAIN ? ENC_CHAIN_WINDOW : ENC_REGION) + ENC_PAD);
     __shared__ int s_scan[NW];
     __shared__ uint32_t s_work;
     __shared__ int s_flush;
@@ -205,9 +283,9 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
         }
         for (int i = bulk + tid; i < rlen; i += NT) data[i] = gsrc[i];
         if (tid < ENC_PAD) data[rlen + tid] = 0;                   // reads past the end see zeros
-        uint16_t *prev = table, *head = table + ENC_REGION;         // CHAIN only
-        if constexpr (CHAIN) { for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += NT) ((uint32_t *)head)[i] = 0xffffffffu; }
-        else { for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += NT) ((uint32_t *)table)[i] = 0xffffffffu; }
+        uint16_t *moff = table;                                     // CHAIN only: per new position, offset and length
+        uint8_t *mlen = (uint8_t *)(table + ENC_CHAIN_REGION);      //   of the longest match found / of the parse's choice
+        if constexpr (!CHAIN) { for (int i = tid; i < (1 << ENC_HASH_BITS) / 2; i += NT) ((uint32_t *)table)[i] = 0xffffffffu; }
         if (bulk) {
             uint32_t done = 0;
             while (!done) {
@@ -224,35 +302,47 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
         // positions per thread (two word loads, three funnel shifts); within a thread and between
         // steps the lower position is stored last, within a step the order is left to the race.
         if constexpr (CHAIN) {
-            // Chain build.  All threads first store every position's hash in prev[]; then warps 0..3 walk
-            // the region in ascending rounds of 128 positions: a position is linked to the head of its
-            // bucket as of the previous round, then the round's positions become the heads (for equal
-            // hashes inside a round the highest position wins, the others stay reachable only through their
-            // own links -- 0.2 % of ratio on text, tests/native/enc_emul.cpp EMUL_BUILD=128000).
-            const int last = rlen - 4;
-            for (int p = tid; p <= last; p += NT) prev[p] = (uint16_t)enc_hash(smem_read4(data32, p));
-            __syncthreads();
-            if (tid < 128) {
-                for (int base = 0; base <= last; base += 128) {
-                    const int p = base + tid;
-                    const bool live = p <= last;
-                    uint32_t h = 0;
-                    if (live) { h = prev[p]; prev[p] = head[h]; }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (live) head[h] = (uint16_t)p;
-                    // equal hashes inside a round race: the HIGHEST position (the most recent one) is made the head,
-                    // whoever finds a lower one stores again -- the links, and the bytes, are the same on every run
-                    for (;;) {
-                        uint32_t any;
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
-                        if (!P.reproducible) break;
-                        const uint32_t lost = live && head[h] < (uint16_t)p;
-                        asm volatile("{\n\t.reg .pred pa, pq;\n\tsetp.ne.u32 pq, %1, 0;\n\tbar.red.or.pred pa, 1, 128, pq;\n\t"
-                                     "selp.u32 %0, 1, 0, pa;\n\t}" : "=r"(any) : "r"(lost) : "memory");
-                        if (!any) break;
-                        if (lost) head[h] = (uint16_t)p;
+            // ---- search: the longest match of every new position, positions dealt out round robin
+            const uint16_t *gp = P.chain + blk_off + r_off;         // gp[c]: link of window position c
+            const int nnew = rlen - lb;
+            for (int k = tid; k < nnew; k += NT) {
+                const int q = lb + k;
+                int best = 0, bo = 0;
+                if (q <= mf_limit) {
+                    const uint32_t v = smem_read4(data32, q);
+                    const int maxlen = min(match_limit - q, ENC_CHAIN_LENCAP);
+                    int c = q, kpos = 0;
+                    for (int a = 0; a < P.depth; a++) {
+                        const int dl = (int)__ldg(gp + c + kpos);
+                        if (!dl) break;
+                        c -= dl;
+                        if (c < 0 || q - c > 65535) break;
+                        if (smem_read4(data32, c) != v) continue;
+                        if (best >= 4 && data[q + best] != data[c + best]) continue;      // cannot beat the best so far
+                        int len = 4;
+                        while (len < maxlen) {
+                            const uint32_t x = smem_read4(data32, q + len) ^ smem_read4(data32, c + len);
+                            if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                            len += 4;
+                        }
+                        len = min(len, maxlen);
+                        if (len > best) {
+                            best = len; bo = q - c;
+                            if (len >= maxlen) break;
+                            if (c + len <= q) {
+                                int far = 1, kb = 0;
+                                const int ns = min(len - 3, ENC_CHAIN_SWAPSCAN);
+                                for (int j = 0; j < ns; j++) {
+                                    const int dj = (int)__ldg(gp + c + j);
+                                    if (dj > far) { far = dj; kb = j; }
+                                }
+                                if (far > 1) kpos = kb;
+                            }
+                        }
                     }
                 }
+                moff[k] = (uint16_t)bo;
+                mlen[k] = (uint8_t)(best >= P.min_match ? best : 0);
             }
             __syncthreads();
         } else {
@@ -288,46 +378,59 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
 
         // ---- parse: one slice per thread.  Inner sequences (all but the last) end inside the
         // slice and fit a packed word; the last one may be long and lives in registers.
-        uint32_t rec[ENC_MAXREC];
+        uint32_t rec[CHAIN ? ENC_CHAIN_MAXREC : ENC_MAXREC];
         int nrec = 0;
         int l_st = 0, l_len = 0, l_off = 0;                        // last sequence (l_len == 0: none)
         const int ss = CHAIN ? lb + tid * ENC_CHAIN_SLICE : tid * ENC_SLICE;
-        if (CHAIN && ss < rlen) {
+        if constexpr (CHAIN) {
+            const bool own = ss < rlen;                             // 512 of the 1024 threads own a slice
             const int se = min(ss + ENC_CHAIN_SLICE, rlen);
-            int p = ss, anchor = ss;
-            int have_p = -1, have_len = 0, have_off = 0;           // a search result carried over by the lazy step
-            auto search = [&](int q, int &bo) -> int {
-                const uint32_t v = smem_read4(data32, q);
-                const int maxlen = match_limit - q;
-                int best = 0, c = (int)prev[q];
-                for (int k = 0; k < P.depth && c != 0xffff; k++, c = (int)prev[c]) {
-                    if (smem_read4(data32, c) != v) continue;
-                    if (best >= 4 && data[q + best] != data[c + best]) continue;      // cannot beat the best so far
-                    int len = 4;
-                    while (len < maxlen) {
-                        const uint32_t x = smem_read4(data32, q + len) ^ smem_read4(data32, c + len);
-                        if (x) { len += (__ffs(x) - 1) >> 3; break; }
-                        len += 4;
+            int end1 = 0;
+            if (own) {
+                // cost-optimal choices, back to front; cost[i]: encoded size (x16) of [i, se) minus the credit for bytes beyond se
+                short cost[ENC_CHAIN_SLICE] = {};
+                auto at = [&](int i) -> int { return i >= se ? -(i - se) * ENC_CHAIN_CREDIT : (int)cost[i - ss]; };
+                for (int i = se - 1; i >= ss; i--) {
+                    int bc = 16 + at(i + 1), bn = 0;
+                    const int L = (int)mlen[i - lb];
+                    if (L) {
+                        const int cf = 16 * (3 + enc_ext_bytes(L - 4)) + at(i + L);
+                        if (cf <= bc) { bc = cf; bn = L; }
+                        const int l0 = min(L - 1, se - i);
+                        for (int l = l0; l >= P.min_match && l > l0 - ENC_CHAIN_SHORTER; l--) {
+                            const int cc = 16 * (3 + enc_ext_bytes(l - 4)) + at(i + l);
+                            if (cc < bc) { bc = cc; bn = l; }
+                        }
                     }
-                    len = min(len, maxlen);
-                    if (len > best) { best = len; bo = q - c; }
+                    cost[i - ss] = (short)bc;
+                    mlen[i - lb] = (uint8_t)bn;
                 }
-                return best;
-            };
-            while (p < se && p <= mf_limit) {
-                int off = 0, len;
-                if (have_p == p) { len = have_len; off = have_off; } else len = search(p, off);
-                if (len < P.min_match) { p++; continue; }
-                if (P.lazy && p + 1 <= mf_limit) {
-                    int off2 = 0;
-                    const int len2 = search(p + 1, off2);
-                    if (len2 > len) { have_p = p + 1; have_len = len2; have_off = off2; p++; continue; }
+                // walk 1: where do my choices end when I start at my own first byte (capped lengths not yet extended)
+                for (int p = ss; p < se;) {
+                    const int l = (int)mlen[p - lb];
+                    if (l) { p += l; end1 = p; } else p++;
                 }
-                int st = p, m = p - off;
-                while (st > anchor && m > 0 && data[st - 1] == data[m - 1]) { st--; m--; len++; }
-                if (l_len) rec[nrec++] = enc_pack(l_st - ss, l_len, l_off);
-                l_st = st; l_len = len; l_off = st - m;
-                p = st + len; anchor = p;
+            }
+            const int cov1 = cta_excl_scan<true, NW>(end1, s_scan, nullptr);
+            if (own) {
+                // walk 2: from the first byte earlier slices leave to me
+                for (int p = max(ss, cov1); p < se;) {
+                    int len = (int)mlen[p - lb];
+                    if (!len) { p++; continue; }
+                    const int off = (int)moff[p - lb];
+                    if (len == ENC_CHAIN_LENCAP) {
+                        const int maxlen = match_limit - p;
+                        while (len < maxlen) {
+                            const uint32_t x = smem_read4(data32, p + len) ^ smem_read4(data32, p + len - off);
+                            if (x) { len += (__ffs(x) - 1) >> 3; break; }
+                            len += 4;
+                        }
+                        len = min(len, maxlen);
+                    }
+                    if (l_len) rec[nrec++] = enc_pack(l_st - ss, l_len, l_off);
+                    l_st = p; l_len = len; l_off = off;
+                    p += len;
+                }
             }
         }
         if (!CHAIN && ss < rlen) {

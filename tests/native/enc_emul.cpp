@@ -18,93 +18,132 @@ inline int ext(int v) { return v < 15 ? 0 : 1 + (v - 15) / 255; }
 inline uint8_t *emit_len(uint8_t *o, int v) { while (v >= 255) { *o++ = 255; v -= 255; } *o++ = (uint8_t)v; return o; }
 
 // depth == 0: the Fast parse (first-occurrence table).  depth > 0: the chain parse of the higher
-// levels -- every position linked to the previous position with the same hash, `depth` candidates
-// per search, optional one-step lazy evaluation.
-// In the chain parse the 64 KiB window is 32 KiB of look-back (earlier bytes of the block: searched, not
-// parsed) + a 32 KiB region of new bytes; positions are relative to the window, new bytes are [lb, rlen).
-constexpr int CHAIN_REGION = 32768, CHAIN_LOOKBACK = REGION - CHAIN_REGION, CHAIN_SLICE = 36, CHAIN_THREADS = 1024;
+// levels -- every position linked to the previous position with the same hash (exact links over the whole
+// block, at most 65535 back: lz4_chain_kernel), `depth` candidates per search with the chain swap, a search at
+// every position, a cost-optimal choice per 64-byte slice and two walks (lz4_region_kernel<., true>).
+// The window is 64 KiB of look-back (earlier bytes of the block: searched, not parsed) + a 32 KiB region of new
+// bytes; positions are relative to the window, new bytes are [lb, rlen).
+constexpr int CHAIN_REGION = 32768, CHAIN_LOOKBACK = 65536, CHAIN_WINDOW = CHAIN_LOOKBACK + CHAIN_REGION, CHAIN_SLICE = 64,
+              CHAIN_THREADS = 1024, LENCAP = 255, CREDIT = 6, SHORTER = 8, SWAPSCAN = 32;
+// chain links of one block: distance to the previous position with the same hash, 0 = none within 65535
+std::vector<uint16_t> chain_links(const uint8_t *blk, uint32_t blk_len)
+{
+    std::vector<uint16_t> link(blk_len, 0);
+    std::vector<int> head(1 << HB, -1);
+    for (int p = 0; p + 4 <= (int)blk_len; p++) {
+        const uint32_t h = hsh(rd4(blk, p));
+        const int q = head[h];
+        link[p] = (q >= 0 && p - q <= 65535) ? (uint16_t)(p - q) : 0;
+        head[h] = p;
+    }
+    return link;
+}
 void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_new, int min_match, std::vector<uint8_t> &body, Meta &mt,
-            int depth = 0, int lazy = 0)
+            int depth = 0, const uint16_t *link = nullptr)
 {
     const int lb = depth > 0 ? (int)std::min<uint32_t>(CHAIN_LOOKBACK, r_new) : 0;
     const uint32_t r_off = r_new - (uint32_t)lb;
     const int rlen = lb + (int)std::min<uint32_t>(depth > 0 ? CHAIN_REGION : REGION, blk_len - r_new);
-    std::vector<uint8_t> data(REGION + PAD, 0);
+    std::vector<uint8_t> data(CHAIN_WINDOW + PAD, 0);
     memcpy(data.data(), blk + r_off, rlen);
     const int mf_limit = std::min(rlen - 1, (int)blk_len - 12 - (int)r_off);
     const int match_limit = std::min(rlen, (int)blk_len - 5 - (int)r_off);
     std::vector<uint16_t> table(1 << HB, 0xffff);
     // index: descending sweep in steps of THREADS; within a step the order is unspecified on
     // the GPU -- emulate "highest thread wins" (any order is legal)
-    for (int base = ((rlen - 1) / THREADS) * THREADS; base >= 0; base -= THREADS)
+    if (depth == 0) for (int base = ((rlen - 1) / THREADS) * THREADS; base >= 0; base -= THREADS)
         for (int t = THREADS - 1; t >= 0; t--) { int p = base + t; if (p <= rlen - 4 && (p & 1) == 0) table[hsh(rd4(data.data(), p))] = (uint16_t)p; }   // even positions only
     const int NTH = depth > 0 ? CHAIN_THREADS : THREADS;
     std::vector<std::vector<Seq>> inner(NTH);
     std::vector<Seq> last(NTH, Seq{0, 0, 0});
     const uint8_t *d = data.data();
-    std::vector<uint16_t> prev;
+    std::vector<uint16_t> moff;
+    std::vector<uint8_t> mlen;
     if (depth > 0) {
-        // chain build, ascending.  EMUL_BUILD=0 is the exact chain; R*1000+W emulates rounds of R positions
-        // with exact links only inside windows of W (the kernel: four warps, rounds of 128, W = 0)
-        prev.assign(REGION, 0xffff);
-        std::vector<uint16_t> head(1 << HB, 0xffff);
-        const char *bm = getenv("EMUL_BUILD");
-        const int mode = bm ? atoi(bm) : 128000;             // the kernel's build: rounds of 128, no links inside a round
-        if (mode == 0)
-            for (int p = 0; p <= rlen - 4; p++) { const uint32_t h = hsh(rd4(d, p)); prev[p] = head[h]; head[h] = (uint16_t)p; }
-        else {
-            // rounds of R positions: links go to the head as of the previous round; inside a round only
-            // positions within W of each other are linked exactly; the round's highest position wins the head
-            const int R = mode / 1000, W = mode % 1000;
-            for (int r0 = 0; r0 <= rlen - 4; r0 += R) {
-                const int r1 = std::min(r0 + R, rlen - 3);
-                for (int p = r0; p < r1; p++) {
-                    const uint32_t h = hsh(rd4(d, p));
-                    int pr = head[h];
-                    for (int q = p - 1; q >= std::max(r0, p - W) && q >= (p / 32) * 32; q--) if (hsh(rd4(d, q)) == h) { pr = q; break; }
-                    prev[p] = (uint16_t)pr;
+        // search: the longest match of every new position
+        const uint16_t *gp = link + r_off;
+        const int nnew = rlen - lb;
+        moff.assign(nnew, 0); mlen.assign(nnew, 0);
+        for (int k = 0; k < nnew; k++) {
+            const int q = lb + k;
+            int best = 0, bo = 0;
+            if (q <= mf_limit) {
+                const uint32_t v = rd4(d, q);
+                const int maxlen = std::min(match_limit - q, LENCAP);
+                int c = q, kpos = 0;
+                for (int a = 0; a < depth; a++) {
+                    const int dl = gp[c + kpos];
+                    if (!dl) break;
+                    c -= dl;
+                    if (c < 0 || q - c > 65535) break;
+                    if (rd4(d, c) != v) continue;
+                    if (best >= 4 && d[q + best] != d[c + best]) continue;
+                    int len = 4;
+                    while (len < maxlen && d[q + len] == d[c + len]) len++;
+                    len = std::min(len, maxlen);
+                    if (len > best) {
+                        best = len; bo = q - c;
+                        if (len >= maxlen) break;
+                        if (c + len <= q) {
+                            int far = 1, kb = 0;
+                            const int ns = std::min(len - 3, SWAPSCAN);
+                            for (int j = 0; j < ns; j++) if (gp[c + j] > far) { far = gp[c + j]; kb = j; }
+                            if (far > 1) kpos = kb;
+                        }
+                    }
                 }
-                for (int p = r0; p < r1; p++) head[hsh(rd4(d, p))] = (uint16_t)p;
             }
+            moff[k] = (uint16_t)bo; mlen[k] = (uint8_t)(best >= min_match ? best : 0);
+        }
+        // parse: cost-optimal choices per slice, back to front; walk 1
+        std::vector<int> end1(NTH, 0);
+        for (int t = 0; t < NTH; t++) {
+            const int ss = lb + t * CHAIN_SLICE;
+            if (ss >= rlen) continue;
+            const int se = std::min(ss + CHAIN_SLICE, rlen);
+            int cost[CHAIN_SLICE];
+            auto at = [&](int i) { return i >= se ? -(i - se) * CREDIT : cost[i - ss]; };
+            for (int i = se - 1; i >= ss; i--) {
+                int bc = 16 + at(i + 1), bn = 0;
+                const int L = mlen[i - lb];
+                if (L) {
+                    const int cf = 16 * (3 + ext(L - 4)) + at(i + L);
+                    if (cf <= bc) { bc = cf; bn = L; }
+                    const int l0 = std::min(L - 1, se - i);
+                    for (int l = l0; l >= min_match && l > l0 - SHORTER; l--) {
+                        const int cc = 16 * (3 + ext(l - 4)) + at(i + l);
+                        if (cc < bc) { bc = cc; bn = l; }
+                    }
+                }
+                cost[i - ss] = bc; mlen[i - lb] = (uint8_t)bn;
+            }
+            for (int p = ss; p < se;) { const int l = mlen[p - lb]; if (l) { p += l; end1[t] = p; } else p++; }
+        }
+        // walk 2 from what earlier slices leave
+        int cov1 = 0;
+        for (int t = 0; t < NTH; t++) {
+            const int ss = lb + t * CHAIN_SLICE;
+            if (ss < rlen) {
+                const int se = std::min(ss + CHAIN_SLICE, rlen);
+                for (int p = std::max(ss, cov1); p < se;) {
+                    int len = mlen[p - lb];
+                    if (!len) { p++; continue; }
+                    const int off = moff[p - lb];
+                    if (len == LENCAP) { const int maxlen = match_limit - p; while (len < maxlen && d[p + len] == d[p + len - off]) len++; }
+                    if (last[t].len) inner[t].push_back(last[t]);
+                    last[t] = Seq{p, len, off};
+                    p += len;
+                }
+            }
+            cov1 = std::max(cov1, end1[t]);
         }
     }
-    auto search = [&](int p, int &bo) -> int {
-        const uint32_t v = rd4(d, p);
-        const int maxlen = match_limit - p;
-        int best = 0, c = prev[p];
-        for (int k = 0; k < depth && c != 0xffff; k++, c = prev[c]) {
-            if (rd4(d, c) != v) continue;
-            int len = 4;
-            while (len < maxlen && d[p + len] == d[c + len]) len++;
-            len = std::min(len, maxlen);
-            if (len > best) { best = len; bo = p - c; }
-        }
-        return best;
-    };
     for (int t = 0; t < NTH; t++) {
         const int ss = depth > 0 ? lb + t * CHAIN_SLICE : t * SLICE;
         if (ss >= rlen) continue;
         const int se = std::min(ss + (depth > 0 ? CHAIN_SLICE : SLICE), rlen);
         int p = ss, anchor = ss;
-        if (depth > 0) {
-            int have_len = 0, have_off = 0, have_p = -1;          // a search result carried over by the lazy step
-            while (p < se && p <= mf_limit) {
-                int off = 0, len;
-                if (have_p == p) { len = have_len; off = have_off; } else len = search(p, off);
-                if (len < min_match) { p++; continue; }
-                if (lazy && p + 1 <= mf_limit) {
-                    int off2 = 0;
-                    const int len2 = search(p + 1, off2);
-                    if (len2 > len) { have_p = p + 1; have_len = len2; have_off = off2; p++; continue; }
-                }
-                int st = p, m = p - off;
-                while (st > anchor && m > 0 && d[st - 1] == d[m - 1]) { st--; m--; len++; }
-                if (last[t].len) inner[t].push_back(last[t]);
-                last[t] = Seq{st, len, st - m};
-                p = st + len; anchor = p;
-            }
-            continue;
-        }
+        if (depth > 0) continue;                                 // parsed above
         while (p < se && p <= mf_limit) {
             const uint32_t v = rd4(d, p);
             const int c = table[hsh(v)];
@@ -171,19 +210,21 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_new, int min_match,
 
 // Compresses one block (n <= 4 MiB) the way the kernels do.  Returns the LZ4 payload size written
 // to dst (capacity must be >= n + n/255 + 64), never "stored".
-static int emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth, int lazy);
-extern "C" int enc_emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match) { return emul_block(src, n, dst, min_match, 0, 0); }
+static int emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth);
+extern "C" int enc_emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match) { return emul_block(src, n, dst, min_match, 0); }
 // the chain parse of levels 2..4 (capi.cu level_chain_depth / level_lazy)
-extern "C" int enc_emul_block_chain(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth, int lazy)
+extern "C" int enc_emul_block_chain(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth)
 {
-    return emul_block(src, n, dst, min_match, depth, lazy);
+    return emul_block(src, n, dst, min_match, depth);
 }
-static int emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth, int lazy)
+static int emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth)
 {
+    std::vector<uint16_t> link;
+    if (depth > 0) link = chain_links(src, (uint32_t)n);
     const int REG = depth > 0 ? CHAIN_REGION : REGION, RPB = BLOCK / REG;
     std::vector<Meta> meta(RPB, Meta{0, 0, 0, 0});
     std::vector<std::vector<uint8_t>> bodies(RPB);
-    for (int r = 0; r < RPB; r++) if ((uint32_t)r * REG < (uint32_t)n) region(src, (uint32_t)n, (uint32_t)r * REG, min_match, bodies[r], meta[r], depth, lazy);
+    for (int r = 0; r < RPB; r++) if ((uint32_t)r * REG < (uint32_t)n) region(src, (uint32_t)n, (uint32_t)r * REG, min_match, bodies[r], meta[r], depth, link.data());
     uint8_t *o = dst; uint32_t carry = 0;
     for (int r = 0; r < RPB; r++) {
         const Meta &x = meta[r];

@@ -391,7 +391,25 @@ def test_levels_2_to_4_chain_parse(ctx, ora, pkg, ref_cli, tmp_path):
                     assert out.read_bytes() == data
     for k in (0, 1):
         assert sizes[4][k] < sizes[3][k] < sizes[2][k] < sizes[1][k], sizes
-    assert len(text) / sizes[2][0] > 2.3 and len(text) / sizes[4][0] > 2.4, sizes
+    assert len(text) / sizes[2][0] > 2.45 and len(text) / sizes[3][0] > 2.6 and len(text) / sizes[4][0] > 2.65, sizes
+    # row a12's bar: High / Ultra compress at least as well as the reference's HC 4 / HC 8 (native/4mc.c:248-251)
+    import ctypes as C
+    rp = os.path.join(os.path.dirname(ref_cli), "libref4mc.so")
+    R = C.CDLL(rp)
+    R.LZ4_compress_HC.restype = C.c_int
+    R.LZ4_compress_HC.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+    dst = C.create_string_buffer(4 * MIB + 4 * MIB // 255 + 64)
+    for level, hc in ((3, 4), (4, 8)):
+        theirs = sum(12 + R.LZ4_compress_HC(text[o:o + 4 * MIB], dst, len(text[o:o + 4 * MIB]), len(dst), hc)
+                     for o in range(0, len(text), 4 * MIB))
+        assert sizes[level][0] <= theirs + 64, (level, len(text) / sizes[level][0], len(text) / theirs)
+    # the chain links are exact, so the bytes are the same on every run and however the blocks are grouped
+    whole = ctx.compress_4mc(text, 3)
+    os.environ["FOURMC_CHAIN_GROUP"] = "1"
+    try:
+        assert ctx.compress_4mc(text, 3) == whole
+    finally:
+        del os.environ["FOURMC_CHAIN_GROUP"]
     # per-block calls: LZ4_compressMC / LZ4_compressHC2 / ZSTD_compress(level) of the JNI natives
     blk = text[:4 * MIB]
     for level in (2, 3, 4):
