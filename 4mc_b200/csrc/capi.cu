@@ -294,7 +294,7 @@ uint32_t chain_group_blocks(uint32_t nb)
 int launch_chain_links(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, const uint8_t *d_in, size_t gn, uint32_t gb, uint32_t block_bytes)
 {
     if (!ctx->chain_attr_set) {
-        CK(cudaFuncSetAttribute(lz4_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_LINK_HASH_BYTES));
+        CK(cudaFuncSetAttribute(lz4_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ENC_LINK_SMEM));
         ctx->chain_attr_set = true;
     }
     // chunk size: enough warps to fill the GPU three times over when the group is small, little warm-up overhead when it is large
@@ -304,7 +304,7 @@ int launch_chain_links(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, const uint8_
     const uint32_t cpb = (block_bytes + chunk - 1) / chunk;
     const uint32_t items = gb * cpb;
     const uint32_t grid = std::min<uint32_t>(items, 3u * (uint32_t)ctx->sm_count);
-    KL("lz4_chain_kernel", st, lz4_chain_kernel<<<grid, 32, ENC_LINK_HASH_BYTES, st>>>(d_in, gn, block_bytes, chunk, cpb, items,
+    KL("lz4_chain_kernel", st, lz4_chain_kernel<<<grid, 32, ENC_LINK_SMEM, st>>>(d_in, gn, block_bytes, chunk, cpb, items,
                                                                                        (uint16_t *)ws.chain.p));
     return FOURMC_OK;
 }

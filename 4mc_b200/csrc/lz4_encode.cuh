@@ -59,14 +59,16 @@ constexpr int ENC_CHAIN_MAXREC = ENC_CHAIN_SLICE / 4 + 1;
 constexpr int ENC_CHAIN_LENCAP = 255;            // match lengths are searched and stored up to here, longer ones are extended when taken
 constexpr int ENC_CHAIN_CREDIT = 6;              // parse cost model: 16 per output byte; a byte covered beyond the slice end is worth 6
 constexpr int ENC_CHAIN_SHORTER = 8;             // shorter lengths of a match tried by the parse
-constexpr int ENC_CHAIN_SWAPSCAN = 32;           // 4-byte windows of a new longest match inspected for a better chain
+constexpr int ENC_CHAIN_SWAPSCAN = 16;           // 4-byte windows of a new longest match inspected for a better chain
 constexpr int ENC_STAGE_CHAIN = 3 * ENC_CHAIN_REGION;
 constexpr int ENC_CHAIN_SLOT = ENC_CHAIN_REGION + 512;
 constexpr int ENC_MAX_REGIONS_PER_BLOCK = FOURMC_BLOCKSIZE / ENC_CHAIN_REGION;   // 128
 static_assert(ENC_CHAIN_THREADS * ENC_CHAIN_SLICE >= ENC_CHAIN_REGION, "chain slices must cover the region");
 constexpr size_t ENC_SMEM_CHAIN = ENC_CHAIN_WINDOW + ENC_PAD + ENC_STAGE_CHAIN;
 // chain links: one warp per CHUNK of a block, 64 KiB of warm-up before it (links reach at most 65535 back)
-constexpr int ENC_LINK_HASH_BYTES = 4 << ENC_HASH_BITS;
+constexpr int ENC_LINK_PIECE = 512;              // positions per staged piece of lz4_chain_kernel
+constexpr int ENC_LINK_STAGE_BYTES = ENC_LINK_PIECE + 32;
+constexpr int ENC_LINK_SMEM = (4 << ENC_HASH_BITS) + 2 * ENC_LINK_STAGE_BYTES;
 static_assert((sizeof(uint16_t) << ENC_HASH_BITS) <= ENC_STAGE, "the hash table lives inside the staging area");
 
 static_assert(ENC_THREADS * ENC_SLICE >= ENC_REGION, "slices must cover the region");
@@ -148,13 +150,16 @@ __device__ __forceinline__ uint32_t enc_pack(int st_rel, int len, int off)
 // chainTable, native/lz4/lz4hc.c:120-141; here for every position of the block at once, 2 bytes per input byte).
 // A link never reaches further than 65535 back, so a block is cut into chunks that are linked independently:
 // one warp per chunk walks 64 KiB of warm-up and then its chunk in steps of 32 positions, a table of the last
-// position per hash in shared memory (64 KiB).  Inside a step equal hashes are linked lane to lane
-// (__match_any_sync) and the highest lane becomes the head, so the links are exact and the same on every run.
+// position per hash in shared memory (64 KiB).  Equal hashes inside a step are detected by reading the table back
+// after the step's stores; only then are they linked lane to lane (__match_any_sync) and the highest lane made the
+// head, so the links are exact and the same on every run.
 __global__ void __launch_bounds__(32) lz4_chain_kernel(const uint8_t *in, uint64_t n, uint32_t block_bytes, uint32_t chunk,
                                                        uint32_t chunks_per_block, uint32_t n_items, uint16_t *chain)
 {
-    extern __shared__ __align__(16) uint32_t link_head[];           // 1 << ENC_HASH_BITS
+    extern __shared__ __align__(16) uint32_t link_head[];           // 1 << ENC_HASH_BITS, then two staging buffers
+    uint8_t *stage = (uint8_t *)(link_head + (1 << ENC_HASH_BITS)); // 2 x ENC_LINK_STAGE_BYTES
     const int lane = threadIdx.x;
+    const uint8_t *in_end = in + n;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const uint32_t blk = item / chunks_per_block, ci = item % chunks_per_block;
         const uint64_t blk_off = (uint64_t)blk * block_bytes;
@@ -166,41 +171,62 @@ __global__ void __launch_bounds__(32) lz4_chain_kernel(const uint8_t *in, uint64
         const int w0 = max(c0 - 65536, 0);
         const int last = blk_len - 4;                               // last position with four bytes
         for (int i = lane; i < (1 << ENC_HASH_BITS); i += 32) link_head[i] = 0xffffffffu;
-        __syncwarp();
         const uint8_t *b = in + blk_off;
-        const int mis = (int)((uintptr_t)b & 3);                    // bytes are fetched as aligned words
-        const uint32_t *bw = (const uint32_t *)(b - mis);
-        const int nwords = (mis + blk_len + 3) >> 2;
         uint16_t *out = chain + blk_off;
-        auto fetch = [&](int base) -> uint32_t {                    // lane l: word l of the ten that hold the step's 32 + 3 bytes
-            const int w = ((base + mis) >> 2) + lane;
-            if (lane >= 10 || w >= nwords) return 0u;
-            const int first = (w << 2) - mis;                       // block position of the word's first byte
-            if (first >= 0 && first + 4 <= blk_len) return __ldg(bw + w);
-            uint32_t v = 0;                                         // a word that straddles the block's ends: only its own bytes
-            for (int j = 0; j < 4; j++) if (first + j >= 0 && first + j < blk_len) v |= (uint32_t)b[first + j] << (8 * j);
-            return v;
+        // The bytes travel in pieces of 512 positions (16 steps): 34 aligned 16-byte loads per piece, requested one
+        // piece ahead and parked in shared memory, so that no step waits for HBM.
+        const uint8_t *ab = (const uint8_t *)((uintptr_t)(b + w0) & ~(uintptr_t)15);
+        const int m16 = (int)((b + w0) - ab);
+        auto fetch = [&](const uint8_t *a) -> uint4 {               // 16 bytes at a (aligned); bytes outside the input read as 0
+            if (a >= in && a + 16 <= in_end) return ldg_nc_v4((const uint4 *)a);
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            for (int j = 0; j < 16; j++) if (a + j >= in && a + j < in_end) w[j >> 2] |= (uint32_t)a[j] << (8 * (j & 3));
+            return make_uint4(w[0], w[1], w[2], w[3]);
         };
-        uint32_t wnext = fetch(w0);
-        for (int base = w0; base < c1; base += 32) {
-            const uint32_t wcur = wnext;
-            if (base + 32 < c1) wnext = fetch(base + 32);
-            const int p = base + lane;
-            const int bi = ((base + mis) & 3) + lane;               // byte index within the ten words
-            const uint32_t lo = __shfl_sync(FM_FULL, wcur, bi >> 2), hi = __shfl_sync(FM_FULL, wcur, (bi >> 2) + 1);
-            const bool live = p <= last;
-            const uint32_t h = live ? enc_hash(__funnelshift_r(lo, hi, (bi & 3) * 8)) : 0x10000u + (uint32_t)lane;
-            const uint32_t same = __match_any_sync(FM_FULL, h);
-            const uint32_t below = same & ((1u << lane) - 1u);
-            uint32_t q = 0xffffffffu;
-            if (below) q = (uint32_t)(base + 31 - __clz(below));
-            else if (live) q = link_head[h];
-            const uint32_t dist = (uint32_t)p - q;                  // q == 0xffffffff: p + 1, never a valid link below
-            if (p >= c0 && p < c1) out[p] = (q != 0xffffffffu && dist <= 65535u) ? (uint16_t)dist : (uint16_t)0;
+        const int n_pieces = (c1 - w0 + ENC_LINK_PIECE - 1) / ENC_LINK_PIECE;
+        uint4 r0 = fetch(ab + 16 * lane), r1 = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < 2) r1 = fetch(ab + 16 * (32 + lane));
+        for (int t = 0; t < n_pieces; t++) {
+            uint8_t *sb = stage + (t & 1) * ENC_LINK_STAGE_BYTES;
+            ((uint4 *)sb)[lane] = r0;
+            if (lane < 2) ((uint4 *)sb)[32 + lane] = r1;
             __syncwarp();
-            if (live && (same >> lane) == 1u) link_head[h] = (uint32_t)p;
-            __syncwarp();
+            if (t + 1 < n_pieces) {
+                const uint8_t *na = ab + (size_t)(t + 1) * ENC_LINK_PIECE;
+                r0 = fetch(na + 16 * lane);
+                if (lane < 2) r1 = fetch(na + 16 * (32 + lane));
+            }
+            const uint32_t *sw = (const uint32_t *)sb;
+            const int pbase = w0 + t * ENC_LINK_PIECE;
+#pragma unroll 4
+            for (int sidx = 0; sidx < ENC_LINK_PIECE / 32; sidx++) {
+                const int base = pbase + 32 * sidx;
+                if (base >= c1) break;
+                const int p = base + lane;
+                const int bo = m16 + 32 * sidx + lane;              // byte offset within the piece
+                const bool live = p <= last;
+                const uint32_t v = __funnelshift_r(sw[bo >> 2], sw[(bo >> 2) + 1], (bo & 3) * 8);
+                const uint32_t h = live ? enc_hash(v) : 0x10000u + (uint32_t)lane;
+                uint32_t q = live ? link_head[h] : 0xffffffffu;
+                __syncwarp();
+                if (live) link_head[h] = (uint32_t)p;               // equal hashes inside the step race: one of them lands
+                __syncwarp();
+                const bool lost = live && link_head[h] != (uint32_t)p;
+                if (__any_sync(FM_FULL, lost)) {
+                    // some hash occurs twice among the 32 positions (rare on text, the rule on short periods): link
+                    // lane to lane and make the highest lane the head
+                    const uint32_t same = __match_any_sync(FM_FULL, h);
+                    const uint32_t below = same & ((1u << lane) - 1u);
+                    if (below) q = (uint32_t)(base + 31 - __clz(below));
+                    __syncwarp();
+                    if (live && (same >> lane) == 1u) link_head[h] = (uint32_t)p;
+                    __syncwarp();
+                }
+                const uint32_t dist = (uint32_t)p - q;              // q == 0xffffffff: p + 1, never a valid link below
+                if (p >= c0 && p < c1) out[p] = (q != 0xffffffffu && dist <= 65535u) ? (uint16_t)dist : (uint16_t)0;
+            }
         }
+        __syncwarp();
     }
 }
 
@@ -312,11 +338,12 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
                     const uint32_t v = smem_read4(data32, q);
                     const int maxlen = min(match_limit - q, ENC_CHAIN_LENCAP);
                     int c = q, kpos = 0;
+                    int dl = (int)__ldg(gp + q);                    // the link to follow next; always requested one candidate ahead
                     for (int a = 0; a < P.depth; a++) {
-                        const int dl = (int)__ldg(gp + c + kpos);
                         if (!dl) break;
                         c -= dl;
                         if (c < 0 || q - c > 65535) break;
+                        dl = (int)__ldg(gp + c + kpos);             // travels while this candidate is evaluated
                         if (smem_read4(data32, c) != v) continue;
                         if (best >= 4 && data[q + best] != data[c + best]) continue;      // cannot beat the best so far
                         int len = 4;
@@ -330,13 +357,22 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
                             best = len; bo = q - c;
                             if (len >= maxlen) break;
                             if (c + len <= q) {
-                                int far = 1, kb = 0;
+                                // chain swap: the links of the match's first 4-byte windows, fetched as aligned pairs in one batch
                                 const int ns = min(len - 3, ENC_CHAIN_SWAPSCAN);
-                                for (int j = 0; j < ns; j++) {
-                                    const int dj = (int)__ldg(gp + c + j);
-                                    if (dj > far) { far = dj; kb = j; }
+                                const int c2 = c & ~1;               // window j sits in pair (c - c2 + j) >> 1
+                                const uint32_t *gw = (const uint32_t *)(gp + c2);
+                                uint32_t pr[ENC_CHAIN_SWAPSCAN / 2 + 1];
+#pragma unroll
+                                for (int u = 0; u < ENC_CHAIN_SWAPSCAN / 2 + 1; u++) pr[u] = 2 * u < ns + 1 ? __ldg(gw + u) : 0u;
+                                int far = 1, kb = 0;
+#pragma unroll
+                                for (int u = 0; u < ENC_CHAIN_SWAPSCAN / 2 + 1; u++) {
+                                    const int j0 = 2 * u - (c - c2), j1 = j0 + 1;
+                                    const int d0 = (int)(pr[u] & 0xffffu), d1 = (int)(pr[u] >> 16);
+                                    if (j0 >= 0 && j0 < ns && d0 > far) { far = d0; kb = j0; }
+                                    if (j1 < ns && d1 > far) { far = d1; kb = j1; }
                                 }
-                                if (far > 1) kpos = kb;
+                                if (far > 1) { kpos = kb; dl = far; }
                             }
                         }
                     }
@@ -394,11 +430,11 @@ __global__ void __launch_bounds__(CHAIN ? ENC_CHAIN_THREADS : ENC_THREADS, CHAIN
                     int bc = 16 + at(i + 1), bn = 0;
                     const int L = (int)mlen[i - lb];
                     if (L) {
-                        const int cf = 16 * (3 + enc_ext_bytes(L - 4)) + at(i + L);
+                        const int cf = 16 * (3 + (L >= 19)) + at(i + L);            // lengths <= 255: one length byte from 19 on
                         if (cf <= bc) { bc = cf; bn = L; }
                         const int l0 = min(L - 1, se - i);
                         for (int l = l0; l >= P.min_match && l > l0 - ENC_CHAIN_SHORTER; l--) {
-                            const int cc = 16 * (3 + enc_ext_bytes(l - 4)) + at(i + l);
+                            const int cc = 16 * (3 + (l >= 19)) + at(i + l);
                             if (cc < bc) { bc = cc; bn = l; }
                         }
                     }

@@ -24,7 +24,7 @@ inline uint8_t *emit_len(uint8_t *o, int v) { while (v >= 255) { *o++ = 255; v -
 // The window is 64 KiB of look-back (earlier bytes of the block: searched, not parsed) + a 32 KiB region of new
 // bytes; positions are relative to the window, new bytes are [lb, rlen).
 constexpr int CHAIN_REGION = 32768, CHAIN_LOOKBACK = 65536, CHAIN_WINDOW = CHAIN_LOOKBACK + CHAIN_REGION, CHAIN_SLICE = 64,
-              CHAIN_THREADS = 1024, LENCAP = 255, CREDIT = 6, SHORTER = 8, SWAPSCAN = 32;
+              CHAIN_THREADS = 1024, LENCAP = 255, CREDIT = 6, SHORTER = 8, SWAPSCAN = 16;
 // chain links of one block: distance to the previous position with the same hash, 0 = none within 65535
 std::vector<uint16_t> chain_links(const uint8_t *blk, uint32_t blk_len)
 {

@@ -28,6 +28,7 @@ int main(int argc, char **argv)
     const int SWAPCAP = getenv("SWAPCAP") ? atoi(getenv("SWAPCAP")) : 1 << 30;
     std::vector<int> DEPTHS; { const char *e = getenv("DEPTHS"); if (!e) e = "16,64"; for (const char *q = e; *q;) { DEPTHS.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q) q++; } }
     const int TRUNC = getenv("TRUNC") ? atoi(getenv("TRUNC")) : 1 << 30;
+    const int NICE = getenv("NICE") ? atoi(getenv("NICE")) : 1 << 30;
     const int SWAP = getenv("SWAP") ? atoi(getenv("SWAP")) : 1;
     for (int HB : {14}) {
         std::vector<uint16_t> prev(n, 0);
@@ -60,6 +61,7 @@ int main(int argc, char **argv)
                     while (len < maxlen && d[p + len] == d[c + len]) len++;
                     if (len > bl) {
                         bl = len; bo = p - c;
+                        if (len >= NICE) break;
                         if (SWAP && c + len <= p) {
                             // chain swap: a longer match must also continue every 4-byte window of this one, so
                             // follow the chain of the window whose previous occurrence lies furthest back
