@@ -29,13 +29,16 @@ int main(int argc, char **argv)
     std::vector<int> DEPTHS; { const char *e = getenv("DEPTHS"); if (!e) e = "16,64"; for (const char *q = e; *q;) { DEPTHS.push_back(atoi(q)); while (*q && *q != ',') q++; if (*q) q++; } }
     const int TRUNC = getenv("TRUNC") ? atoi(getenv("TRUNC")) : 1 << 30;
     const int NICE = getenv("NICE") ? atoi(getenv("NICE")) : 1 << 30;
+    const int HLEN = getenv("HLEN") ? atoi(getenv("HLEN")) : 4;
     const int SWAP = getenv("SWAP") ? atoi(getenv("SWAP")) : 1;
     for (int HB : {14}) {
         std::vector<uint16_t> prev(n, 0);
         {
             std::vector<int> head(1 << HB, -1);
             for (int p = 0; p + 4 <= n; p++) {
-                const uint32_t h = (rd4(d, p) * 2654435761u) >> (32 - HB);
+                uint32_t h;
+                if (HLEN == 4) h = (rd4(d, p) * 2654435761u) >> (32 - HB);
+                else { uint64_t v8 = 0; memcpy(&v8, d + p, p + 8 <= n ? 8 : n - p); h = (uint32_t)(((v8 << (64 - 8 * HLEN)) * 0x9E3779B185EBCA87ull) >> (64 - HB)); }
                 const int q = head[h];
                 prev[p] = (q >= 0 && p - q <= 65535) ? (uint16_t)(p - q) : 0;
                 head[h] = p;
