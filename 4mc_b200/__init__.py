@@ -138,7 +138,11 @@ class Context:
             lib().fourmc_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except TypeError:       # interpreter shutdown: the module globals are already gone, the process frees the rest
+            pass
 
     @property
     def handle(self):
