@@ -419,6 +419,20 @@ def test_levels_2_to_4_chain_parse(ctx, ora, pkg, ref_cli, tmp_path):
         assert ctx.zstd_decompress(f, len(blk)) == (len(blk), blk)
 
 
+@pytest.mark.parametrize("n", [1, 12, 13, 4095, 65535, 65537, 98305, 131071, 4 * MIB - 1, 4 * MIB + 1, 5 * MIB + 77])
+def test_levels_2_to_4_ragged_sizes(ctx, ora, pkg, n):
+    """The chain kernels at sizes around their own boundaries (the 32-position steps and 512-position pieces of the link
+    kernel, 64 KiB of warm-up, the 32 KiB regions, the block end rules): every stream decodes to the input, on text, on a
+    period shorter than a step (every step holds equal hashes) and on zeros (every match hits the length cap)."""
+    text = gen_logtext(pkg, n, first_page=3)
+    for data in (text, (b"abcdefg" * (n // 7 + 1))[:n], bytes(n)):
+        for level in (2, 3, 4):
+            s = ctx.compress_4mc(data, level)
+            assert ora.decompress_4mc(s, len(data)) == (len(data), data), (n, level)
+        z = ctx.compress_4mz(data, 3)
+        assert ctx.decompress_4mz(z) == data, n
+
+
 def test_generators_host_equals_device_and_round_trip(ctx, ora, pkg, ref_cli, tmp_path):
     """The JSON (configs[2]) and silesia-like mix (configs[3]) inputs: the device generator is bit-identical to
     the host one, and both containers restore them -- the mix holds incompressible blocks (stored path)."""

@@ -30,6 +30,7 @@ int main(int argc, char **argv)
     const int TRUNC = getenv("TRUNC") ? atoi(getenv("TRUNC")) : 1 << 30;
     const int NICE = getenv("NICE") ? atoi(getenv("NICE")) : 1 << 30;
     const int HLEN = getenv("HLEN") ? atoi(getenv("HLEN")) : 4;
+    const int SWAPMIN = getenv("SWAPMIN") ? atoi(getenv("SWAPMIN")) : 4;
     const int SWAP = getenv("SWAP") ? atoi(getenv("SWAP")) : 1;
     for (int HB : {14}) {
         std::vector<uint16_t> prev(n, 0);
@@ -47,7 +48,7 @@ int main(int argc, char **argv)
         for (int depth : DEPTHS) {
             // longest match at every position
             std::vector<M> best(n, M{0, 0});
-            double hops = 0, swaps = 0;
+            double hops = 0, swaps = 0, swapev = 0;
             for (int p = 0; p <= mf_limit; p++) {
                 const uint32_t v = rd4(d, p);
                 const int maxlen = match_limit - p;
@@ -65,7 +66,7 @@ int main(int argc, char **argv)
                     if (len > bl) {
                         bl = len; bo = p - c;
                         if (len >= NICE) break;
-                        if (SWAP && c + len <= p) {
+                        if (SWAP && len >= SWAPMIN && c + len <= p) { swapev++;
                             // chain swap: a longer match must also continue every 4-byte window of this one, so
                             // follow the chain of the window whose previous occurrence lies furthest back
                             int far = 1, kb = 0;
@@ -159,7 +160,7 @@ int main(int argc, char **argv)
                         }
                     }
                     cost += 1 + (n - anchor) + ext(n - anchor);
-                    printf("HB %d depth %3d slice %7d mode %d: ratio %.4f  nseq %d  hops/pos %.1f swapreads/pos %.1f\n", HB, depth, S, mode, (double)n / cost, nseq, hops / n, swaps / n);
+                    printf("HB %d depth %3d slice %7d mode %d: ratio %.4f  nseq %d  hops/pos %.1f swapreads/pos %.1f swap events/pos %.2f\n", HB, depth, S, mode, (double)n / cost, nseq, hops / n, swaps / n, swapev / n);
                 }
             }
         }
