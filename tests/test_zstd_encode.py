@@ -264,6 +264,7 @@ def test_gpu_4mz_device_calls(ctx, pkg):
         size2 = int(d_size.item())
         assert ctx.decompress_4mz(bytes(d_out[:size2].cpu().numpy())) == host
         assert ctx.decompress_4mz(ctx.compress_4mz(host)) == host
+        assert ctx.decompress_4mz(ctx.compress_4mz(host, 3)) == host      # the chain links are rebuilt per group
     finally:
         del os.environ["FOURMC_ZGROUP"]
 
