@@ -38,6 +38,45 @@ std::vector<uint16_t> chain_links(const uint8_t *blk, uint32_t blk_len)
     }
     return link;
 }
+// lz4_chain_kernel restated lane by lane: the block is cut into chunks, every chunk is linked on its own after 64 KiB of
+// warm-up, in steps of 32 positions; a step reads the heads, stores its positions (equal hashes race: here the LOWEST lane
+// lands, the opposite of what the kernel finally wants, so the repair path is always exercised), reads back, and repairs
+// the step lane to lane when some lane lost.  Must equal chain_links() for every chunk size.
+std::vector<uint16_t> chain_links_chunked(const uint8_t *blk, uint32_t blk_len, uint32_t chunk)
+{
+    std::vector<uint16_t> link(blk_len, 0xAAAA);
+    const int last = (int)blk_len - 4;
+    for (uint32_t c0u = 0; c0u < blk_len; c0u += chunk) {
+        const int c0 = (int)c0u, c1 = (int)std::min<uint32_t>(c0u + chunk, blk_len), w0 = std::max(c0 - 65536, 0);
+        std::vector<uint32_t> head(1 << HB, 0xffffffffu);
+        for (int base = w0; base < c1; base += 32) {
+            uint32_t h[32], q[32]; bool live[32];
+            for (int l = 0; l < 32; l++) {
+                const int p = base + l;
+                live[l] = p <= last;
+                h[l] = live[l] ? hsh(rd4(blk, p)) : 0x10000u + (uint32_t)l;
+                q[l] = live[l] ? head[h[l]] : 0xffffffffu;
+            }
+            for (int l = 31; l >= 0; l--) if (live[l]) head[h[l]] = (uint32_t)(base + l);      // the lowest lane lands
+            bool any_lost = false;
+            for (int l = 0; l < 32; l++) if (live[l] && head[h[l]] != (uint32_t)(base + l)) any_lost = true;
+            if (any_lost) {
+                for (int l = 0; l < 32; l++) {
+                    int below = -1, above = -1;
+                    for (int m = 0; m < 32; m++) if (h[m] == h[l]) { if (m < l) below = m; if (m > l) above = m; }
+                    if (below >= 0) q[l] = (uint32_t)(base + below);
+                    if (live[l] && above < 0) head[h[l]] = (uint32_t)(base + l);
+                }
+            }
+            for (int l = 0; l < 32; l++) {
+                const int p = base + l;
+                const uint32_t dist = (uint32_t)p - q[l];
+                if (p >= c0 && p < c1) link[p] = (q[l] != 0xffffffffu && dist <= 65535u) ? (uint16_t)dist : (uint16_t)0;
+            }
+        }
+    }
+    return link;
+}
 void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_new, int min_match, std::vector<uint8_t> &body, Meta &mt,
             int depth = 0, const uint16_t *link = nullptr)
 {
@@ -211,6 +250,13 @@ void region(const uint8_t *blk, uint32_t blk_len, uint32_t r_new, int min_match,
 // Compresses one block (n <= 4 MiB) the way the kernels do.  Returns the LZ4 payload size written
 // to dst (capacity must be >= n + n/255 + 64), never "stored".
 static int emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth);
+// 0 when the chunked, step-wise links (lz4_chain_kernel) equal the sequential ones; else 1 + the first differing position
+extern "C" long long enc_emul_chain_links_check(const uint8_t *src, int n, int chunk)
+{
+    const std::vector<uint16_t> a = chain_links(src, (uint32_t)n), b = chain_links_chunked(src, (uint32_t)n, (uint32_t)chunk);
+    for (int i = 0; i < n; i++) if (a[i] != b[i]) return 1 + i;
+    return 0;
+}
 extern "C" int enc_emul_block(const uint8_t *src, int n, uint8_t *dst, int min_match) { return emul_block(src, n, dst, min_match, 0); }
 // the chain parse of levels 2..4 (capi.cu level_chain_depth / level_lazy)
 extern "C" int enc_emul_block_chain(const uint8_t *src, int n, uint8_t *dst, int min_match, int depth)

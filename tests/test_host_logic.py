@@ -98,6 +98,21 @@ def test_chain_parse_algorithm_roundtrip(emul, ora, pkg, n):
             assert n / sizes[0] > 2.5 and n / sizes[1] > 2.66 and n / sizes[2] > 2.69
 
 
+def test_chain_links_chunked_equal_sequential(emul, pkg):
+    """lz4_chain_kernel's scheme (chunks with 64 KiB of warm-up, steps of 32 positions, read-back + lane-to-lane repair
+    of equal hashes inside a step) gives exactly the sequential links, whatever the chunk size."""
+    import random
+    emul.enc_emul_chain_links_check.restype = C.c_longlong
+    emul.enc_emul_chain_links_check.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    text = gen_logtext(pkg, 1 << 20)
+    rng = random.Random(3)
+    cases = [text, text[:300001], (b"abcdefg" * 60000)[:400003], bytes(200000), rng.randbytes(150000),
+             b"".join(bytes([rng.getrandbits(8)]) * rng.choice([1, 2, 3, 33, 70]) for _ in range(20000)), b"abc", b""]
+    for data in cases:
+        for chunk in (1 << 16, 1 << 18, 1 << 20):
+            assert emul.enc_emul_chain_links_check(data, len(data), chunk) == 0, (len(data), chunk)
+
+
 def test_chain_parse_reaches_the_reference_ratios(emul, ref, pkg):
     """Row a12's bar: levels 3 / 4 (32 / 128 candidates) compress the bench inputs at least as well as the
     reference's LZ4_compress_HC at its levels 4 / 8 (native/4mc.c:248-251 -> native/lz4/lz4hc.c), level 2 better
