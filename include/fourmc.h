@@ -81,7 +81,9 @@ int fourmc_lz4_compress_bound(int n);
  * Returns the compressed size (> 0), 0 when it does not fit in dst_capacity (the caller then
  * stores the block raw, native/4mc.c:318-329), or a negative FOURMC_E_*.
  * The bytes are a valid LZ4 block but not the reference's bytes.  level: 1 fast (first-occurrence
- * table, greedy) .. 2 medium / 3 high / 4 ultra (hash chains, 4 / 16 / 64 candidates, lazy). */
+ * table, greedy) .. 2 medium / 3 high / 4 ultra (LZ4_compressMC / LZ4_compressHC at 4 / 8, native/4mc.c:243-253: exact
+ * hash chains over the sliding 64 KiB history, 4 / 32 / 128 candidates, cost-optimal parse; ratios at or above the
+ * reference's; 2 bytes of device scratch per input byte). */
 int fourmc_lz4_compress(fourmc_ctx *ctx, int level, const void *src, int src_size,
                         void *dst, int dst_capacity);
 
