@@ -349,7 +349,7 @@ int enc_span(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const uint8
     P.work_counter = (uint32_t *)ws.misc.p;
     P.min_match = level_min_match(level);
     P.slot_bytes = slot_bytes;
-    P.depth = depth; P.lazy = depth > 0;
+    P.depth = depth;
     P.region_bytes = region_bytes; P.regions_per_block = rpb;
     P.block_bytes = block_bytes;
     P.reproducible = ctx->repro_call;
@@ -448,7 +448,7 @@ int enc_span_zstd(fourmc_ctx *ctx, cudaStream_t st, EncWs &ws, int level, const 
         P.work_counter = (uint32_t *)misc;
         P.min_match = level_min_match(level);
         P.slot_bytes = fmz::ze_in_slot(region_bytes);
-        P.depth = depth; P.lazy = depth > 0;
+        P.depth = depth;
         P.region_bytes = region_bytes; P.regions_per_block = rpb;
         P.block_bytes = block_bytes;
         P.reproducible = ctx->repro_call;

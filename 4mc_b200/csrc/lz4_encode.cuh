@@ -90,7 +90,6 @@ struct EncParams {
     int min_match;           // >= 4
     uint32_t slot_bytes;     // scratch bytes per region (ENC_SLOT; fmz::ZE_IN_SLOT for sequence output)
     int depth;               // chain parse: candidates tried per search (levels 2..4); unused by the Fast parse
-    int lazy;                // chain parse: one-step lazy evaluation
     uint32_t region_bytes;   // new bytes per region: ENC_REGION (Fast) or ENC_CHAIN_REGION (chain)
     uint32_t regions_per_block;
     uint32_t block_bytes;    // bytes per block: 0 = FOURMC_BLOCKSIZE (the containers); the raw codec streams cut smaller chunks
