@@ -15,3 +15,5 @@ python tools/asan_oracle_cases.py
 python tools/asan_product_cases.py
 g++ $F -std=c++17 -o $D/zenc_emul_asan.so tests/native/zenc_emul.cpp
 python tools/asan_encoder_cases.py
+g++ $F -std=c++17 -D_GLIBCXX_SANITIZE_VECTOR -o $D/enc_emul_asan.so tests/native/enc_emul.cpp
+python tools/asan_lz4_encoder_cases.py
